@@ -1,0 +1,139 @@
+"""CPU oracle for the ToMe bipartite soft-matching merge -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Restates /root/reference/src/tome/merge.py:18-97 (bipartite_soft_matching), :210-225 (merge_wavg),
+:228-241 (merge_source) and the 23-step schedule driven by src/tome/patch/timm.py:35-65,
+src/tome/utils.py:94-97 and scripts/extract_ToMe/extract_tome14.py:162 (r=[25]*23, class token
+protected).  Index outputs are explicit arrays instead of closures.
+
+Parity pin: tests/golden/tome_*.npz written by oracle/make_golden.py from the real merge.py
+(loaded by file path) -- the reference holds no golden vectors of its own ("parity unpinned"
+by upstream tests; pinned here against reference outputs generated in-container).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Tuple
+
+import torch
+
+Tensor = torch.Tensor
+
+
+def clamp_r(t: int, r: int, class_token: bool = True, distill_token: bool = False) -> int:
+    """merge.py:36-44: at most half of the unprotected tokens can be removed."""
+    prot = int(class_token) + int(distill_token)
+    return max(0, min(r, (t - prot) // 2))
+
+
+def match(metric: Tensor, r: int, class_token: bool = True, distill_token: bool = False):
+    """metric [N,t,C] -> (unm_idx [N,ta-r], src_idx [N,r], dst_idx [N,r], node_max, node_idx) or None if r<=0.
+
+    Tokens at even positions form set A (ta = ceil(t/2)), odd positions set B (tb = floor(t/2)).
+    """
+    N, t, C = metric.shape
+    r = clamp_r(t, r, class_token, distill_token)
+    if r <= 0:
+        return None
+    m = metric / metric.norm(dim=-1, keepdim=True)                  # :50
+    a, b = m[:, 0::2, :], m[:, 1::2, :]                             # :51
+    scores = a @ b.transpose(-1, -2)                                # :52  [N,ta,tb]
+    if class_token:
+        scores[:, 0, :] = -math.inf                                 # :55
+    if distill_token:
+        scores[:, :, 0] = -math.inf                                 # :57
+    node_max, node_idx = scores.max(dim=-1)                         # :59 first max index on CPU
+    edge_idx = node_max.argsort(dim=-1, descending=True)            # :60
+    unm_idx = edge_idx[:, r:]                                       # :62
+    src_idx = edge_idx[:, :r]                                       # :63
+    dst_idx = torch.gather(node_idx, 1, src_idx)                    # :64
+    if class_token:
+        unm_idx = unm_idx.sort(dim=1).values                        # :66-68
+    return unm_idx, src_idx, dst_idx, node_max, node_idx
+
+
+def merge_apply(x: Tensor, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, mode: str = "sum") -> Tensor:
+    """merge closure (:70-80): out = [A[unm_idx], B scatter-reduced with A[src_idx] at dst_idx]."""
+    N, t, C = x.shape
+    A, Bs = x[:, 0::2, :], x[:, 1::2, :].clone()
+    unm = torch.gather(A, 1, unm_idx[..., None].expand(-1, -1, C))
+    src = torch.gather(A, 1, src_idx[..., None].expand(-1, -1, C))
+    for n in range(N):                                              # explicit scatter (include_self)
+        for k in range(src_idx.shape[1]):
+            d = int(dst_idx[n, k])
+            if mode == "sum":
+                Bs[n, d] += src[n, k]
+            elif mode == "amax":
+                Bs[n, d] = torch.maximum(Bs[n, d], src[n, k])
+            else:
+                raise ValueError(mode)
+    return torch.cat([unm, Bs], dim=1)
+
+
+def merge_apply_fast(x, unm_idx, src_idx, dst_idx, mode="sum"):
+    """Same result as merge_apply via index_add (used for the bigger cases; sum order may differ
+    in the last bit when several sources hit one destination)."""
+    N, t, C = x.shape
+    A, Bs = x[:, 0::2, :], x[:, 1::2, :].clone()
+    unm = torch.gather(A, 1, unm_idx[..., None].expand(-1, -1, C))
+    src = torch.gather(A, 1, src_idx[..., None].expand(-1, -1, C))
+    Bs = Bs.scatter_reduce(1, dst_idx[..., None].expand(-1, -1, C), src, reduce=mode)
+    return torch.cat([unm, Bs], dim=1)
+
+
+def merge_wavg(x: Tensor, size: Optional[Tensor], idx, fast: bool = True):
+    """merge.py:210-225: size-weighted mean.  size [N,t,1]."""
+    if size is None:
+        size = torch.ones_like(x[..., 0, None])
+    f = merge_apply_fast if fast else merge_apply
+    xs = f(x * size, *idx, mode="sum")
+    size = f(size, *idx, mode="sum")
+    return xs / size, size
+
+
+def group_ids_update(group: Tensor, t: int, idx) -> Tensor:
+    """Integer form of merge_source (:228-241).  group [N,T0] holds, per ORIGINAL token, its current
+    token position; after a merge step it holds the position in the merged sequence."""
+    unm_idx, src_idx, dst_idx = idx
+    N = group.shape[0]
+    ta = (t + 1) // 2
+    n_unm = unm_idx.shape[1]
+    newpos = torch.empty(N, t, dtype=torch.int64)
+    for n in range(N):
+        newpos[n, 1::2] = n_unm + torch.arange(t // 2)
+        newpos[n, 2 * unm_idx[n]] = torch.arange(n_unm)
+        newpos[n, 2 * src_idx[n]] = n_unm + dst_idx[n]
+    return torch.gather(newpos, 1, group)
+
+
+def default_schedule(t0: int = 577, r: int = 25, blocks: int = 24, steps: int = 23) -> List[int]:
+    """extract_tome14.py:162 `model.r=[25]*23`, padded with 0 to 24 blocks (tome/utils.py:94-97)."""
+    return [r] * steps + [0] * (blocks - steps)
+
+
+def standin_metric(x: Tensor) -> Tensor:
+    """the real metric (mean over heads of K inside the ViT block) is out of
+    scope, so the chain is driven by x.view(N,t,16,64).mean(2)."""
+    N, t, C = x.shape
+    return x.view(N, t, C // 64, 64).mean(2)
+
+
+def chain(x: Tensor, schedule: Optional[List[int]] = None, class_token: bool = True, fast: bool = True):
+    """Run the whole schedule.  Returns (x [N,t_end,C], size [N,t_end,1], group [N,T0], per-step idx list)."""
+    N, t0, C = x.shape
+    if schedule is None:
+        schedule = default_schedule(t0)
+    size = None
+    group = torch.arange(t0)[None, :].expand(N, t0).contiguous()
+    steps = []
+    for r in schedule:
+        t = x.shape[1]
+        res = match(standin_metric(x), r, class_token=class_token)
+        if res is None:
+            continue
+        idx = res[:3]
+        steps.append(idx)
+        group = group_ids_update(group, t, idx)
+        x, size = merge_wavg(x, size, idx, fast=fast)
+    if size is None:
+        size = torch.ones_like(x[..., 0, None])
+    return x, size, group, steps
