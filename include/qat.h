@@ -1,0 +1,264 @@
+/*
+ * qat.h -- C ABI of libqat_b200.so: the QA-TIGER batched-eval hot path on B200 (sm_100a).
+ *
+ * The reference (/root/reference, 100% Python/PyTorch) has no FFI; the boundary it offers is the
+ * set of nn.Module.forward() signatures in src/models/modules.py and src/models/net.py.  Each
+ * entry point below replaces the body of one of those forwards (file:line cited per function) and
+ * is called from the Python mirror in qa-tiger_b200/models/ through ctypes (INTEGRATION.md shows
+ * the stub a maintainer would add to the reference's own modules.py).
+ *
+ * Conventions
+ *  - plain C structs of DEVICE pointers + int sizes + a cudaStream_t passed as void*.
+ *  - the CALLER owns every buffer: inputs, outputs and the workspace (sized with
+ *    qat_workspace_bytes).  The library never allocates or frees device memory, never
+ *    synchronises the device or the stream, never changes the current device.
+ *  - every tensor is dense, row-major, in the reference's [B,T,...] order, fp32 unless noted.
+ *  - return 0 on success; otherwise a QAT_E* code, with a thread-local message in
+ *    qat_last_error().  Unsupported shapes / arch (!= sm_100) are errors, never fallbacks.
+ *  - re-entrant: no global mutable state (nn.DataParallel drives one thread per GPU).
+ */
+#ifndef QAT_H_
+#define QAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QAT_ABI_VERSION 1
+
+enum {
+  QAT_OK = 0,
+  QAT_EINVAL = 1,     /* bad argument / unsupported shape */
+  QAT_EWORKSPACE = 2, /* workspace too small */
+  QAT_ECUDA = 3,      /* CUDA runtime / driver error (message has the CUDA string) */
+  QAT_EARCH = 4       /* device is not sm_100 */
+};
+
+/* Arithmetic mode of the dense contractions (error budget in DESIGN.md). */
+enum {
+  QAT_PREC_FP32 = 0, /* fp32 FFMA on CUDA cores: the 1e-5 parity gate */
+  QAT_PREC_BF16 = 1  /* "bf16 mode": tcgen05 tensor cores, fp32 accumulate in TMEM; operands are
+                        bf16 hi+lo pairs (3 MMAs per product) on the serial chain and tf32 on the
+                        patch path; router / Gaussian / rank path stays fp32: the 1e-3 gate */
+};
+
+/* Element type of the streamed tensor of qat_gauss_reduce_fwd. */
+enum { QAT_DT_F32 = 0, QAT_DT_BF16 = 1 };
+
+/* One nn.Linear: y = x W^T + b.  `w` is the reference parameter itself ([n,k] row-major fp32);
+ * `w_hi`/`w_lo` are its bf16 split (w ~= hi + lo), required only with QAT_PREC_BF16. */
+typedef struct {
+  const float* w;
+  const void* w_hi;
+  const void* w_lo;
+  const float* bias; /* [n] or NULL */
+  int32_t n, k;
+} QatLinearW;
+
+typedef struct {
+  const float* gamma;
+  const float* beta;
+} QatLayerNormW;
+
+/* ---- P1: Projection.forward, modules.py:35-43 (net.py:120-124) ------------------------------ */
+typedef struct {
+  int32_t rows;     /* product of the leading dims */
+  int32_t prec;
+  void* stream;
+  const float* x;   /* [rows, w.k] */
+  QatLinearW w;
+  float* y;         /* [rows, w.n] */
+  int32_t relu;     /* 0/1 */
+  void* workspace;
+  size_t workspace_bytes;
+} QatLinearArgs;
+int qat_linear_fwd(const QatLinearArgs* a);
+
+/* ---- A1-A3: AVQCrossAttn.forward, modules.py:239-265 (sub_forward :194-237) ----------------- */
+typedef struct {
+  int32_t B, T, L, D, H; /* T frames, L words; D = H*64 */
+  int32_t prec;
+  void* stream;
+  const float* audio;    /* src_q [B,T,D] */
+  const float* video;    /* src_v [B,T,D] */
+  const float* words;    /* query [B,L,D] */
+  /* rows: q_qst | q_slf k_slf v_slf | q_crs k_crs v_crs  = cat(qst.in_proj[0:D], slf.in_proj, crs.in_proj) */
+  QatLinearW in_src;     /* [7D, D] */
+  QatLinearW in_words;   /* [2D, D] = qst.in_proj[D:3D] */
+  QatLinearW out_cat;    /* [D, 3D] = [Wo_qst | Wo_slf | Wo_crs], bias = sum of the three out_proj biases */
+  QatLinearW ffn1, ffn2; /* linear1, linear2 */
+  QatLayerNormW norm1, norm2;
+  float* out_audio;      /* [B,T,D] */
+  float* out_video;      /* [B,T,D] */
+  float* attw_audio;     /* optional [B,T,L] head-averaged qst_attn weights (visualize=True), else NULL; must be zeroed */
+  float* attw_video;
+  void* workspace;
+  size_t workspace_bytes;
+} QatAvqArgs;
+int qat_avq_cross_attn_fwd(const QatAvqArgs* a);
+
+/* ---- P1(patch) + S1: patch_proj (net.py:124) + PatchSelecter.forward, modules.py:656-716 ---- */
+typedef struct {
+  int32_t B, T, P, D, H, Cin; /* Cin = raw patch dim (1024) when patch_proj is fused, else ignored */
+  int32_t prec;
+  void* stream;
+  const float* patch;    /* [B,T,P,Cin] if has_proj else [B,T,P,D] */
+  const float* audio;    /* [B,T,D] */
+  const float* video;    /* [B,T,D] */
+  int32_t has_proj;
+  QatLinearW proj;       /* patch_proj.proj */
+  QatLinearW slf_in;     /* [3D,D] */
+  QatLinearW slf_out;    /* [D,D] */
+  QatLinearW crs_q;      /* crs.in_proj[0:D] */
+  QatLinearW crs_kv;     /* crs.in_proj[D:3D] */
+  QatLinearW crs_out;
+  QatLinearW mlp0, mlp2;
+  QatLayerNormW anorm, vnorm;
+  float* out_a;          /* [B,T,D] anorm(a) */
+  float* out_v;          /* [B,T,D] vnorm(v) */
+  int32_t chunk_frames;  /* frames (b,t pairs) per pass, 0 = library default (keeps a pass L2-resident) */
+  void* workspace;
+  size_t workspace_bytes;
+} QatPatchArgs;
+int qat_patch_select_fwd(const QatPatchArgs* a);
+
+/* ---- M2-M4 standalone: router softmax + top-K + Gaussian masks + weighted temporal reduction.
+ *      TempMoE.forward :565-578, generate_gaussian :420-471, get_output :473-534 ---------------- */
+typedef struct {
+  int32_t B, T, E, K, C;
+  int32_t dtype;           /* QAT_DT_* of `experts` */
+  float sigma;             /* 9 */
+  void* stream;
+  const void* experts;     /* experts_logits: element (t,b,e,c) at t*stride_t + b*stride_b + e*C + c */
+  int64_t stride_t, stride_b; /* reference layout [T,B,E,C]: stride_t = B*E*C, stride_b = E*C */
+  const float* router_logits; /* [B,E]  pre-softmax */
+  const float* gauss_raw;     /* [B,2E] pre tanh/sigmoid, interleaved (centre, width) per expert */
+  float* out;              /* [B,C] (pre-LayerNorm) */
+  int64_t* topk_inds;      /* optional [B,K] */
+  float* topk_probs;       /* optional [B,K] renormalised */
+  float* gauss_weight;     /* optional [B,K,T] peak-normalised */
+  int32_t t_split;         /* CTAs per sample (cluster size) 0 = auto */
+} QatGaussArgs;
+int qat_gauss_reduce_fwd(const QatGaussArgs* a);
+
+/* ---- M1-M4 (+LN): TempMoE.forward, modules.py:536-612 -------------------------------------- */
+typedef struct {
+  int32_t B, T, D, H, E, K;
+  int32_t prec;
+  float sigma;
+  void* stream;
+  const float* qst;        /* [B,D] */
+  const float* data;       /* [B,T,D] */
+  const float* sub_a;      /* optional sub_data[0] [B,T,D] */
+  const float* sub_v;      /* optional sub_data[1] [B,T,D] */
+  QatLinearW attn_q;       /* qst_attn.in_proj[0:D] */
+  QatLinearW attn_kv;      /* qst_attn.in_proj[D:3D] */
+  QatLinearW attn_out;
+  QatLinearW router_gauss; /* [3E, D] = cat(router.0, gauss_pred.0) */
+  QatLinearW w1_cat;       /* [E*D/2, D] = cat_e experts.e.0 */
+  QatLinearW w2_ext;       /* [D, E*D/2 + 64]: cols e*D/2+c = experts.e.2.weight[:,c]; col E*D/2+e = experts.e.2.bias; 0 after */
+  QatLayerNormW norm_a;    /* `norm` (single branch) or `anorm` */
+  QatLayerNormW norm_v;    /* `vnorm` (two branches) */
+  float* out_a;            /* [B,D]  (norm(main) or anorm(a)) */
+  float* out_v;            /* [B,D]  or NULL when sub_* are NULL */
+  int64_t* topk_inds;      /* optional debug/parity outputs, as in QatGaussArgs */
+  float* topk_probs;
+  float* gauss_weight;
+  void* workspace;
+  size_t workspace_bytes;
+} QatMoeArgs;
+int qat_temp_moe_fwd(const QatMoeArgs* a);
+
+/* ---- G1 (x1) : QstGrounding.forward, modules.py:304-347, on a length-2 sequence; optionally
+ *      followed by H1: head(relu(.)) net.py:141-142 ------------------------------------------ */
+typedef struct {
+  int32_t B, D, H;
+  int32_t prec;
+  void* stream;
+  const float* qst;        /* [B,D] */
+  const float* d0;         /* [B,D] first element of the data list */
+  const float* d1;         /* [B,D] second */
+  QatLinearW attn_q, attn_kv, attn_out, mlp0, mlp2;
+  QatLayerNormW norm;
+  float* out;              /* [B,D] */
+  int32_t has_head;
+  QatLinearW head;         /* [n_ans, D] */
+  float* logits;           /* [B,n_ans] when has_head */
+  void* workspace;
+  size_t workspace_bytes;
+} QatGroundArgs;
+int qat_qst_grounding_head_fwd(const QatGroundArgs* a);
+
+/* ---- T1: bipartite_soft_matching, tome/merge.py:18-97 (index form) -------------------------- */
+typedef struct {
+  int32_t N, t, C;          /* metric [N,t,C] */
+  int32_t r;                /* requested; clamped as merge.py:43-44 */
+  int32_t class_token;
+  void* stream;
+  const float* metric;
+  int32_t* unm_idx;         /* [N, ceil(t/2)-r'] */
+  int32_t* src_idx;         /* [N, r'] */
+  int32_t* dst_idx;         /* [N, r'] */
+  void* workspace;
+  size_t workspace_bytes;
+} QatTomeMatchArgs;
+int qat_tome_match(const QatTomeMatchArgs* a);
+int qat_tome_clamp_r(int t, int r, int class_token);
+
+/* ---- T2/T3: merge_wavg :210-225 and merge_source :228-241 (as group ids) --------------------- */
+enum { QAT_TOME_MODE_WAVG = 0, /* merge_wavg: x*size summed / summed size */
+       QAT_TOME_MODE_SUM = 1, QAT_TOME_MODE_MEAN = 2, QAT_TOME_MODE_AMAX = 3 /* the bare merge(x, mode) closure */ };
+typedef struct {
+  int32_t N, t, C, r;       /* r = clamped */
+  int32_t mode;             /* QAT_TOME_MODE_* */
+  void* stream;
+  const float* x;           /* [N,t,C] */
+  const float* size;        /* [N,t] or NULL (= ones); WAVG only */
+  const int32_t* unm_idx;
+  const int32_t* src_idx;
+  const int32_t* dst_idx;
+  float* x_out;             /* [N,t-r,C] */
+  float* size_out;          /* [N,t-r]; WAVG only */
+  int32_t* group;           /* optional in/out [N,T0]: current position of every original token */
+  int32_t T0;
+  void* workspace;
+  size_t workspace_bytes;
+} QatTomeMergeArgs;
+int qat_tome_merge(const QatTomeMergeArgs* a);
+
+/* ---- T0: the schedule driver tome/patch/timm.py:35-65 with the stand-in metric of SURVEY 8d --- */
+typedef struct {
+  int32_t N, t0, C;
+  int32_t n_steps;
+  const int32_t* r_list;    /* HOST pointer, n_steps entries */
+  int32_t class_token;
+  void* stream;
+  const float* x;           /* [N,t0,C] */
+  float* x_out;             /* [N,t_end,C] */
+  float* size_out;          /* [N,t_end] */
+  int32_t* group;           /* optional [N,t0] */
+  int32_t* idx_trace;       /* optional: per step unm|src|dst concatenated, see qat_tome_chain_trace_len */
+  void* workspace;
+  size_t workspace_bytes;
+} QatTomeChainArgs;
+int qat_tome_chain(const QatTomeChainArgs* a);
+int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token);
+size_t qat_tome_chain_trace_len(int N, int t0, int n_steps, const int32_t* r_list, int class_token);
+
+/* ---- bookkeeping ---------------------------------------------------------------------------- */
+enum { QAT_OP_LINEAR = 0, QAT_OP_AVQ = 1, QAT_OP_PATCH = 2, QAT_OP_MOE = 3, QAT_OP_GROUND = 4,
+       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7 };
+/* Pass the same args struct the op will be called with (pointers may be NULL). */
+size_t qat_workspace_bytes(int op, const void* args);
+const char* qat_last_error(void);
+int qat_abi_version(void);
+/* number of kernel launches issued by this thread since the last reset (bench.py's gpu_launches) */
+long long qat_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QAT_H_ */

@@ -1,0 +1,227 @@
+"""ctypes binding of include/qat.h.  There is NO fallback: if libqat_b200.so is missing or an entry
+point returns non-zero, a RuntimeError is raised ("errors, never fallbacks")."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+from typing import Dict, Optional, Tuple
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libqat_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+DT_F32, DT_BF16 = 0, 1
+OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN = range(8)
+PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16}
+
+c_f32p = C.c_void_p  # all device pointers travel as void*
+
+
+class LinearW(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p),
+                ("n", C.c_int32), ("k", C.c_int32)]
+
+
+class LayerNormW(C.Structure):
+    _fields_ = [("gamma", C.c_void_p), ("beta", C.c_void_p)]
+
+
+class LinearArgs(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("prec", C.c_int32), ("stream", C.c_void_p), ("x", C.c_void_p),
+                ("w", LinearW), ("y", C.c_void_p), ("relu", C.c_int32), ("workspace", C.c_void_p),
+                ("workspace_bytes", C.c_size_t)]
+
+
+class AvqArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32), ("D", C.c_int32), ("H", C.c_int32),
+                ("prec", C.c_int32), ("stream", C.c_void_p),
+                ("audio", C.c_void_p), ("video", C.c_void_p), ("words", C.c_void_p),
+                ("in_src", LinearW), ("in_words", LinearW), ("out_cat", LinearW), ("ffn1", LinearW), ("ffn2", LinearW),
+                ("norm1", LayerNormW), ("norm2", LayerNormW),
+                ("out_audio", C.c_void_p), ("out_video", C.c_void_p), ("attw_audio", C.c_void_p), ("attw_video", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class PatchArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("P", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("Cin", C.c_int32),
+                ("prec", C.c_int32), ("stream", C.c_void_p),
+                ("patch", C.c_void_p), ("audio", C.c_void_p), ("video", C.c_void_p),
+                ("has_proj", C.c_int32),
+                ("proj", LinearW), ("slf_in", LinearW), ("slf_out", LinearW), ("crs_q", LinearW), ("crs_kv", LinearW),
+                ("crs_out", LinearW), ("mlp0", LinearW), ("mlp2", LinearW),
+                ("anorm", LayerNormW), ("vnorm", LayerNormW),
+                ("out_a", C.c_void_p), ("out_v", C.c_void_p), ("chunk_frames", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class GaussArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("E", C.c_int32), ("K", C.c_int32), ("C", C.c_int32),
+                ("dtype", C.c_int32), ("sigma", C.c_float), ("stream", C.c_void_p),
+                ("experts", C.c_void_p), ("stride_t", C.c_int64), ("stride_b", C.c_int64),
+                ("router_logits", C.c_void_p), ("gauss_raw", C.c_void_p), ("out", C.c_void_p),
+                ("topk_inds", C.c_void_p), ("topk_probs", C.c_void_p), ("gauss_weight", C.c_void_p),
+                ("t_split", C.c_int32)]
+
+
+class MoeArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("E", C.c_int32), ("K", C.c_int32),
+                ("prec", C.c_int32), ("sigma", C.c_float), ("stream", C.c_void_p),
+                ("qst", C.c_void_p), ("data", C.c_void_p), ("sub_a", C.c_void_p), ("sub_v", C.c_void_p),
+                ("attn_q", LinearW), ("attn_kv", LinearW), ("attn_out", LinearW), ("router_gauss", LinearW),
+                ("w1_cat", LinearW), ("w2_ext", LinearW), ("norm_a", LayerNormW), ("norm_v", LayerNormW),
+                ("out_a", C.c_void_p), ("out_v", C.c_void_p),
+                ("topk_inds", C.c_void_p), ("topk_probs", C.c_void_p), ("gauss_weight", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class GroundArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("prec", C.c_int32), ("stream", C.c_void_p),
+                ("qst", C.c_void_p), ("d0", C.c_void_p), ("d1", C.c_void_p),
+                ("attn_q", LinearW), ("attn_kv", LinearW), ("attn_out", LinearW), ("mlp0", LinearW), ("mlp2", LinearW),
+                ("norm", LayerNormW), ("out", C.c_void_p), ("has_head", C.c_int32), ("head", LinearW),
+                ("logits", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class TomeMatchArgs(C.Structure):
+    _fields_ = [("N", C.c_int32), ("t", C.c_int32), ("C", C.c_int32), ("r", C.c_int32), ("class_token", C.c_int32),
+                ("stream", C.c_void_p), ("metric", C.c_void_p), ("unm_idx", C.c_void_p), ("src_idx", C.c_void_p),
+                ("dst_idx", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class TomeMergeArgs(C.Structure):
+    _fields_ = [("N", C.c_int32), ("t", C.c_int32), ("C", C.c_int32), ("r", C.c_int32), ("mode", C.c_int32), ("stream", C.c_void_p),
+                ("x", C.c_void_p), ("size", C.c_void_p), ("unm_idx", C.c_void_p), ("src_idx", C.c_void_p),
+                ("dst_idx", C.c_void_p), ("x_out", C.c_void_p), ("size_out", C.c_void_p), ("group", C.c_void_p),
+                ("T0", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class TomeChainArgs(C.Structure):
+    _fields_ = [("N", C.c_int32), ("t0", C.c_int32), ("C", C.c_int32), ("n_steps", C.c_int32),
+                ("r_list", C.POINTER(C.c_int32)), ("class_token", C.c_int32), ("stream", C.c_void_p),
+                ("x", C.c_void_p), ("x_out", C.c_void_p), ("size_out", C.c_void_p), ("group", C.c_void_p),
+                ("idx_trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+EXPORTS = {
+    "qat_linear_fwd": (C.c_int, [C.POINTER(LinearArgs)]),
+    "qat_avq_cross_attn_fwd": (C.c_int, [C.POINTER(AvqArgs)]),
+    "qat_patch_select_fwd": (C.c_int, [C.POINTER(PatchArgs)]),
+    "qat_gauss_reduce_fwd": (C.c_int, [C.POINTER(GaussArgs)]),
+    "qat_temp_moe_fwd": (C.c_int, [C.POINTER(MoeArgs)]),
+    "qat_qst_grounding_head_fwd": (C.c_int, [C.POINTER(GroundArgs)]),
+    "qat_tome_match": (C.c_int, [C.POINTER(TomeMatchArgs)]),
+    "qat_tome_clamp_r": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "qat_tome_merge": (C.c_int, [C.POINTER(TomeMergeArgs)]),
+    "qat_tome_chain": (C.c_int, [C.POINTER(TomeChainArgs)]),
+    "qat_tome_chain_t_end": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "qat_tome_chain_trace_len": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32), C.c_int]),
+    "qat_workspace_bytes": (C.c_size_t, [C.c_int, C.c_void_p]),
+    "qat_last_error": (C.c_char_p, []),
+    "qat_abi_version": (C.c_int, []),
+    "qat_launch_count": (C.c_longlong, [C.c_int]),
+}
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load libqat_b200.so (once).  Missing library => RuntimeError, never a silent fallback."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(LIB_PATH):
+                    raise RuntimeError(
+                        f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+                        "(qa-tiger_b200 has no CPU or PyTorch fallback for its CUDA path)")
+                l = C.CDLL(LIB_PATH)
+                for name, (res, args) in EXPORTS.items():
+                    fn = getattr(l, name)
+                    fn.restype, fn.argtypes = res, args
+                if l.qat_abi_version() != 1:
+                    raise RuntimeError("libqat_b200.so ABI version mismatch")
+                _lib = l
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib().qat_last_error().decode()}")
+
+
+def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda_f32(t: torch.Tensor, name: str, shape: Optional[Tuple[int, ...]] = None):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (qa-tiger_b200 has no CPU path), got {t.device}")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: expected a contiguous tensor (SURVEY 8b: the shim asserts, it does not copy)")
+    if shape is not None and tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+# ---- weights ------------------------------------------------------------------------------------
+class Lin:
+    """A prepared nn.Linear operand: fp32 weight (+ bf16 hi/lo split when prec == bf16) and bias.
+    Holds the tensors alive; `.c` is the C struct."""
+
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], prec: int):
+        w = w.detach().contiguous().float()
+        self.w = w
+        self.b = None if b is None else b.detach().contiguous().float()
+        self.hi = self.lo = None
+        if prec == PREC_BF16:
+            self.hi = w.to(torch.bfloat16)
+            self.lo = (w - self.hi.float()).to(torch.bfloat16)
+        self.c = LinearW(ptr(w), ptr(self.hi), ptr(self.lo), ptr(self.b), w.shape[0], w.shape[1])
+
+
+class LN:
+    def __init__(self, m: torch.nn.LayerNorm):
+        self.g = m.weight.detach().contiguous().float()
+        self.b = m.bias.detach().contiguous().float()
+        self.c = LayerNormW(ptr(self.g), ptr(self.b))
+
+
+def params_version(module: torch.nn.Module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=True))
+
+
+# ---- workspace ----------------------------------------------------------------------------------
+_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+
+
+def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
+    """Per (device, stream) grow-only scratch buffer owned by torch's caching allocator."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
+    buf = _ws.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = buf
+    return buf
+
+
+def run(op: int, fn_name: str, args, device: torch.device):
+    """Size the workspace from the same args struct, attach it, call the entry point."""
+    l = lib()
+    need = l.qat_workspace_bytes(op, C.addressof(args))
+    if need == 0:
+        raise RuntimeError(f"{fn_name}: workspace sizing failed: {l.qat_last_error().decode()}")
+    ws = workspace(device, need)
+    args.workspace = ws.data_ptr()
+    args.workspace_bytes = ws.numel()
+    args.stream = stream_ptr(device)
+    with torch.cuda.device(device):
+        check(getattr(l, fn_name)(C.byref(args)), fn_name)

@@ -1,0 +1,169 @@
+// Softmax(QK^T)V cores for the short sequences of the hot path: lengths 1/2/14/60/77/120,
+// head dim 64.  These are <1% of the FLOPs; they run on CUDA cores in fp32 straight out of the
+// projection GEMM outputs (strided views, no head split / transpose is ever materialised).
+// Semantics: torch MHA slow path, F.multi_head_attention_forward -- q is scaled by hd^-0.5 BEFORE the
+// dot product, softmax = exp(s - max)/sum, no masks (modules.py:217-221,338,562,688,698).
+#pragma once
+#include "qat_common.cuh"
+
+namespace qat {
+
+struct AttnP {
+  const float* q;
+  const float* k;
+  const float* v;
+  long long q_sn, q_si;  // float strides: per sequence, per query row
+  long long k_sn, k_si;  // per kv-sequence, per key row (k and v share them)
+  int k_shift, k_mod;    // kv sequence of query sequence n is (n + k_shift) % k_mod
+  Act o;                 // output, row = n*o_rn + i*o_ri, col = h*64 + d
+  long long o_rn, o_ri;
+  float* attw;           // optional [nseq, Lq, Lk] head-averaged weights (zero-initialised by the caller)
+  int nseq, H, Lq, Lk;
+  float scale;
+};
+
+constexpr int HD = 64;
+
+// ---- one CTA (4 warps) per (sequence, head); Lk <= 128 --------------------------------------------
+__global__ void __launch_bounds__(128) attn_block_kernel(AttnP p) {
+  extern __shared__ __align__(16) float smem[];
+  const int Lk = p.Lk;
+  float* Ks = smem;                   // [Lk][65]
+  float* Vs = Ks + Lk * 65;           // [Lk][64]
+  float* Ps = Vs + Lk * 64;           // [4][128]
+  const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int kn = (n + p.k_shift) % p.k_mod;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const float* kb = p.k + kn * p.k_sn + h * HD;
+  const float* vb = p.v + kn * p.k_sn + h * HD;
+  for (int f = tid; f < Lk * 16; f += 128) {
+    int r = f >> 4, c4 = f & 15;
+    float4 kv = __ldg(reinterpret_cast<const float4*>(kb + r * p.k_si) + c4);
+    float4 vv = __ldg(reinterpret_cast<const float4*>(vb + r * p.k_si) + c4);
+    float* kd = Ks + r * 65 + c4 * 4;
+    kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+    *reinterpret_cast<float4*>(Vs + r * 64 + c4 * 4) = vv;
+  }
+  __syncthreads();
+  float* Pw = Ps + w * 128;
+  const float invH = 1.f / p.H;
+  for (int i = w; i < p.Lq; i += 4) {
+    const float* qr = p.q + n * p.q_sn + i * p.q_si + h * HD;
+    float q0 = __ldg(qr + lane) * p.scale, q1 = __ldg(qr + 32 + lane) * p.scale;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
+    for (int d = 0; d < 64; ++d) {
+      float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        int j = lane + 32 * m;
+        if (j < Lk) s[m] = fmaf(qd, Ks[j * 65 + d], s[m]);
+      }
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int m = 0; m < 4; ++m)
+      if (lane + 32 * m < Lk) mx = fmaxf(mx, s[m]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      s[m] = (lane + 32 * m < Lk) ? expf(s[m] - mx) : 0.f;
+      sum += s[m];
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      int j = lane + 32 * m;
+      if (j < Lk) {
+        float pj = s[m] / sum;
+        Pw[j] = pj;
+        if (p.attw) atomicAdd(p.attw + ((long long)n * p.Lq + i) * Lk + j, pj * invH);
+      }
+    }
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f;
+    for (int j = 0; j < Lk; ++j) {
+      float pj = Pw[j];
+      o0 = fmaf(pj, Vs[j * 64 + lane], o0);
+      o1 = fmaf(pj, Vs[j * 64 + 32 + lane], o1);
+    }
+    long long row = n * p.o_rn + i * p.o_ri;
+    act_store1(p.o, row, h * HD + lane, o0);
+    act_store1(p.o, row, h * HD + 32 + lane, o1);
+  }
+}
+
+// ---- one warp per (sequence, head); Lk <= 32; a CTA carries WPB consecutive (seq, head) problems ----
+template <int WPB>
+__global__ void __launch_bounds__(32 * WPB) attn_warp_kernel(AttnP p) {
+  extern __shared__ __align__(16) float smem[];
+  const int Lk = p.Lk;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long prob = (long long)blockIdx.x * WPB + w;
+  if (prob >= (long long)p.nseq * p.H) return;
+  const int n = (int)(prob / p.H), h = (int)(prob % p.H);
+  const int kn = (n + p.k_shift) % p.k_mod;
+  float* Ks = smem + w * (Lk * (65 + 64));  // [Lk][65]
+  float* Vs = Ks + Lk * 65;                 // [Lk][64]
+  const float* kb = p.k + kn * p.k_sn + h * HD;
+  const float* vb = p.v + kn * p.k_sn + h * HD;
+  for (int f = lane; f < Lk * 16; f += 32) {
+    int r = f >> 4, c4 = f & 15;
+    float4 kv = __ldg(reinterpret_cast<const float4*>(kb + r * p.k_si) + c4);
+    float4 vv = __ldg(reinterpret_cast<const float4*>(vb + r * p.k_si) + c4);
+    float* kd = Ks + r * 65 + c4 * 4;
+    kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+    *reinterpret_cast<float4*>(Vs + r * 64 + c4 * 4) = vv;
+  }
+  __syncwarp();
+  const float invH = 1.f / p.H;
+  for (int i = 0; i < p.Lq; ++i) {
+    const float* qr = p.q + n * p.q_sn + i * p.q_si + h * HD;
+    float q0 = __ldg(qr + lane) * p.scale, q1 = __ldg(qr + 32 + lane) * p.scale;
+    float s = 0.f;
+    const int j = lane < Lk ? lane : 0;
+#pragma unroll 16
+    for (int d = 0; d < 64; ++d) {
+      float qd = __shfl_sync(0xffffffffu, d < 32 ? q0 : q1, d & 31);
+      s = fmaf(qd, Ks[j * 65 + d], s);
+    }
+    float mx = warp_max(lane < Lk ? s : -INFINITY);
+    float e = lane < Lk ? expf(s - mx) : 0.f;
+    float sum = warp_sum(e);
+    float pj = e / sum;
+    if (p.attw && lane < Lk) atomicAdd(p.attw + ((long long)n * p.Lq + i) * Lk + lane, pj * invH);
+    float o0 = 0.f, o1 = 0.f;
+    for (int jj = 0; jj < Lk; ++jj) {
+      float pb = __shfl_sync(0xffffffffu, pj, jj);
+      o0 = fmaf(pb, Vs[jj * 64 + lane], o0);
+      o1 = fmaf(pb, Vs[jj * 64 + 32 + lane], o1);
+    }
+    long long row = n * p.o_rn + i * p.o_ri;
+    act_store1(p.o, row, h * HD + lane, o0);
+    act_store1(p.o, row, h * HD + 32 + lane, o1);
+  }
+}
+
+inline int attention(Ctx& c, const AttnP& p) {
+  QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
+  QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
+  if (c.dry || p.nseq == 0) return QAT_OK;
+  if (p.Lk <= 32) {
+    constexpr int WPB = 8;
+    size_t smem = size_t(WPB) * p.Lk * (65 + 64) * 4;
+    if (smem > 48 * 1024)
+      QAT_CUDA(cudaFuncSetAttribute(attn_warp_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    long long probs = (long long)p.nseq * p.H;
+    attn_warp_kernel<WPB><<<(unsigned)((probs + WPB - 1) / WPB), 32 * WPB, smem, c.stream>>>(p);
+    return check_launch("attn_warp_kernel");
+  }
+  size_t smem = (size_t(p.Lk) * (65 + 64) + 4 * 128) * 4;
+  if (smem > 48 * 1024)
+    QAT_CUDA(cudaFuncSetAttribute(attn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  attn_block_kernel<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
+  return check_launch("attn_block_kernel");
+}
+
+}  // namespace qat

@@ -1,0 +1,296 @@
+// The question-aware Gaussian mixture of temporal experts, M2-M4 of SURVEY 8a, as ONE kernel:
+//   router softmax over E -> top-K (descending, lowest index on ties) -> renormalise
+//   centre/width from gauss_pred (tanh*margin, sigmoid) -> clamp -> Gaussian over t/(T-1)
+//   -> divide by the max over t (peak normalisation, modules.py:467-469)
+//   -> out[b] = sum_t sum_j coef[t][j] * X[t,b,j,:],  coef[t][j] = sum_{i: perm_t[i]=j} p[i] G[i][t]
+// where perm_t is the rank list of sample (b*T+t) mod B -- the `topk_inds.repeat(T,1)` batch-coupling
+// quirk of modules.py:502, reproduced on purpose.
+//
+// HBM-bound: X is read exactly once with coalesced 128-bit streaming loads (L1 no-allocate), every
+// thread keeps SLOTS independent loads in flight; the t axis of one sample is split over a thread-block
+// cluster whose partial sums meet in distributed shared memory (fixed order => bit-reproducible).
+#pragma once
+#include <cooperative_groups.h>
+
+#include "qat_common.cuh"
+
+namespace qat {
+namespace cg = cooperative_groups;
+
+struct GaussP {
+  const void* x;
+  long long st, sb;   // element strides of X over t and b; (e, c) are contiguous: e*C + c
+  const float* rl;    // [B,E]
+  const float* gr;    // [B,2E]
+  int B, T, E, K, C;
+  float sigma;
+  int per_expert;     // 0: out[b, c] summed over experts (reference get_output)
+                      // 1: out[b, e*C + c] kept per expert and out[b, E*C + e] = sum_t coef[t][e]
+                      //    (the M4 refactor: reduce the hidden activations before the 2nd expert GEMM)
+  Act out;
+  long long* topk_inds;  // optional [B,K]
+  float* topk_probs;     // optional [B,K]
+  float* gauss_weight;   // optional [B,K,T]
+};
+
+__device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
+  // torch.linspace (fp32): symmetric evaluation around the midpoint
+  if (steps == 1) return start;
+  float step = (end - start) / (float)(steps - 1);
+  return (i < steps / 2) ? start + step * (float)i : end - step * (float)(steps - 1 - i);
+}
+
+constexpr int GAUSS_MAX_E = 32;
+
+template <typename VecT, int VEC>
+__device__ __forceinline__ void fma_vec(float (&acc)[VEC], const VecT& v, float cf);
+
+template <>
+__device__ __forceinline__ void fma_vec<float4, 4>(float (&acc)[4], const float4& v, float cf) {
+  acc[0] = fmaf(cf, v.x, acc[0]);
+  acc[1] = fmaf(cf, v.y, acc[1]);
+  acc[2] = fmaf(cf, v.z, acc[2]);
+  acc[3] = fmaf(cf, v.w, acc[3]);
+}
+template <>
+__device__ __forceinline__ void fma_vec<uint4, 8>(float (&acc)[8], const uint4& v, float cf) {
+  const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float lo = __uint_as_float(u[i] << 16);          // bf16 -> fp32 is a shift
+    float hi = __uint_as_float(u[i] & 0xffff0000u);
+    acc[2 * i] = fmaf(cf, lo, acc[2 * i]);
+    acc[2 * i + 1] = fmaf(cf, hi, acc[2 * i + 1]);
+  }
+}
+
+// VecT = float4 (fp32 X) or uint4 (bf16 X); SLOTS = vectors per thread per time step.
+template <typename VecT, int VEC, int SLOTS, int NT, bool CLUSTER>
+__global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.T, E = p.E, K = p.K, C = p.C;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.x;
+  const int rank = CLUSTER ? blockIdx.y : 0;
+  const int nrank = CLUSTER ? gridDim.y : 1;
+  const int nvec = E * C / VEC;   // vectors per (b,t) row
+  const int cvec = C / VEC;       // vectors per expert
+
+  // ---- shared layout -------------------------------------------------------------------------
+  float* s_part = reinterpret_cast<float*>(smem_raw);            // [nvec*VEC] partial sums (DSMEM-visible)
+  float* s_coef = s_part + (size_t)nvec * VEC;                    // [T][E]
+  float* s_G = s_coef + T * E;                                    // [K][T]
+  float* s_p = s_G + K * T;                                       // [K]
+  float* s_c = s_p + K;                                           // [K]
+  float* s_w = s_c + K;                                           // [K]
+  int* s_idx = reinterpret_cast<int*>(s_w + K);                   // [K]
+  unsigned char* s_perm = reinterpret_cast<unsigned char*>(s_idx + K);  // [T][K]
+
+  // ---- phase 0: rank lists.  Thread t ranks sample (b*T+t)%B; the last thread ranks sample b. ----
+  for (int t = tid; t < T + 1; t += NT) {
+    const bool own = (t == T);
+    const int o = own ? b : (int)(((long long)b * T + t) % p.B);
+    float pr[GAUSS_MAX_E];
+    float mx = -INFINITY;
+    for (int e = 0; e < E; ++e) {
+      pr[e] = __ldg(p.rl + (long long)o * E + e);
+      mx = fmaxf(mx, pr[e]);
+    }
+    float sum = 0.f;
+    for (int e = 0; e < E; ++e) {
+      pr[e] = expf(pr[e] - mx);
+      sum += pr[e];
+    }
+    for (int e = 0; e < E; ++e) pr[e] = pr[e] / sum;
+    float psum = 0.f;
+    for (int i = 0; i < K; ++i) {
+      int best = 0;
+      float bv = -1.f;
+      for (int e = 0; e < E; ++e)
+        if (pr[e] > bv) { bv = pr[e]; best = e; }   // strict > keeps the lowest index on ties
+      pr[best] = -2.f;
+      if (own) {
+        s_idx[i] = best;
+        s_p[i] = bv;
+        psum += bv;
+      } else {
+        s_perm[t * K + i] = (unsigned char)best;
+      }
+    }
+    if (own) {
+      const float margin = 1.0f / (float)(E * 2);
+      for (int i = 0; i < K; ++i) {
+        const int e = s_idx[i];
+        s_p[i] = s_p[i] / psum;
+        float g0 = __ldg(p.gr + (long long)b * 2 * E + 2 * e);
+        float g1 = __ldg(p.gr + (long long)b * 2 * E + 2 * e + 1);
+        float centre = linspace_at(margin, 1.f - margin, E, e) + tanhf(g0) * margin;
+        float width = 1.f / (1.f + expf(-g1));
+        s_c[i] = fminf(fmaxf(centre, 0.f), 1.f);
+        s_w[i] = fmaxf(width, 0.09f) / p.sigma;
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 1: Gaussian masks, one warp per selected expert, peak-normalised over t ----------
+  for (int i = warp; i < K; i += NT / 32) {
+    const float c = s_c[i], w = s_w[i];
+    const float pref = 0.3989422804014327f / w;
+    const float den = 2.f * (w * w);
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) {
+      float d = linspace_at(0.f, 1.f, T, t) - c;
+      float g = pref * expf(-(d * d) / den);
+      s_G[i * T + t] = g;
+      mx = fmaxf(mx, g);
+    }
+    mx = warp_max(mx);
+    for (int t = lane; t < T; t += 32) s_G[i * T + t] = s_G[i * T + t] / mx;
+  }
+  __syncthreads();
+
+  // ---- phase 2: coef[t][j] -------------------------------------------------------------------
+  for (int t = tid; t < T; t += NT) {
+    for (int e = 0; e < E; ++e) s_coef[t * E + e] = 0.f;
+    for (int i = 0; i < K; ++i) s_coef[t * E + s_perm[t * K + i]] += s_p[i] * s_G[i * T + t];
+  }
+  if (rank == 0) {
+    if (p.topk_inds && tid < K) p.topk_inds[(long long)b * K + tid] = s_idx[tid];
+    if (p.topk_probs && tid < K) p.topk_probs[(long long)b * K + tid] = s_p[tid];
+    if (p.gauss_weight)
+      for (int f = tid; f < K * T; f += NT) p.gauss_weight[(long long)b * K * T + f] = s_G[f];
+  }
+  __syncthreads();
+
+  // ---- main loop: stream X[t, b, :, :] for my slice of t -------------------------------------
+  const int t0 = (int)((long long)T * rank / nrank), t1 = (int)((long long)T * (rank + 1) / nrank);
+  float acc[SLOTS][VEC];
+  int je[SLOTS];
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[s][v] = 0.f;
+    int f = tid + s * NT;
+    je[s] = f < nvec ? f / cvec : 0;
+  }
+  const VecT* xb = reinterpret_cast<const VecT*>(p.x) + ((long long)b * p.sb) / VEC;
+  const long long stv = p.st / VEC;
+  for (int t = t0; t < t1; ++t) {
+    const VecT* xr = xb + (long long)t * stv;
+    VecT v[SLOTS];
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      int f = tid + s * NT;
+      if (f < nvec) v[s] = ldg_stream(xr + f);
+    }
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      int f = tid + s * NT;
+      if (f < nvec) fma_vec<VecT, VEC>(acc[s], v[s], s_coef[t * E + je[s]]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < SLOTS; ++s) {
+    int f = tid + s * NT;
+    if (f < nvec) {
+#pragma unroll
+      for (int v = 0; v < VEC; ++v) s_part[(size_t)f * VEC + v] = acc[s][v];
+    }
+  }
+
+  // ---- combine the cluster's partial sums in rank order (deterministic) ----------------------
+  if (CLUSTER) {
+    cg::this_cluster().sync();
+  } else {
+    __syncthreads();
+  }
+  if (rank == 0) {
+    const int nout = p.per_expert ? E * C : C;
+    for (int o = tid; o < nout; o += NT) {
+      float sum = 0.f;
+      for (int r = 0; r < nrank; ++r) {
+        const float* part = s_part;
+        if (CLUSTER) part = cg::this_cluster().map_shared_rank(s_part, r);
+        if (p.per_expert) {
+          sum += part[o];
+        } else {
+          for (int e = 0; e < E; ++e) sum += part[e * C + o];
+        }
+      }
+      act_store1(p.out, b, o, sum);
+    }
+    if (p.per_expert) {
+      for (int e = tid; e < 64; e += NT) {
+        float sum = 0.f;
+        if (e < E)
+          for (int t = 0; t < T; ++t) sum += s_coef[t * E + e];
+        act_store1(p.out, b, E * C + e, sum);
+      }
+    }
+  }
+  if (CLUSTER) cg::this_cluster().sync();   // keep every CTA's smem alive until rank 0 has read it
+}
+
+inline size_t gauss_smem_bytes(const GaussP& p) {
+  size_t f = (size_t)p.E * p.C + (size_t)p.T * p.E + (size_t)p.K * p.T + 3 * (size_t)p.K;
+  return f * 4 + (size_t)p.K * 4 + (size_t)p.T * p.K + 16;
+}
+
+template <typename VecT, int VEC, int SLOTS, int NT>
+inline int gauss_launch(Ctx& c, const GaussP& p, int tsplit) {
+  size_t smem = gauss_smem_bytes(p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(p.B, tsplit, 1);
+  cfg.blockDim = dim3(NT, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute attr[1];
+  if (tsplit > 1) {
+    auto kern = gauss_reduce_kernel<VecT, VEC, SLOTS, NT, true>;
+    if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = tsplit;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  } else {
+    auto kern = gauss_reduce_kernel<VecT, VEC, SLOTS, NT, false>;
+    if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
+  }
+  return check_launch("gauss_reduce_kernel");
+}
+
+// dtype: QAT_DT_F32 / QAT_DT_BF16.  tsplit: CTAs per sample (cluster size), 0 = auto.
+inline int gauss_reduce(Ctx& c, const GaussP& p, int dtype, int tsplit) {
+  QAT_REQUIRE(p.E >= 1 && p.E <= GAUSS_MAX_E && p.K >= 1 && p.K <= p.E, "gauss_reduce: need 1<=K<=E<=%d (E=%d K=%d)", GAUSS_MAX_E, p.E, p.K);
+  QAT_REQUIRE(p.T >= 1 && p.T <= 4096 && p.B >= 1, "gauss_reduce: bad B/T");
+  const int VEC = dtype == QAT_DT_BF16 ? 8 : 4;
+  QAT_REQUIRE(dtype == QAT_DT_F32 || dtype == QAT_DT_BF16, "gauss_reduce: unknown dtype %d", dtype);
+  QAT_REQUIRE(p.C % VEC == 0 && p.st % VEC == 0 && p.sb % VEC == 0, "gauss_reduce: C and strides must be multiples of %d elements", VEC);
+  QAT_REQUIRE((size_t)p.E * p.C <= 16384, "gauss_reduce: E*C=%d exceeds 16384 (one CTA holds a full (b,t) row in flight)", p.E * p.C);
+  if (c.dry) return QAT_OK;
+  if (tsplit <= 0) {
+    // enough CTAs for >= 4 per SM, but never slices shorter than ~8 time steps; cluster size <= 8
+    tsplit = 1;
+    while (tsplit < 8 && (long long)p.B * tsplit < 148 * 4 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
+  }
+  QAT_REQUIRE(tsplit >= 1 && tsplit <= 8, "gauss_reduce: t_split=%d outside [1,8]", tsplit);
+  const int nvec = p.E * p.C / VEC;
+  // SLOTS*NT >= nvec
+  if (dtype == QAT_DT_F32) {
+    if (nvec <= 4 * 128) return gauss_launch<float4, 4, 4, 128>(c, p, tsplit);
+    if (nvec <= 8 * 128) return gauss_launch<float4, 4, 8, 128>(c, p, tsplit);
+    if (nvec <= 8 * 256) return gauss_launch<float4, 4, 8, 256>(c, p, tsplit);
+    return gauss_launch<float4, 4, 16, 256>(c, p, tsplit);
+  } else {
+    if (nvec <= 4 * 128) return gauss_launch<uint4, 8, 4, 128>(c, p, tsplit);
+    if (nvec <= 8 * 128) return gauss_launch<uint4, 8, 8, 128>(c, p, tsplit);
+    return gauss_launch<uint4, 8, 8, 256>(c, p, tsplit);
+  }
+}
+
+}  // namespace qat

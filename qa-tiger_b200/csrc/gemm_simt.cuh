@@ -1,0 +1,149 @@
+// fp32 FFMA GEMM on CUDA cores: C[M,N] = act(A[M,K] W[N,K]^T + bias) + res.
+// This is the QAT_PREC_FP32 path (1e-5 parity gate) and the path of the tiny fp32-only
+// contractions (router / gauss_pred / head) in every mode.
+#pragma once
+#include "qat_common.cuh"
+
+namespace qat {
+
+struct Epi {
+  const float* bias = nullptr;  // [N]
+  int relu = 0;
+  const float* res = nullptr;   // [M, ldr] added after the activation
+  int ldr = 0;
+};
+
+// Tile = (8*TY) x (8*TX), BK = 16, TY*TX threads; each thread owns two 4-row and two 4-col strips
+// (rows ty*4+i and BM/2+ty*4+i) so that every shared-memory float4 read is conflict-free.
+template <int TY, int TX>
+__global__ void __launch_bounds__(TY* TX) gemm_simt_kernel(const float* __restrict__ A, int lda,
+                                                           const float* __restrict__ W, int ldw, Epi epi, Act C,
+                                                           int M, int N, int K) {
+  constexpr int BM = 8 * TY, BN = 8 * TX, BK = 16, NT = TY * TX;
+  constexpr int PAD = 4;
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Ws[2][BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const long long m0 = (long long)blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+
+  constexpr int A_LD = BM * 4 / NT;  // float4 loads per thread per k-tile
+  constexpr int W_LD = BN * 4 / NT;
+  float4 ra[A_LD], rw[W_LD];
+
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int f = tid + i * NT;
+      int r = f >> 2, kq = f & 3;
+      long long gr = m0 + r;
+      ra[i] = (gr < M) ? __ldg(reinterpret_cast<const float4*>(A + gr * lda + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < W_LD; ++i) {
+      int f = tid + i * NT;
+      int r = f >> 2, kq = f & 3;
+      int gn = n0 + r;
+      rw[i] = (gn < N) ? __ldg(reinterpret_cast<const float4*>(W + (long long)gn * ldw + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < A_LD; ++i) {
+      int f = tid + i * NT;
+      int r = f >> 2, kq = f & 3;
+      As[buf][kq * 4 + 0][r] = ra[i].x;
+      As[buf][kq * 4 + 1][r] = ra[i].y;
+      As[buf][kq * 4 + 2][r] = ra[i].z;
+      As[buf][kq * 4 + 3][r] = ra[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < W_LD; ++i) {
+      int f = tid + i * NT;
+      int r = f >> 2, kq = f & 3;
+      Ws[buf][kq * 4 + 0][r] = rw[i].x;
+      Ws[buf][kq * 4 + 1][r] = rw[i].y;
+      Ws[buf][kq * 4 + 2][r] = rw[i].z;
+      Ws[buf][kq * 4 + 3][r] = rw[i].w;
+    }
+  };
+
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+  const int nk = K / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][BM / 2 + ty * 4]);
+      float4 b0 = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      float4 b1 = *reinterpret_cast<const float4*>(&Ws[buf][k][BN / 2 + tx * 4]);
+      float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+
+  const bool vec_ok = ((C.ld & 3) == 0) && (epi.res == nullptr || (epi.ldr & 3) == 0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    long long gr = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+    if (gr >= M) continue;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int gc = n0 + (h == 0 ? tx * 4 : BN / 2 + tx * 4);
+      if (gc >= N) continue;
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float x = acc[i][h * 4 + j];
+        if (gc + j < N) {
+          if (epi.bias) x += __ldg(epi.bias + gc + j);
+          if (epi.relu) x = fmaxf(x, 0.f);
+          if (epi.res) x += __ldg(epi.res + gr * epi.ldr + gc + j);
+        }
+        v[j] = x;
+      }
+      if (vec_ok && gc + 3 < N) {
+        act_store4(C, gr, gc, make_float4(v[0], v[1], v[2], v[3]));
+      } else {
+        for (int j = 0; j < 4 && gc + j < N; ++j) act_store1(C, gr, gc + j, v[j]);
+      }
+    }
+  }
+}
+
+inline int gemm_simt(Ctx& c, const float* A, int lda, long long M, const float* W, int N, int K, const Epi& epi, Act C) {
+  if (M == 0 || N == 0) return QAT_OK;
+  QAT_REQUIRE(K % 16 == 0 && lda % 4 == 0, "gemm_simt: K=%d must be a multiple of 16 and lda=%d of 4", K, lda);
+  QAT_REQUIRE(M < (1ll << 31), "gemm_simt: M too large");
+  if (c.dry) return QAT_OK;
+  if (M >= 1024) {
+    dim3 grid((N + 127) / 128, (unsigned)((M + 127) / 128));
+    QAT_REQUIRE(grid.y <= 65535, "gemm_simt: M=%lld exceeds the grid limit; chunk the rows", M);
+    gemm_simt_kernel<16, 16><<<grid, 256, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
+  } else {
+    dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64));
+    gemm_simt_kernel<8, 8><<<grid, 64, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
+  }
+  return check_launch("gemm_simt_kernel");
+}
+
+}  // namespace qat

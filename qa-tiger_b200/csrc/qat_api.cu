@@ -1,0 +1,616 @@
+// libqat_b200: C-ABI entry points (include/qat.h) and the host-side orchestration of the sm_100a kernels.
+// Every entry point: validate -> carve the caller's workspace -> enqueue kernels on the caller's stream.
+// No allocation, no synchronisation, no global mutable state.
+#include "attn_core.cuh"
+#include "gauss.cuh"
+#include "gemm_simt.cuh"
+#include "gemm_tc.cuh"
+#include "qat_common.cuh"
+#include "rowops.cuh"
+#include "tome.cuh"
+
+namespace qat {
+
+thread_local char g_err[512] = "";
+thread_local long long g_launches = 0;
+
+// rows [n0, n0+n) of one nn.Linear
+struct WView {
+  const float* w = nullptr;
+  const bf16* hi = nullptr;
+  const bf16* lo = nullptr;
+  const float* bias = nullptr;
+  int n = 0, k = 0;
+};
+
+static WView wview(const QatLinearW& W, int n0 = 0, int n = -1) {
+  WView v;
+  if (n < 0) n = W.n - n0;
+  v.n = n;
+  v.k = W.k;
+  v.w = W.w ? W.w + (size_t)n0 * W.k : nullptr;
+  v.hi = W.w_hi ? reinterpret_cast<const bf16*>(W.w_hi) + (size_t)n0 * W.k : nullptr;
+  v.lo = W.w_lo ? reinterpret_cast<const bf16*>(W.w_lo) + (size_t)n0 * W.k : nullptr;
+  v.bias = W.bias ? W.bias + n0 : nullptr;
+  return v;
+}
+
+static int check_w(const QatLinearW& W, int n, int k, const char* name, int prec) {
+  QAT_REQUIRE(W.w != nullptr, "%s: weight pointer is NULL", name);
+  QAT_REQUIRE(W.n == n && W.k == k, "%s: expected [%d,%d], got [%d,%d]", name, n, k, W.n, W.k);
+  (void)prec;
+  return QAT_OK;
+}
+
+// Which engine runs a given contraction (DESIGN.md "precision policy").
+enum GemmKind { G_SIMT = 0, G_TF32 = 1, G_BF16X3 = 2 };
+
+static GemmKind pick_kind(const Ctx& c, long long M, int N, int K, bool patch_path, const WView& W) {
+  if (c.prec != QAT_PREC_BF16) return G_SIMT;
+  if (M < 1024 || N < 64 || (N % 8) != 0) return G_SIMT;     // tiny / fp32-only contractions stay on CUDA cores
+  if (patch_path) return (K % 32 == 0) ? G_TF32 : G_SIMT;
+  if (K % 64 == 0 && W.hi && W.lo) return G_BF16X3;
+  return (K % 32 == 0) ? G_TF32 : G_SIMT;
+}
+
+static bool reads_planes(GemmKind k) { return k == G_BF16X3; }
+
+static int gemm(Ctx& c, GemmKind kind, const Act& A, long long M, const WView& W, Epi epi, Act C) {
+  if (!epi.bias) epi.bias = W.bias;
+  switch (kind) {
+    case G_SIMT:
+      QAT_REQUIRE(c.dry || A.f, "gemm: fp32 operand missing");
+      return gemm_simt(c, A.f, A.ld, M, W.w, W.n, W.k, epi, C);
+    case G_TF32:
+      QAT_REQUIRE(c.dry || A.f, "gemm: fp32 operand missing");
+      return gemm_tc_tf32(c, A.f, A.ld, M, W.w, W.n, W.k, epi, C);
+    case G_BF16X3:
+      QAT_REQUIRE(c.dry || (A.hi && A.lo && W.hi && W.lo), "gemm: bf16 hi/lo operand planes missing");
+      return gemm_tc_bf16x3(c, A.hi, A.lo, A.ld, M, W.hi, W.lo, W.n, W.k, epi, C);
+  }
+  return QAT_EINVAL;
+}
+
+static Act act_of(float* p, int ld) {
+  Act a;
+  a.f = p;
+  a.ld = ld;
+  return a;
+}
+static Act act_of(const float* p, int ld) { return act_of(const_cast<float*>(p), ld); }
+
+// an input tensor that a bf16x3 GEMM wants to read: make the planes (and keep the fp32 view)
+static int planes_of(Ctx& c, const float* x, long long rows, int cols, bool want, Act& out) {
+  out = act_of(x, cols);
+  if (!want) return QAT_OK;
+  Act pl;
+  QAT_TRY(act_alloc(c, pl, rows, cols, false, true));
+  QAT_TRY(add_rows(c, x, cols, nullptr, 0, pl, rows, cols));
+  out.hi = pl.hi;
+  out.lo = pl.lo;
+  return QAT_OK;
+}
+
+static int ln(Ctx& c, const float* x0, long long ld0, const float* x1, long long ld1, const float* x2, long long ld2, float c01,
+              const QatLayerNormW& w, Act out, long long rows, int D) {
+  QAT_REQUIRE(w.gamma && w.beta, "layer_norm: affine parameters missing");
+  LnP p;
+  p.x0 = x0; p.ld0 = ld0; p.x1 = x1; p.ld1 = ld1; p.x2 = x2; p.ld2 = ld2;
+  p.c01 = c01; p.gamma = w.gamma; p.beta = w.beta; p.out = out; p.rows = rows; p.D = D; p.eps = 1e-5f;
+  return layer_norm(c, p);
+}
+
+// =================================================================================================
+// P1  Projection
+// =================================================================================================
+static int run_linear(const QatLinearArgs* a, Ctx& c) {
+  QAT_REQUIRE(a->rows >= 0 && a->w.n > 0 && a->w.k > 0, "linear: bad shape");
+  QAT_TRY(check_w(a->w, a->w.n, a->w.k, "linear.w", c.prec));
+  WView W = wview(a->w);
+  GemmKind kind = pick_kind(c, a->rows, W.n, W.k, false, W);
+  Act X;
+  QAT_TRY(planes_of(c, a->x, a->rows, W.k, reads_planes(kind), X));
+  Epi e;
+  e.relu = a->relu;
+  return gemm(c, kind, X, a->rows, W, e, act_of(a->y, W.n));
+}
+
+// =================================================================================================
+// A1-A3  AVQCrossAttn
+// =================================================================================================
+static int run_avq(const QatAvqArgs* a, Ctx& c) {
+  const int B = a->B, T = a->T, L = a->L, D = a->D, H = a->H;
+  QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && H >= 1 && D == H * 64, "avq: need D == H*64 (D=%d H=%d)", D, H);
+  QAT_REQUIRE(T <= 128 && L <= 128, "avq: sequence lengths T=%d L=%d must be <= 128", T, L);
+  QAT_TRY(check_w(a->in_src, 7 * D, D, "avq.in_src", c.prec));
+  QAT_TRY(check_w(a->in_words, 2 * D, D, "avq.in_words", c.prec));
+  QAT_TRY(check_w(a->out_cat, D, 3 * D, "avq.out_cat", c.prec));
+  QAT_TRY(check_w(a->ffn1, D, D, "avq.ffn1", c.prec));
+  QAT_TRY(check_w(a->ffn2, D, D, "avq.ffn2", c.prec));
+  const long long BT = (long long)B * T, BL = (long long)B * L;
+  const WView Wsrc = wview(a->in_src), Wwords = wview(a->in_words), Wout = wview(a->out_cat), W1 = wview(a->ffn1), W2 = wview(a->ffn2);
+  const GemmKind k_src = pick_kind(c, BT, 7 * D, D, false, Wsrc), k_words = pick_kind(c, BL, 2 * D, D, false, Wwords);
+  const GemmKind k_out = pick_kind(c, BT, D, 3 * D, false, Wout), k_f1 = pick_kind(c, BT, D, D, false, W1), k_f2 = pick_kind(c, BT, D, D, false, W2);
+
+  Act Xa, Xv, Xw;
+  QAT_TRY(planes_of(c, a->audio, BT, D, reads_planes(k_src), Xa));
+  QAT_TRY(planes_of(c, a->video, BT, D, reads_planes(k_src), Xv));
+  QAT_TRY(planes_of(c, a->words, BL, D, reads_planes(k_words), Xw));
+  // S = in-projections of both modalities, rows [0,BT) audio, [BT,2BT) video; cols as in_src
+  Act S, KVw, O, X1, Hh, Y;
+  QAT_TRY(act_alloc(c, S, 2 * BT, 7 * D, true, false));
+  QAT_TRY(act_alloc(c, KVw, BL, 2 * D, true, false));
+  QAT_TRY(gemm(c, k_src, Xa, BT, Wsrc, Epi(), S));
+  QAT_TRY(gemm(c, k_src, Xv, BT, Wsrc, Epi(), S.rows(BT)));
+  QAT_TRY(gemm(c, k_words, Xw, BL, Wwords, Epi(), KVw));
+  // O = [o_qst | o_slf | o_crs] per row, both directions
+  QAT_TRY(act_alloc(c, O, 2 * BT, 3 * D, !reads_planes(k_out), reads_planes(k_out)));
+  const float scale = 0.125f;  // 64^-0.5
+  AttnP p;
+  p.nseq = 2 * B; p.H = H; p.Lq = T; p.scale = scale;
+  p.q_sn = (long long)T * 7 * D; p.q_si = 7 * D;
+  p.o_rn = T; p.o_ri = 1;
+  // qst: keys/values = words of sample n % B
+  p.q = S.f; p.k = KVw.f; p.v = KVw.f + D; p.k_sn = (long long)L * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B; p.Lk = L;
+  p.o = O.cols(0); p.attw = nullptr;
+  if (a->attw_audio || a->attw_video) {
+    QAT_REQUIRE(a->attw_audio && a->attw_video, "avq: pass both attention-weight outputs or neither");
+    // the two outputs are separate tensors: run the two directions as separate launches
+    AttnP pa = p;
+    pa.nseq = B; pa.attw = a->attw_audio;
+    QAT_TRY(attention(c, pa));
+    AttnP pv = p;
+    pv.nseq = B; pv.attw = a->attw_video; pv.q = S.f + BT * 7 * D; pv.o = O.rows(BT).cols(0);
+    QAT_TRY(attention(c, pv));
+  } else {
+    QAT_TRY(attention(c, p));
+  }
+  // slf: own keys/values
+  p.attw = nullptr;
+  p.q = S.f + D; p.k = S.f + 2 * D; p.v = S.f + 3 * D; p.k_sn = p.q_sn; p.k_si = 7 * D; p.k_shift = 0; p.k_mod = 2 * B; p.Lk = T;
+  p.o = O.cols(D);
+  QAT_TRY(attention(c, p));
+  // crs: keys/values of the OTHER modality (direction 2 sees the original audio, modules.py:257-259)
+  p.q = S.f + 4 * D; p.k = S.f + 5 * D; p.v = S.f + 6 * D; p.k_shift = B; p.k_mod = 2 * B;
+  p.o = O.cols(2 * D);
+  QAT_TRY(attention(c, p));
+  // x1 = LN1(src + [o_qst|o_slf|o_crs] Wout^T + (b_qst+b_slf+b_crs))
+  QAT_TRY(act_alloc(c, Y, 2 * BT, D, true, false));
+  {
+    Epi e;
+    e.res = a->audio; e.ldr = D;
+    QAT_TRY(gemm(c, k_out, O, BT, Wout, e, Y));
+    e.res = a->video;
+    QAT_TRY(gemm(c, k_out, O.rows(BT), BT, Wout, e, Y.rows(BT)));
+  }
+  QAT_TRY(act_alloc(c, X1, 2 * BT, D, true, reads_planes(k_f1)));
+  QAT_TRY(ln(c, Y.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm1, X1, 2 * BT, D));
+  // FFN
+  QAT_TRY(act_alloc(c, Hh, 2 * BT, D, !reads_planes(k_f2), reads_planes(k_f2)));
+  {
+    Epi e;
+    e.relu = 1;
+    QAT_TRY(gemm(c, k_f1, X1, 2 * BT, W1, e, Hh));
+    Epi e2;
+    e2.res = X1.f; e2.ldr = D;
+    QAT_TRY(gemm(c, k_f2, Hh, 2 * BT, W2, e2, Y));
+  }
+  QAT_TRY(ln(c, Y.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm2, act_of(a->out_audio, D), BT, D));
+  QAT_TRY(ln(c, Y.f + BT * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm2, act_of(a->out_video, D), BT, D));
+  return QAT_OK;
+}
+
+// =================================================================================================
+// P1(patch) + S1  PatchSelecter
+// =================================================================================================
+static int run_patch(const QatPatchArgs* a, Ctx& c) {
+  const int B = a->B, T = a->T, P = a->P, D = a->D, H = a->H;
+  QAT_REQUIRE(B >= 1 && T >= 1 && P >= 1 && P <= 32 && D == H * 64, "patch_select: need P<=32 and D==H*64 (P=%d D=%d H=%d)", P, D, H);
+  if (a->has_proj) QAT_TRY(check_w(a->proj, D, a->Cin, "patch.proj", c.prec));
+  QAT_TRY(check_w(a->slf_in, 3 * D, D, "patch.slf_in", c.prec));
+  QAT_TRY(check_w(a->slf_out, D, D, "patch.slf_out", c.prec));
+  QAT_TRY(check_w(a->crs_q, D, D, "patch.crs_q", c.prec));
+  QAT_TRY(check_w(a->crs_kv, 2 * D, D, "patch.crs_kv", c.prec));
+  QAT_TRY(check_w(a->crs_out, D, D, "patch.crs_out", c.prec));
+  QAT_TRY(check_w(a->mlp0, D / 2, D, "patch.mlp0", c.prec));
+  QAT_TRY(check_w(a->mlp2, D, D / 2, "patch.mlp2", c.prec));
+  const long long BT = (long long)B * T;
+  const int Cin = a->has_proj ? a->Cin : D;
+  // frames per pass: keep the per-pass intermediates (~ P*D*4*(1+3+1+1+2) bytes per frame) near L2 size
+  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 1024;
+  if (chunk > BT) chunk = BT;
+  const float scale = 0.125f;
+  const WView Wp = wview(a->proj), Wsi = wview(a->slf_in), Wso = wview(a->slf_out), Wq = wview(a->crs_q), Wkv = wview(a->crs_kv);
+  const WView Wco = wview(a->crs_out), Wm0 = wview(a->mlp0), Wm2 = wview(a->mlp2);
+
+  // per-frame query rows [video; audio] -> q2 [BT, 2, D]  (modules.py:692: video first)
+  Act Q2, O2, O3, Hm, Mo;
+  QAT_TRY(act_alloc(c, Q2, BT, 2 * D, true, false));
+  {
+    GemmKind kq = pick_kind(c, BT, D, D, false, Wq);
+    Act Xv, Xa;
+    QAT_TRY(planes_of(c, a->video, BT, D, reads_planes(kq), Xv));
+    QAT_TRY(planes_of(c, a->audio, BT, D, reads_planes(kq), Xa));
+    QAT_TRY(gemm(c, kq, Xv, BT, Wq, Epi(), Q2.cols(0)));
+    QAT_TRY(gemm(c, kq, Xa, BT, Wq, Epi(), Q2.cols(D)));
+  }
+  const GemmKind k_co = pick_kind(c, 2 * BT, D, D, false, Wco), k_m0 = pick_kind(c, 2 * BT, D / 2, D, false, Wm0);
+  const GemmKind k_m2 = pick_kind(c, 2 * BT, D, D / 2, false, Wm2);
+  QAT_TRY(act_alloc(c, O2, 2 * BT, D, !reads_planes(k_co), reads_planes(k_co)));
+
+  const size_t mark = c.mark();
+  for (long long f0 = 0; f0 < BT; f0 += chunk) {
+    const long long nf = (BT - f0 < chunk) ? BT - f0 : chunk;
+    const long long rows = nf * P;
+    c.release(mark);
+    Act Pp, QKV, Oa, P2, KV;
+    const float* pin = a->patch + (size_t)f0 * P * Cin;
+    if (a->has_proj) {
+      QAT_TRY(act_alloc(c, Pp, rows, D, true, false));
+      QAT_TRY(gemm(c, pick_kind(c, rows, D, Cin, true, Wp), act_of(pin, Cin), rows, Wp, Epi(), Pp));
+    } else {
+      Pp = act_of(pin, D);
+    }
+    QAT_TRY(act_alloc(c, QKV, rows, 3 * D, true, false));
+    QAT_TRY(gemm(c, pick_kind(c, rows, 3 * D, D, true, Wsi), Pp, rows, Wsi, Epi(), QKV));
+    QAT_TRY(act_alloc(c, Oa, rows, D, true, false));
+    AttnP p;
+    p.nseq = (int)nf; p.H = H; p.Lq = P; p.Lk = P; p.scale = scale;
+    p.q = QKV.f; p.k = QKV.f + D; p.v = QKV.f + 2 * D;
+    p.q_sn = (long long)P * 3 * D; p.q_si = 3 * D; p.k_sn = p.q_sn; p.k_si = 3 * D; p.k_shift = 0; p.k_mod = (int)nf;
+    p.o = Oa; p.o_rn = P; p.o_ri = 1; p.attw = nullptr;
+    QAT_TRY(attention(c, p));
+    // p' = p + slf_attn(p)   (:688, no LayerNorm)
+    QAT_TRY(act_alloc(c, P2, rows, D, true, false));
+    {
+      Epi e;
+      e.res = Pp.f; e.ldr = Pp.ld;
+      QAT_TRY(gemm(c, pick_kind(c, rows, D, D, true, Wso), Oa, rows, Wso, e, P2));
+    }
+    QAT_TRY(act_alloc(c, KV, rows, 2 * D, true, false));
+    QAT_TRY(gemm(c, pick_kind(c, rows, 2 * D, D, true, Wkv), P2, rows, Wkv, Epi(), KV));
+    AttnP q;
+    q.nseq = (int)nf; q.H = H; q.Lq = 2; q.Lk = P; q.scale = scale;
+    q.q = Q2.f + (size_t)f0 * 2 * D; q.q_sn = 2 * D; q.q_si = D;
+    q.k = KV.f; q.v = KV.f + D; q.k_sn = (long long)P * 2 * D; q.k_si = 2 * D; q.k_shift = 0; q.k_mod = (int)nf;
+    q.o = O2.rows(2 * f0); q.o_rn = 2; q.o_ri = 1; q.attw = nullptr;
+    QAT_TRY(attention(c, q));
+  }
+  c.release(mark);
+  QAT_TRY(act_alloc(c, O3, 2 * BT, D, !reads_planes(k_m0), reads_planes(k_m0)));
+  QAT_TRY(gemm(c, k_co, O2, 2 * BT, Wco, Epi(), O3));
+  QAT_TRY(act_alloc(c, Hm, 2 * BT, D / 2, !reads_planes(k_m2), reads_planes(k_m2)));
+  {
+    Epi e;
+    e.relu = 1;
+    QAT_TRY(gemm(c, k_m0, O3, 2 * BT, Wm0, e, Hm));
+  }
+  QAT_TRY(act_alloc(c, Mo, 2 * BT, D, true, false));
+  QAT_TRY(gemm(c, k_m2, Hm, 2 * BT, Wm2, Epi(), Mo));
+  // rows (bt,0) = video-related, (bt,1) = audio-related (:706); returned as [anorm(a), vnorm(v)] (:713-716)
+  QAT_TRY(ln(c, Mo.f + D, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->anorm, act_of(a->out_a, D), BT, D));
+  QAT_TRY(ln(c, Mo.f, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->vnorm, act_of(a->out_v, D), BT, D));
+  return QAT_OK;
+}
+
+// =================================================================================================
+// M2-M4 standalone
+// =================================================================================================
+static int run_gauss(const QatGaussArgs* a, Ctx& c) {
+  QAT_REQUIRE(a->experts && a->router_logits && a->gauss_raw && a->out, "gauss_reduce: NULL tensor");
+  GaussP p;
+  p.x = a->experts; p.st = a->stride_t; p.sb = a->stride_b;
+  p.rl = a->router_logits; p.gr = a->gauss_raw;
+  p.B = a->B; p.T = a->T; p.E = a->E; p.K = a->K; p.C = a->C; p.sigma = a->sigma;
+  p.per_expert = 0;
+  p.out = act_of(a->out, a->C);
+  p.topk_inds = reinterpret_cast<long long*>(a->topk_inds);
+  p.topk_probs = a->topk_probs;
+  p.gauss_weight = a->gauss_weight;
+  QAT_REQUIRE(a->sigma > 0.f, "gauss_reduce: sigma must be positive");
+  return gauss_reduce(c, p, a->dtype, a->t_split);
+}
+
+// =================================================================================================
+// M1-M4 (+LN)  TempMoE
+// =================================================================================================
+static int run_moe(const QatMoeArgs* a, Ctx& c) {
+  const int B = a->B, T = a->T, D = a->D, H = a->H, E = a->E, K = a->K;
+  QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
+  QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
+  QAT_REQUIRE((a->sub_a == nullptr) == (a->sub_v == nullptr), "temp_moe: sub_data needs both tensors or none");
+  const int Ch = D / 2, KE = E * Ch + 64;
+  QAT_TRY(check_w(a->attn_q, D, D, "moe.attn_q", c.prec));
+  QAT_TRY(check_w(a->attn_kv, 2 * D, D, "moe.attn_kv", c.prec));
+  QAT_TRY(check_w(a->attn_out, D, D, "moe.attn_out", c.prec));
+  QAT_TRY(check_w(a->router_gauss, 3 * E, D, "moe.router_gauss", c.prec));
+  QAT_TRY(check_w(a->w1_cat, E * Ch, D, "moe.w1_cat", c.prec));
+  QAT_TRY(check_w(a->w2_ext, D, KE, "moe.w2_ext", c.prec));
+  const long long BT = (long long)B * T;
+  const bool two = a->sub_a != nullptr;
+  QAT_REQUIRE(a->out_a && (!two || a->out_v), "temp_moe: output pointer missing");
+  const WView Wq = wview(a->attn_q), Wkv = wview(a->attn_kv), Wo = wview(a->attn_out), Wrg = wview(a->router_gauss);
+  const WView W1 = wview(a->w1_cat), W2 = wview(a->w2_ext);
+  const GemmKind k_kv = pick_kind(c, BT, 2 * D, D, false, Wkv), k_w1 = pick_kind(c, BT, E * Ch, D, false, W1);
+
+  // temp_w = qst_attn(q = qst, kv = data)   (:562) -- the rank-critical chain: K/V at bf16x3 or fp32, rest fp32
+  Act Xd, KV, Q, Oq, TW, RG;
+  QAT_TRY(planes_of(c, a->data, BT, D, reads_planes(k_kv) || (!two && reads_planes(k_w1)), Xd));
+  QAT_TRY(act_alloc(c, KV, BT, 2 * D, true, false));
+  QAT_TRY(gemm(c, k_kv, Xd, BT, Wkv, Epi(), KV));
+  QAT_TRY(act_alloc(c, Q, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, act_of(a->qst, D), B, Wq, Epi(), Q));
+  QAT_TRY(act_alloc(c, Oq, B, D, true, false));
+  AttnP p;
+  p.nseq = B; p.H = H; p.Lq = 1; p.Lk = T; p.scale = 0.125f;
+  p.q = Q.f; p.q_sn = D; p.q_si = D;
+  p.k = KV.f; p.v = KV.f + D; p.k_sn = (long long)T * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B;
+  p.o = Oq; p.o_rn = 1; p.o_ri = 1; p.attw = nullptr;
+  QAT_TRY(attention(c, p));
+  QAT_TRY(act_alloc(c, TW, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, Oq, B, Wo, Epi(), TW));
+  // router logits [B,E] | gauss_pred [B,2E] in one fp32 contraction (:565,573)
+  QAT_TRY(act_alloc(c, RG, B, 3 * E, true, false));
+  QAT_TRY(gemm(c, G_SIMT, TW, B, Wrg, Epi(), RG));
+  // RG rows are [router(E) | gauss(2E)] with ld 3E: the reduce kernel wants dense [B,E] and [B,2E]
+  Act RL, GR;
+  QAT_TRY(act_alloc(c, RL, B, E, true, false));
+  QAT_TRY(act_alloc(c, GR, B, 2 * E, true, false));
+  if (!c.dry) {
+    QAT_CUDA(cudaMemcpy2DAsync(RL.f, (size_t)E * 4, RG.f, (size_t)3 * E * 4, (size_t)E * 4, B, cudaMemcpyDeviceToDevice, c.stream));
+    QAT_CUDA(cudaMemcpy2DAsync(GR.f, (size_t)2 * E * 4, RG.f + E, (size_t)3 * E * 4, (size_t)2 * E * 4, B, cudaMemcpyDeviceToDevice, c.stream));
+    g_launches += 2;
+  }
+
+  const int nbranch = two ? 2 : 1;
+  for (int br = 0; br < nbranch; ++br) {
+    const size_t mark = c.mark();
+    Act Xe = Xd;
+    if (two) {
+      QAT_TRY(act_alloc(c, Xe, BT, D, !reads_planes(k_w1), reads_planes(k_w1)));
+      QAT_TRY(add_rows(c, a->data, D, br == 0 ? a->sub_a : a->sub_v, D, Xe, BT, D));     // :587,597
+    }
+    // hidden = relu(W1_e x + b1_e) for every expert: [BT, E*Ch]
+    Act Hd, Hb, Ob;
+    QAT_TRY(act_alloc(c, Hd, BT, E * Ch, true, false));
+    {
+      Epi e;
+      e.relu = 1;
+      QAT_TRY(gemm(c, k_w1, Xe, BT, W1, e, Hd));
+    }
+    // hbar[b, e, :] = sum_t coef[b,t,e] hidden[b,t,e,:]  |  csum[b,e] = sum_t coef[b,t,e]
+    QAT_TRY(act_alloc(c, Hb, B, KE, true, false));
+    GaussP g;
+    g.x = Hd.f; g.st = (long long)E * Ch; g.sb = (long long)T * E * Ch;
+    g.rl = RL.f; g.gr = GR.f; g.B = B; g.T = T; g.E = E; g.K = K; g.C = Ch; g.sigma = a->sigma;
+    g.per_expert = 1; g.out = Hb;
+    g.topk_inds = br == 0 ? reinterpret_cast<long long*>(a->topk_inds) : nullptr;
+    g.topk_probs = br == 0 ? a->topk_probs : nullptr;
+    g.gauss_weight = br == 0 ? a->gauss_weight : nullptr;
+    QAT_TRY(gauss_reduce(c, g, QAT_DT_F32, 0));
+    // out = sum_e W2_e hbar_e + b2_e csum_e : one [B, E*Ch+64] x [D, E*Ch+64]^T contraction, no bias
+    QAT_TRY(act_alloc(c, Ob, B, D, true, false));
+    {
+      Epi e;
+      WView w2 = W2;
+      w2.bias = nullptr;
+      QAT_TRY(gemm(c, G_SIMT, Hb, B, w2, e, Ob));
+    }
+    const QatLayerNormW& nw = (br == 0) ? a->norm_a : a->norm_v;
+    QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, nw, act_of(br == 0 ? a->out_a : a->out_v, D), B, D));
+    c.release(mark);
+  }
+  return QAT_OK;
+}
+
+// =================================================================================================
+// G1 (+H1)  QstGrounding on a length-2 sequence, optional head
+// =================================================================================================
+static int run_ground(const QatGroundArgs* a, Ctx& c) {
+  const int B = a->B, D = a->D, H = a->H;
+  QAT_REQUIRE(B >= 1 && D == H * 64, "qst_grounding: need D==H*64");
+  QAT_TRY(check_w(a->attn_q, D, D, "ground.attn_q", c.prec));
+  QAT_TRY(check_w(a->attn_kv, 2 * D, D, "ground.attn_kv", c.prec));
+  QAT_TRY(check_w(a->attn_out, D, D, "ground.attn_out", c.prec));
+  QAT_TRY(check_w(a->mlp0, D / 2, D, "ground.mlp0", c.prec));
+  QAT_TRY(check_w(a->mlp2, D, D / 2, "ground.mlp2", c.prec));
+  Act KV, Q, O, A1, Hm, Mo;
+  QAT_TRY(act_alloc(c, KV, 2ll * B, 2 * D, true, false));      // [B, 2, 2D]
+  {
+    Act kv0 = KV, kv1 = KV;
+    kv0.ld = 4 * D;
+    kv1.ld = 4 * D;
+    kv1.f += 2 * D;
+    QAT_TRY(gemm(c, G_SIMT, act_of(a->d0, D), B, wview(a->attn_kv), Epi(), kv0));
+    QAT_TRY(gemm(c, G_SIMT, act_of(a->d1, D), B, wview(a->attn_kv), Epi(), kv1));
+  }
+  QAT_TRY(act_alloc(c, Q, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, act_of(a->qst, D), B, wview(a->attn_q), Epi(), Q));
+  QAT_TRY(act_alloc(c, O, B, D, true, false));
+  AttnP p;
+  p.nseq = B; p.H = H; p.Lq = 1; p.Lk = 2; p.scale = 0.125f;
+  p.q = Q.f; p.q_sn = D; p.q_si = D;
+  p.k = KV.f; p.v = KV.f + D; p.k_sn = 4 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B;
+  p.o = O; p.o_rn = 1; p.o_ri = 1; p.attw = nullptr;
+  QAT_TRY(attention(c, p));
+  QAT_TRY(act_alloc(c, A1, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, O, B, wview(a->attn_out), Epi(), A1));
+  QAT_TRY(act_alloc(c, Hm, B, D / 2, true, false));
+  {
+    Epi e;
+    e.relu = 1;
+    QAT_TRY(gemm(c, G_SIMT, A1, B, wview(a->mlp0), e, Hm));
+  }
+  QAT_TRY(act_alloc(c, Mo, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, Hm, B, wview(a->mlp2), Epi(), Mo));
+  // feat = mean_seq(data) + mlp(attn)  -> LN   (:344-346)
+  QAT_TRY(ln(c, a->d0, D, a->d1, D, Mo.f, D, 0.5f, a->norm, act_of(a->out, D), B, D));
+  if (a->has_head) {
+    QAT_REQUIRE(a->logits && a->head.w && a->head.k == D, "qst_grounding: head weights/logits missing");
+    // head(relu(fusion)) net.py:141-142: relu folded into a tiny elementwise pass on the LN output
+    Act R;
+    QAT_TRY(act_alloc(c, R, B, D, true, false));
+    if (!c.dry) {
+      QAT_TRY(relu_rows(c, a->out, R.f, (long long)B * D));
+    }
+    QAT_TRY(gemm(c, G_SIMT, R, B, wview(a->head), Epi(), act_of(a->logits, a->head.n)));
+  }
+  return QAT_OK;
+}
+
+// =================================================================================================
+// T1-T3, T0
+// =================================================================================================
+static int run_tome_match(const QatTomeMatchArgs* a, Ctx& c) {
+  const int r = tome_clamp_r(a->t, a->r, a->class_token);
+  QAT_REQUIRE(r > 0, "tome_match: nothing to merge (r clamps to 0 for t=%d)", a->t);
+  QAT_REQUIRE(a->metric && a->unm_idx && a->src_idx && a->dst_idx, "tome_match: NULL tensor");
+  return tome_match(c, a->metric, a->N, a->t, a->C, r, a->class_token, a->unm_idx, a->src_idx, a->dst_idx);
+}
+
+static int run_tome_merge(const QatTomeMergeArgs* a, Ctx& c) {
+  QAT_REQUIRE(a->x && a->unm_idx && a->src_idx && a->dst_idx && a->x_out, "tome_merge: NULL tensor");
+  return tome_merge(c, a->x, a->size, a->N, a->t, a->C, a->r, a->mode, a->unm_idx, a->src_idx, a->dst_idx, a->x_out,
+                    a->size_out, a->group, a->T0);
+}
+
+static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
+  const int N = a->N, C = a->C;
+  QAT_REQUIRE(a->n_steps >= 0 && (a->n_steps == 0 || a->r_list), "tome_chain: r_list missing");
+  QAT_REQUIRE(C % 64 == 0, "tome_chain: C=%d must be a multiple of 64 (stand-in metric)", C);
+  int t = a->t0;
+  // ping-pong buffers sized for the first step's output
+  float* xb[2] = {nullptr, nullptr};
+  float* sb[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; ++i) {
+    xb[i] = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * C * 4));
+    sb[i] = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * 4));
+  }
+  float* metric = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * 64 * 4));
+  int* idx = reinterpret_cast<int*>(c.alloc((size_t)N * ((a->t0 + 1) / 2 + 2 * (a->t0 / 2)) * 4));
+  if (!c.dry && (!xb[1] || !sb[1] || !metric || !idx)) QAT_FAIL(QAT_EWORKSPACE, "tome_chain: workspace too small (need %zu)", c.peak);
+  if (a->group && !c.dry) {
+    long long tot = (long long)N * a->t0;
+    iota_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.stream>>>(a->group, N, a->t0);
+    QAT_TRY(check_launch("iota_rows_kernel"));
+  }
+  const float* xcur = a->x;
+  const float* scur = nullptr;
+  int pp = 0;
+  size_t trace_off = 0;
+  for (int s = 0; s < a->n_steps; ++s) {
+    const int r = tome_clamp_r(t, a->r_list[s], a->class_token);
+    if (r <= 0) continue;
+    const int ta = (t + 1) / 2, n_unm = ta - r;
+    int* unm = idx;
+    int* src = unm + (size_t)N * n_unm;
+    int* dst = src + (size_t)N * r;
+    if (a->idx_trace && !c.dry) {
+      unm = a->idx_trace + trace_off;
+      src = unm + (size_t)N * n_unm;
+      dst = src + (size_t)N * r;
+    }
+    trace_off += (size_t)N * (n_unm + 2 * r);
+    QAT_TRY(tome_metric(c, xcur, metric, (long long)N * t, C));
+    QAT_TRY(tome_match(c, metric, N, t, 64, r, a->class_token, unm, src, dst));
+    QAT_TRY(tome_merge(c, xcur, scur, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, xb[pp], sb[pp], a->group, a->t0));
+    xcur = xb[pp];
+    scur = sb[pp];
+    pp ^= 1;
+    t -= r;
+  }
+  if (!c.dry) {
+    QAT_REQUIRE(a->x_out && a->size_out, "tome_chain: output pointer missing");
+    if (scur == nullptr) {
+      QAT_CUDA(cudaMemcpyAsync(a->x_out, a->x, (size_t)N * t * C * 4, cudaMemcpyDeviceToDevice, c.stream));
+      ones_kernel<<<(unsigned)(((long long)N * t + 255) / 256), 256, 0, c.stream>>>(a->size_out, (long long)N * t);
+      QAT_TRY(check_launch("ones_kernel"));
+    } else {
+      QAT_CUDA(cudaMemcpyAsync(a->x_out, xcur, (size_t)N * t * C * 4, cudaMemcpyDeviceToDevice, c.stream));
+      QAT_CUDA(cudaMemcpyAsync(a->size_out, scur, (size_t)N * t * 4, cudaMemcpyDeviceToDevice, c.stream));
+    }
+  }
+  return QAT_OK;
+}
+
+template <typename Args, typename Fn>
+static int dispatch(const Args* a, void* stream, int prec, void* ws, size_t wsb, Fn fn) {
+  if (!a) QAT_FAIL(QAT_EINVAL, "args is NULL");
+  Ctx c;
+  QAT_TRY(ctx_init(c, stream, prec, ws, wsb, false));
+  int dev = 0;
+  QAT_CUDA(cudaGetDevice(&dev));
+  int major = 0;
+  QAT_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  if (major != 10) QAT_FAIL(QAT_EARCH, "libqat_b200 is built for sm_100a only; device %d has compute capability %d.x", dev, major);
+  return fn(a, c);
+}
+
+template <typename Args, typename Fn>
+static size_t dry_bytes(const Args* a, int prec, Fn fn) {
+  Ctx c;
+  if (ctx_init(c, nullptr, prec, nullptr, 0, true) != QAT_OK) return 0;
+  if (fn(a, c) != QAT_OK) return 0;
+  return c.peak + 256;
+}
+
+}  // namespace qat
+
+using namespace qat;
+
+extern "C" {
+
+int qat_linear_fwd(const QatLinearArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_linear); }
+int qat_avq_cross_attn_fwd(const QatAvqArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_avq); }
+int qat_patch_select_fwd(const QatPatchArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_patch); }
+int qat_gauss_reduce_fwd(const QatGaussArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, run_gauss); }
+int qat_temp_moe_fwd(const QatMoeArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_moe); }
+int qat_qst_grounding_head_fwd(const QatGroundArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_ground); }
+int qat_tome_match(const QatTomeMatchArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_match); }
+int qat_tome_merge(const QatTomeMergeArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_merge); }
+int qat_tome_chain(const QatTomeChainArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_chain); }
+
+int qat_tome_clamp_r(int t, int r, int class_token) { return tome_clamp_r(t, r, class_token); }
+
+int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token) {
+  int t = t0;
+  for (int s = 0; s < n_steps; ++s) t -= tome_clamp_r(t, r_list[s], class_token);
+  return t;
+}
+
+size_t qat_tome_chain_trace_len(int N, int t0, int n_steps, const int32_t* r_list, int class_token) {
+  size_t tot = 0;
+  int t = t0;
+  for (int s = 0; s < n_steps; ++s) {
+    int r = tome_clamp_r(t, r_list[s], class_token);
+    if (r <= 0) continue;
+    tot += (size_t)N * ((t + 1) / 2 - r + 2 * r);
+    t -= r;
+  }
+  return tot;
+}
+
+size_t qat_workspace_bytes(int op, const void* args) {
+  if (!args) return 0;
+  switch (op) {
+    case QAT_OP_LINEAR: return dry_bytes(reinterpret_cast<const QatLinearArgs*>(args), reinterpret_cast<const QatLinearArgs*>(args)->prec, run_linear);
+    case QAT_OP_AVQ: return dry_bytes(reinterpret_cast<const QatAvqArgs*>(args), reinterpret_cast<const QatAvqArgs*>(args)->prec, run_avq);
+    case QAT_OP_PATCH: return dry_bytes(reinterpret_cast<const QatPatchArgs*>(args), reinterpret_cast<const QatPatchArgs*>(args)->prec, run_patch);
+    case QAT_OP_MOE: return dry_bytes(reinterpret_cast<const QatMoeArgs*>(args), reinterpret_cast<const QatMoeArgs*>(args)->prec, run_moe);
+    case QAT_OP_GROUND: return dry_bytes(reinterpret_cast<const QatGroundArgs*>(args), reinterpret_cast<const QatGroundArgs*>(args)->prec, run_ground);
+    case QAT_OP_TOME_MATCH: return 256;
+    case QAT_OP_TOME_MERGE: return 256;
+    case QAT_OP_TOME_CHAIN: return dry_bytes(reinterpret_cast<const QatTomeChainArgs*>(args), QAT_PREC_FP32, run_tome_chain);
+    default: return 0;
+  }
+}
+
+const char* qat_last_error(void) { return g_err; }
+int qat_abi_version(void) { return QAT_ABI_VERSION; }
+long long qat_launch_count(int reset) {
+  long long v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// Shared host/device helpers for libqat_b200 (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/qat.h"
+
+namespace qat {
+
+typedef __nv_bfloat16 bf16;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing: thread-local message, no exceptions across the C ABI
+// ------------------------------------------------------------------------------------------------
+extern thread_local char g_err[512];
+extern thread_local long long g_launches;
+
+#define QAT_FAIL(code, ...)                     \
+  do {                                          \
+    snprintf(qat::g_err, sizeof(qat::g_err), __VA_ARGS__); \
+    return (code);                              \
+  } while (0)
+
+#define QAT_REQUIRE(cond, ...)                  \
+  do {                                          \
+    if (!(cond)) QAT_FAIL(QAT_EINVAL, __VA_ARGS__); \
+  } while (0)
+
+#define QAT_CUDA(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      QAT_FAIL(QAT_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define QAT_TRY(expr)        \
+  do {                       \
+    int _r = (expr);         \
+    if (_r != QAT_OK) return _r; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// An activation as the kernels see it: fp32 and/or a bf16 (hi, lo) pair, all with the same leading
+// dimension.  x ~= hi + lo carries 16 mantissa bits, which is what the bf16x3 tensor-core GEMMs eat.
+// ------------------------------------------------------------------------------------------------
+struct Act {
+  float* f = nullptr;
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+  int ld = 0;
+  __host__ __device__ Act cols(int c0) const {
+    Act a = *this;
+    if (a.f) a.f += c0;
+    if (a.hi) a.hi += c0;
+    if (a.lo) a.lo += c0;
+    return a;
+  }
+  __host__ __device__ Act rows(long long r0) const {
+    Act a = *this;
+    if (a.f) a.f += r0 * ld;
+    if (a.hi) a.hi += r0 * ld;
+    if (a.lo) a.lo += r0 * ld;
+    return a;
+  }
+};
+
+__device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// store 4 consecutive values of one row into whichever planes exist (col multiple of 4)
+__device__ __forceinline__ void act_store4(const Act& a, long long row, int col, float4 v) {
+  long long off = row * a.ld + col;
+  if (a.f) *reinterpret_cast<float4*>(a.f + off) = v;
+  if (a.hi) {
+    bf16 h0, h1, h2, h3, l0, l1, l2, l3;
+    split_bf16(v.x, h0, l0);
+    split_bf16(v.y, h1, l1);
+    split_bf16(v.z, h2, l2);
+    split_bf16(v.w, h3, l3);
+    __nv_bfloat162 a0 = __halves2bfloat162(h0, h1), a1 = __halves2bfloat162(h2, h3);
+    uint2 u;
+    u.x = *reinterpret_cast<uint32_t*>(&a0);
+    u.y = *reinterpret_cast<uint32_t*>(&a1);
+    *reinterpret_cast<uint2*>(a.hi + off) = u;
+    if (a.lo) {
+      __nv_bfloat162 b0 = __halves2bfloat162(l0, l1), b1 = __halves2bfloat162(l2, l3);
+      u.x = *reinterpret_cast<uint32_t*>(&b0);
+      u.y = *reinterpret_cast<uint32_t*>(&b1);
+      *reinterpret_cast<uint2*>(a.lo + off) = u;
+    }
+  }
+}
+
+__device__ __forceinline__ void act_store1(const Act& a, long long row, int col, float v) {
+  long long off = row * a.ld + col;
+  if (a.f) a.f[off] = v;
+  if (a.hi) {
+    bf16 h, l;
+    split_bf16(v, h, l);
+    a.hi[off] = h;
+    if (a.lo) a.lo[off] = l;
+  }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit load that does not pollute L1
+__device__ __forceinline__ float4 ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-call context: stream, precision, bump allocator over the caller's workspace.
+// `dry` = size the workspace without touching the GPU (qat_workspace_bytes runs the same code path).
+// ------------------------------------------------------------------------------------------------
+struct Ctx {
+  cudaStream_t stream = nullptr;
+  int prec = QAT_PREC_FP32;
+  bool dry = false;
+  char* base = nullptr;
+  size_t cap = 0;
+  size_t off = 0;
+  size_t peak = 0;
+
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > peak) peak = off;
+    if (dry) return reinterpret_cast<void*>(size_t(256));  // never dereferenced
+    if (off > cap) return nullptr;
+    return base + a;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+inline int ctx_init(Ctx& c, void* stream, int prec, void* ws, size_t ws_bytes, bool dry) {
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  c.prec = prec;
+  c.dry = dry;
+  c.base = reinterpret_cast<char*>(ws);
+  c.cap = ws_bytes;
+  QAT_REQUIRE(prec == QAT_PREC_FP32 || prec == QAT_PREC_BF16, "unknown precision mode %d", prec);
+  if (!dry) QAT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
+  return QAT_OK;
+}
+
+// allocate an activation [rows, ld] with the planes a consumer needs
+inline int act_alloc(Ctx& c, Act& a, long long rows, int ld, bool want_f, bool want_planes) {
+  a = Act();
+  a.ld = ld;
+  if (want_f) {
+    a.f = reinterpret_cast<float*>(c.alloc(size_t(rows) * ld * 4));
+    if (!a.f) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+  }
+  if (want_planes) {
+    a.hi = reinterpret_cast<bf16*>(c.alloc(size_t(rows) * ld * 2));
+    a.lo = reinterpret_cast<bf16*>(c.alloc(size_t(rows) * ld * 2));
+    if (!a.hi || !a.lo) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+  }
+  return QAT_OK;
+}
+
+inline int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) QAT_FAIL(QAT_ECUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  ++g_launches;
+  return QAT_OK;
+}
+
+}  // namespace qat

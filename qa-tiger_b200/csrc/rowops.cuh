@@ -1,0 +1,129 @@
+// Row-wise helpers: LayerNorm (eps 1e-5, biased variance, affine) over rows of D<=1024, fused with
+// the small linear combinations that precede it on the hot path, plus add / split / copy kernels.
+#pragma once
+#include "qat_common.cuh"
+
+namespace qat {
+
+// y = LN(c0*x0 + c1*x1 + x2) * gamma + beta ; x1, x2 optional.  One warp per row.
+// x0 + x1 is formed first, then scaled by c01, then x2 is added -- the order used by
+// QstGrounding (`data.mean(0) + mlp(.)`, modules.py:344) and by plain LN (x1=x2=null, c01=1).
+struct LnP {
+  const float* x0; long long ld0;
+  const float* x1; long long ld1;
+  const float* x2; long long ld2;
+  float c01;
+  const float* gamma;
+  const float* beta;
+  Act out;             // row r -> out row r
+  long long rows;
+  int D;
+  float eps;
+};
+
+template <int VPL>  // float4 per lane: D = 128*VPL
+__global__ void __launch_bounds__(256) ln_kernel(LnP p) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= p.rows) return;
+  float4 v[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    int c4 = lane + 32 * i;
+    float4 a = __ldg(reinterpret_cast<const float4*>(p.x0 + row * p.ld0) + c4);
+    if (p.x1) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(p.x1 + row * p.ld1) + c4);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      a.x *= p.c01; a.y *= p.c01; a.z *= p.c01; a.w *= p.c01;
+    }
+    if (p.x2) {
+      float4 b = __ldg(reinterpret_cast<const float4*>(p.x2 + row * p.ld2) + c4);
+      a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    }
+    v[i] = a;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / p.D;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+    q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / p.D + p.eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    int c4 = lane + 32 * i;
+    float4 g = __ldg(reinterpret_cast<const float4*>(p.gamma) + c4);
+    float4 b = __ldg(reinterpret_cast<const float4*>(p.beta) + c4);
+    float4 o;
+    o.x = v[i].x * rstd * g.x + b.x;
+    o.y = v[i].y * rstd * g.y + b.y;
+    o.z = v[i].z * rstd * g.z + b.z;
+    o.w = v[i].w * rstd * g.w + b.w;
+    act_store4(p.out, row, c4 * 4, o);
+  }
+}
+
+inline int layer_norm(Ctx& c, const LnP& p) {
+  QAT_REQUIRE(p.D % 128 == 0 && p.D <= 1024, "layer_norm: D=%d must be a multiple of 128 and <= 1024", p.D);
+  if (c.dry || p.rows == 0) return QAT_OK;
+  unsigned grid = (unsigned)((p.rows + 7) / 8);
+  switch (p.D / 128) {
+    case 1: ln_kernel<1><<<grid, 256, 0, c.stream>>>(p); break;
+    case 2: ln_kernel<2><<<grid, 256, 0, c.stream>>>(p); break;
+    case 3: ln_kernel<3><<<grid, 256, 0, c.stream>>>(p); break;
+    case 4: ln_kernel<4><<<grid, 256, 0, c.stream>>>(p); break;
+    case 5: ln_kernel<5><<<grid, 256, 0, c.stream>>>(p); break;
+    case 6: ln_kernel<6><<<grid, 256, 0, c.stream>>>(p); break;
+    case 7: ln_kernel<7><<<grid, 256, 0, c.stream>>>(p); break;
+    default: ln_kernel<8><<<grid, 256, 0, c.stream>>>(p); break;
+  }
+  return check_launch("ln_kernel");
+}
+
+// out[r, :] = a[r, :] + b[r, :]  (b optional) -- also the fp32 -> (fp32, hi, lo) plane converter
+__global__ void __launch_bounds__(256) add_rows_kernel(const float* __restrict__ a, long long lda,
+                                                       const float* __restrict__ b, long long ldb, Act out,
+                                                       long long rows, int cols4) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = rows * cols4;
+  for (; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i / cols4;
+    int c4 = (int)(i % cols4);
+    float4 x = __ldg(reinterpret_cast<const float4*>(a + r * lda) + c4);
+    if (b) {
+      float4 y = __ldg(reinterpret_cast<const float4*>(b + r * ldb) + c4);
+      x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+    }
+    act_store4(out, r, c4 * 4, x);
+  }
+}
+
+inline int add_rows(Ctx& c, const float* a, long long lda, const float* b, long long ldb, Act out, long long rows, int cols) {
+  QAT_REQUIRE(cols % 4 == 0, "add_rows: cols=%d must be a multiple of 4", cols);
+  if (c.dry || rows == 0) return QAT_OK;
+  long long total = rows * (cols / 4);
+  unsigned grid = (unsigned)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+  add_rows_kernel<<<grid, 256, 0, c.stream>>>(a, lda, b, ldb, out, rows, cols / 4);
+  return check_launch("add_rows_kernel");
+}
+
+__global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = fmaxf(x[i], 0.f);
+}
+inline int relu_rows(Ctx& c, const float* x, float* y, long long n) {
+  if (c.dry || n == 0) return QAT_OK;
+  relu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(x, y, n);
+  return check_launch("relu_kernel");
+}
+
+__global__ void __launch_bounds__(256) ones_kernel(float* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = 1.f;
+}
+
+}  // namespace qat

@@ -1,0 +1,315 @@
+// ToMe bipartite soft matching (T1), size-weighted merge (T2), source tracking as group ids (T3) and the
+// stand-in metric of the 577->14 schedule (T0).  Reference: src/tome/merge.py:18-97, 210-241.
+//
+// Bit-exactness: the reference's indices are a function of fp32 roundings, so the
+// arithmetic ORDER of torch's CPU kernels is reproduced, not just their math.  Orders were pinned
+// empirically against torch 2.11 CPU in the build container (0 mismatching floats):
+//   norm   : 8 interleaved partial sums acc[l] += x[d+l]*x[d+l] (separate mul and add), then
+//            ((acc0+acc1)+acc2)+...; sqrt; every element divided by the norm        (merge.py:50)
+//   scores : one sequential FMA chain over the channel index, starting from 0        (merge.py:52)
+//   max    : first index among equal maxima; argsort descending, equal keys keep index order (:59-60)
+//   merge  : dst += src in ascending order of the sorted edge list; x*size first, /size last (:70-80,221-224)
+//   metric : ((x_0 + x_1) + ...) + x_15 over the 16 channel groups, then /16          
+// All of it is plain IEEE fp32 (__fmul_rn/__fadd_rn/__fmaf_rn/__fdiv_rn/__fsqrt_rn: no contraction).
+#pragma once
+#include "qat_common.cuh"
+
+namespace qat {
+
+__host__ __device__ inline int tome_clamp_r(int t, int r, int class_token) {
+  int prot = class_token ? 1 : 0;
+  int m = (t - prot) / 2;
+  r = r < m ? r : m;
+  return r > 0 ? r : 0;
+}
+
+constexpr int TOME_MAX_C = 64;   // metric channels held in registers per thread
+
+// ---- T1 -------------------------------------------------------------------------------------------
+// One CTA per frame.  Thread (i, half) owns row i of set A (even tokens) and scans half of set B.
+template <int C>
+__global__ void __launch_bounds__(640) tome_match_kernel(const float* __restrict__ metric, int t, int r, int class_token,
+                                                         int* __restrict__ unm_idx, int* __restrict__ src_idx,
+                                                         int* __restrict__ dst_idx) {
+  extern __shared__ __align__(16) float smem[];
+  const int ta = (t + 1) / 2, tb = t / 2;
+  float* Bs = smem;                                  // [tb][C] normalised odd tokens
+  float* nmax = Bs + (size_t)tb * C;                 // [ta]
+  int* nidx = reinterpret_cast<int*>(nmax + ta);     // [ta]
+  int* rank = nidx + ta;                             // [ta]
+  float* hmax = reinterpret_cast<float*>(rank + ta); // [ta] second-half partials
+  int* hidx = reinterpret_cast<int*>(hmax + ta);     // [ta]
+  const int n = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  const float* mf = metric + (size_t)n * t * C;
+
+  // out <- row / ||row||, in place (keeps one C-float array live)
+  auto normalise = [&](const float* row, float (&out)[C]) {
+#pragma unroll
+    for (int d = 0; d < C; d += 4) {
+      float4 v = __ldg(reinterpret_cast<const float4*>(row + d));
+      out[d] = v.x; out[d + 1] = v.y; out[d + 2] = v.z; out[d + 3] = v.w;
+    }
+    float acc[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+#pragma unroll
+    for (int d = 0; d < C; d += 8)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[l] = __fadd_rn(acc[l], __fmul_rn(out[d + l], out[d + l]));
+    float s = acc[0];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) s = __fadd_rn(s, acc[l]);
+    const float nrm = __fsqrt_rn(s);
+#pragma unroll
+    for (int d = 0; d < C; ++d) out[d] = __fdiv_rn(out[d], nrm);
+  };
+
+  // normalised B rows -> shared
+  for (int j = tid; j < tb; j += NT) {
+    float o[C];
+    normalise(mf + (size_t)(2 * j + 1) * C, o);
+#pragma unroll
+    for (int d = 0; d < C; d += 4) *reinterpret_cast<float4*>(Bs + (size_t)j * C + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+  }
+  __syncthreads();
+
+  const int halfT = NT / 2;
+  const int half = tid / halfT;
+  const int jlo = half == 0 ? 0 : (tb + 1) / 2, jhi = half == 0 ? (tb + 1) / 2 : tb;
+  for (int i = tid % halfT; i < ta; i += halfT) {
+    float a[C];
+    normalise(mf + (size_t)(2 * i) * C, a);
+    float best = -INFINITY;
+    int bidx = jlo;
+    int j = jlo;
+    for (; j + 4 <= jhi; j += 4) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float4* b0 = reinterpret_cast<const float4*>(Bs + (size_t)j * C);
+#pragma unroll
+      for (int d4 = 0; d4 < C / 4; ++d4) {
+        const float4 v0 = b0[d4], v1 = b0[C / 4 + d4], v2 = b0[2 * (C / 4) + d4], v3 = b0[3 * (C / 4) + d4];
+        const int d = d4 * 4;
+        s0 = __fmaf_rn(a[d], v0.x, s0); s0 = __fmaf_rn(a[d + 1], v0.y, s0); s0 = __fmaf_rn(a[d + 2], v0.z, s0); s0 = __fmaf_rn(a[d + 3], v0.w, s0);
+        s1 = __fmaf_rn(a[d], v1.x, s1); s1 = __fmaf_rn(a[d + 1], v1.y, s1); s1 = __fmaf_rn(a[d + 2], v1.z, s1); s1 = __fmaf_rn(a[d + 3], v1.w, s1);
+        s2 = __fmaf_rn(a[d], v2.x, s2); s2 = __fmaf_rn(a[d + 1], v2.y, s2); s2 = __fmaf_rn(a[d + 2], v2.z, s2); s2 = __fmaf_rn(a[d + 3], v2.w, s2);
+        s3 = __fmaf_rn(a[d], v3.x, s3); s3 = __fmaf_rn(a[d + 1], v3.y, s3); s3 = __fmaf_rn(a[d + 2], v3.z, s3); s3 = __fmaf_rn(a[d + 3], v3.w, s3);
+      }
+      if (s0 > best) { best = s0; bidx = j; }
+      if (s1 > best) { best = s1; bidx = j + 1; }
+      if (s2 > best) { best = s2; bidx = j + 2; }
+      if (s3 > best) { best = s3; bidx = j + 3; }
+    }
+    for (; j < jhi; ++j) {
+      float s0 = 0.f;
+      const float* b0 = Bs + (size_t)j * C;
+#pragma unroll
+      for (int d = 0; d < C; ++d) s0 = __fmaf_rn(a[d], b0[d], s0);
+      if (s0 > best) { best = s0; bidx = j; }
+    }
+    if (half == 0) { nmax[i] = best; nidx[i] = bidx; }
+    else { hmax[i] = best; hidx[i] = bidx; }
+  }
+  __syncthreads();
+  for (int i = tid; i < ta; i += NT) {
+    float m0 = nmax[i];
+    int i0 = nidx[i];
+    // the upper half of B only wins with a strictly larger score (first index on ties, merge.py:59)
+    if (hmax[i] > m0) { m0 = hmax[i]; i0 = hidx[i]; }
+    if (class_token && i == 0) { m0 = -INFINITY; i0 = 0; }     // merge.py:55: whole row -inf -> argmax 0
+    nmax[i] = m0;
+    nidx[i] = i0;
+  }
+  __syncthreads();
+  // descending, index-stable rank by counting
+  for (int i = tid; i < ta; i += NT) {
+    const float v = nmax[i];
+    int rk = 0;
+    for (int k = 0; k < ta; ++k) {
+      float u = nmax[k];
+      rk += (u > v) || (u == v && k < i);
+    }
+    rank[i] = rk;
+  }
+  __syncthreads();
+  const int n_unm = ta - r;
+  int* unm = unm_idx + (size_t)n * n_unm;
+  int* src = src_idx + (size_t)n * r;
+  int* dst = dst_idx + (size_t)n * r;
+  for (int i = tid; i < ta; i += NT) {
+    const int rk = rank[i];
+    if (rk < r) {
+      src[rk] = i;
+      dst[rk] = nidx[i];
+    } else if (!class_token) {
+      unm[rk - r] = i;                                         // stays in sorted-score order
+    } else {
+      int pos = 0;                                             // merge.py:66-68: ascending token order
+      for (int k = 0; k < i; ++k) pos += rank[k] >= r;
+      unm[pos] = i;
+    }
+  }
+}
+
+// ---- T2 + T3 ------------------------------------------------------------------------------------
+// grid (N, RS): CTA (n, s) writes output rows s, s+RS, ... of frame n.  A dst row scans the (<= r) edge
+// list held in shared memory for its sources, in ascending edge order (the CPU scatter order).
+// mode: QAT_TOME_WAVG  x*size summed, divided by the summed size (merge_wavg, merge.py:210-225)
+//       QAT_TOME_SUM / _MEAN / _AMAX  the bare `merge(x, mode)` closure (:70-80; mean = sum / (1 + #sources))
+enum { QAT_TOME_WAVG = 0, QAT_TOME_SUM = 1, QAT_TOME_MEAN = 2, QAT_TOME_AMAX = 3 };
+
+template <int V> struct TVec;
+template <> struct TVec<4> {
+  typedef float4 T;
+  static __device__ __forceinline__ T ld(const float* p) { return ldg_stream(reinterpret_cast<const float4*>(p)); }
+  static __device__ __forceinline__ void st(float* p, const T& v) { *reinterpret_cast<float4*>(p) = v; }
+};
+template <> struct TVec<1> {
+  typedef float T;
+  static __device__ __forceinline__ T ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ void st(float* p, const T& v) { *p = v; }
+};
+template <typename F> __device__ __forceinline__ float4 vmap(const float4& a, F f) { return make_float4(f(a.x), f(a.y), f(a.z), f(a.w)); }
+template <typename F> __device__ __forceinline__ float vmap(const float& a, F f) { return f(a); }
+template <typename F> __device__ __forceinline__ float4 vzip(const float4& a, const float4& b, F f) { return make_float4(f(a.x, b.x), f(a.y, b.y), f(a.z, b.z), f(a.w, b.w)); }
+template <typename F> __device__ __forceinline__ float vzip(const float& a, const float& b, F f) { return f(a, b); }
+
+template <int V>
+__global__ void __launch_bounds__(256) tome_merge_kernel(const float* __restrict__ x, const float* __restrict__ size, int t, int C, int r, int mode,
+                                                         const int* __restrict__ unm_idx, const int* __restrict__ src_idx,
+                                                         const int* __restrict__ dst_idx, float* __restrict__ x_out,
+                                                         float* __restrict__ size_out, int* __restrict__ group, int T0) {
+  extern __shared__ __align__(16) int smi[];
+  const int ta = (t + 1) / 2, tb = t / 2, n_unm = ta - r, t_out = t - r;
+  int* s_src = smi;               // [r]
+  int* s_dst = s_src + r;         // [r]
+  int* s_newpos = s_dst + r;      // [t]   (only when group != null)
+  const int n = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < r; k += blockDim.x) {
+    s_src[k] = src_idx[(size_t)n * r + k];
+    s_dst[k] = dst_idx[(size_t)n * r + k];
+  }
+  __syncthreads();
+  const float* xf = x + (size_t)n * t * C;
+  const bool wavg = mode == QAT_TOME_WAVG;
+  const float* sf = (wavg && size) ? size + (size_t)n * t : nullptr;
+  const int CV = C / V;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  typedef typename TVec<V>::T VT;
+  for (int row = blockIdx.y * nwarp + warp; row < t_out; row += gridDim.y * nwarp) {
+    float* xo = x_out + ((size_t)n * t_out + row) * C;
+    if (row < n_unm) {
+      const int tok = 2 * unm_idx[(size_t)n * n_unm + row];
+      const float s = sf ? sf[tok] : 1.f;
+      for (int c = lane; c < CV; c += 32) {
+        VT v = TVec<V>::ld(xf + (size_t)tok * C + c * V);
+        if (wavg) v = vmap(v, [s](float a) { return __fdiv_rn(__fmul_rn(a, s), s); });
+        TVec<V>::st(xo + c * V, v);
+      }
+      if (wavg && lane == 0) size_out[(size_t)n * t_out + row] = s;
+    } else {
+      const int j = row - n_unm;
+      const int tok = 2 * j + 1;
+      const float s0 = sf ? sf[tok] : 1.f;
+      float stot = s0;
+      for (int k = 0; k < r; ++k)
+        if (s_dst[k] == j) stot = __fadd_rn(stot, sf ? sf[2 * s_src[k]] : 1.f);
+      for (int c = lane; c < CV; c += 32) {
+        VT v = TVec<V>::ld(xf + (size_t)tok * C + c * V);
+        if (wavg) v = vmap(v, [s0](float a) { return __fmul_rn(a, s0); });
+        for (int k = 0; k < r; ++k) {
+          if (s_dst[k] == j) {
+            const int st = 2 * s_src[k];
+            VT u = TVec<V>::ld(xf + (size_t)st * C + c * V);
+            if (mode == QAT_TOME_AMAX) {
+              v = vzip(v, u, [](float a, float b) { return fmaxf(a, b); });
+            } else {
+              const float ss = sf ? sf[st] : 1.f;
+              if (wavg) u = vmap(u, [ss](float a) { return __fmul_rn(a, ss); });
+              v = vzip(v, u, [](float a, float b) { return __fadd_rn(a, b); });
+            }
+          }
+        }
+        if (wavg || mode == QAT_TOME_MEAN) v = vmap(v, [stot](float a) { return __fdiv_rn(a, stot); });
+        TVec<V>::st(xo + c * V, v);
+      }
+      if (wavg && lane == 0) size_out[(size_t)n * t_out + row] = stot;
+    }
+  }
+  if (group && blockIdx.y == 0) {
+    for (int j = tid; j < tb; j += blockDim.x) s_newpos[2 * j + 1] = n_unm + j;
+    for (int k = tid; k < n_unm; k += blockDim.x) s_newpos[2 * unm_idx[(size_t)n * n_unm + k]] = k;
+    for (int k = tid; k < r; k += blockDim.x) s_newpos[2 * s_src[k]] = n_unm + s_dst[k];
+    __syncthreads();
+    int* g = group + (size_t)n * T0;
+    for (int o = tid; o < T0; o += blockDim.x) g[o] = s_newpos[g[o]];
+  }
+}
+
+// ---- stand-in metric: mean over the C/64 channel groups --------------------
+__global__ void __launch_bounds__(256) tome_metric_kernel(const float* __restrict__ x, float* __restrict__ metric, long long tokens, int C) {
+  const int G = C / 64;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of one token's 64-vector
+  if (i >= tokens * 16) return;
+  const long long tok = i >> 4;
+  const int c4 = (int)(i & 15);
+  const float4* xr = reinterpret_cast<const float4*>(x + tok * C) + c4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int g = 0; g < G; ++g) {
+    float4 v = __ldg(xr + g * 16);
+    s.x = __fadd_rn(s.x, v.x); s.y = __fadd_rn(s.y, v.y); s.z = __fadd_rn(s.z, v.z); s.w = __fadd_rn(s.w, v.w);
+  }
+  const float d = (float)G;
+  s.x = __fdiv_rn(s.x, d); s.y = __fdiv_rn(s.y, d); s.z = __fdiv_rn(s.z, d); s.w = __fdiv_rn(s.w, d);
+  reinterpret_cast<float4*>(metric + tok * 64)[c4] = s;
+}
+
+__global__ void iota_rows_kernel(int* g, long long rows, int cols) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * cols) g[i] = (int)(i % cols);
+}
+
+inline size_t tome_match_smem(int t, int C) {
+  const int ta = (t + 1) / 2, tb = t / 2;
+  return (size_t)tb * C * 4 + (size_t)ta * 5 * 4 + 16;
+}
+
+inline int tome_match(Ctx& c, const float* metric, int N, int t, int C, int r, int class_token, int* unm, int* src, int* dst) {
+  QAT_REQUIRE(C == 64, "tome_match: metric channels C=%d unsupported (the ViT-L head dim 64 is built)", C);
+  QAT_REQUIRE(r > 0 && r <= tome_clamp_r(t, r, class_token), "tome_match: r=%d not clamped for t=%d", r, t);
+  size_t smem = tome_match_smem(t, C);
+  QAT_REQUIRE(smem <= 200 * 1024, "tome_match: t=%d too long for one CTA", t);
+  if (c.dry || N == 0) return QAT_OK;
+  if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(tome_match_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int ta = (t + 1) / 2;
+  int nt = ta <= 64 ? 128 : (ta <= 128 ? 256 : (ta <= 192 ? 384 : 640));
+  tome_match_kernel<64><<<N, nt, smem, c.stream>>>(metric, t, r, class_token, unm, src, dst);
+  return check_launch("tome_match_kernel");
+}
+
+inline int tome_merge(Ctx& c, const float* x, const float* size, int N, int t, int C, int r, int mode, const int* unm, const int* src,
+                      const int* dst, float* x_out, float* size_out, int* group, int T0) {
+  QAT_REQUIRE(mode >= QAT_TOME_WAVG && mode <= QAT_TOME_AMAX, "tome_merge: unknown mode %d", mode);
+  QAT_REQUIRE(r > 0 && r <= t / 2, "tome_merge: bad r=%d for t=%d", r, t);
+  QAT_REQUIRE(mode != QAT_TOME_WAVG || size_out, "tome_merge: size_out missing");
+  if (c.dry || N == 0) return QAT_OK;
+  int rs = 1;
+  while ((long long)N * rs < 148 * 4 && rs < 64) rs *= 2;
+  size_t smem = ((size_t)2 * r + t) * 4 + 16;
+  dim3 grid(N, rs);
+  const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out)) % 16 == 0);
+  if (vec)
+    tome_merge_kernel<4><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0);
+  else
+    tome_merge_kernel<1><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0);
+  return check_launch("tome_merge_kernel");
+}
+
+inline int tome_metric(Ctx& c, const float* x, float* metric, long long tokens, int C) {
+  QAT_REQUIRE(C % 64 == 0, "tome_metric: C=%d must be a multiple of 64", C);
+  if (c.dry || tokens == 0) return QAT_OK;
+  long long th = tokens * 16;
+  tome_metric_kernel<<<(unsigned)((th + 255) / 256), 256, 0, c.stream>>>(x, metric, tokens, C);
+  return check_launch("tome_metric_kernel");
+}
+
+}  // namespace qat

@@ -1,0 +1,133 @@
+"""Frozen CLIP text tower (mirror of /root/reference/src/models/encoders.py:7-37 and the text half of
+src/models/base/clip_base.py:186-254,300-460).  Out of kernel scope by BASELINE.json's north_star: it
+stays PyTorch.  Parameter names match the reference (`transformer.resblocks.N.{attn,ln_1,mlp.c_fc,
+mlp.c_proj,ln_2}`, `token_embedding`, `positional_embedding`, `ln_final`, `text_projection`,
+`logit_scale`) so a reference checkpoint / CLIP state_dict loads unchanged.
+
+Differences from the reference, all outside the parity contract:
+  * weights are looked up locally (`~/.cache/clip/<name>.pt`, a TorchScript or state_dict file) and
+    otherwise randomly initialised -- there is no download (`clip.py:39,125` fetches from the network);
+  * attention uses F.scaled_dot_product_attention(is_causal=True) instead of the additive -inf mask.
+"""
+from __future__ import annotations
+
+import os
+import warnings
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+# text-side dims: (embed_dim, context_length, vocab_size, width, heads, layers)
+_TEXT_DIMS = {
+    "ViT-L/14@336px": (768, 77, 49408, 768, 12, 12),
+    "ViT-L/14": (768, 77, 49408, 768, 12, 12),
+    "ViT-B/32": (512, 77, 49408, 512, 8, 12),
+    "ViT-B/16": (512, 77, 49408, 512, 8, 12),
+}
+
+
+class QuickGELU(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class ResidualAttentionBlock(nn.Module):
+    def __init__(self, d_model: int, n_head: int):
+        super().__init__()
+        self.attn = nn.MultiheadAttention(d_model, n_head)     # parameter holder; math below
+        self.ln_1 = nn.LayerNorm(d_model)
+        self.mlp = nn.Sequential(OrderedDict([
+            ("c_fc", nn.Linear(d_model, d_model * 4)), ("gelu", QuickGELU()), ("c_proj", nn.Linear(d_model * 4, d_model))]))
+        self.ln_2 = nn.LayerNorm(d_model)
+        self.n_head = n_head
+
+    def forward(self, x):                                        # x [B, L, W]
+        B, L, W = x.shape
+        y = F.layer_norm(x.float(), (W,), self.ln_1.weight.float(), self.ln_1.bias.float(), 1e-5).to(x.dtype)
+        qkv = F.linear(y, self.attn.in_proj_weight.to(x.dtype), self.attn.in_proj_bias.to(x.dtype))
+        q, k, v = qkv.view(B, L, 3, self.n_head, W // self.n_head).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, L, W)
+        x = x + F.linear(o, self.attn.out_proj.weight.to(x.dtype), self.attn.out_proj.bias.to(x.dtype))
+        y = F.layer_norm(x.float(), (W,), self.ln_2.weight.float(), self.ln_2.bias.float(), 1e-5).to(x.dtype)
+        y = F.linear(y, self.mlp.c_fc.weight.to(x.dtype), self.mlp.c_fc.bias.to(x.dtype))
+        y = y * torch.sigmoid(1.702 * y)
+        return x + F.linear(y, self.mlp.c_proj.weight.to(x.dtype), self.mlp.c_proj.bias.to(x.dtype))
+
+
+class Transformer(nn.Module):
+    def __init__(self, width: int, layers: int, heads: int):
+        super().__init__()
+        self.width, self.layers = width, layers
+        self.resblocks = nn.Sequential(*[ResidualAttentionBlock(width, heads) for _ in range(layers)])
+
+    def forward(self, x):
+        return self.resblocks(x)
+
+
+class CLIP_TEncoder(nn.Module):
+    """forward(text int[B,77]) -> (quest [B,embed], words [B,77,width])  (encoders.py:30-37)."""
+
+    def __init__(self, model_name: str):
+        super().__init__()
+        if model_name not in _TEXT_DIMS:
+            raise RuntimeError(f"unknown CLIP text tower {model_name}; known: {list(_TEXT_DIMS)}")
+        embed, ctx, vocab, width, heads, layers = _TEXT_DIMS[model_name]
+        self.dtype = torch.float32
+        self.transformer = Transformer(width, layers, heads)
+        self.vocab_size = vocab
+        self.token_embedding = nn.Embedding(vocab, width)
+        self.positional_embedding = nn.Parameter(torch.empty(ctx, width))
+        self.ln_final = nn.LayerNorm(width)
+        self.text_projection = nn.Parameter(torch.empty(width, embed))
+        self.logit_scale = nn.Parameter(torch.ones([]) * 2.6592)
+        nn.init.normal_(self.token_embedding.weight, std=0.02)
+        nn.init.normal_(self.positional_embedding, std=0.01)
+        nn.init.normal_(self.text_projection, std=width ** -0.5)
+        # 'fp32' keeps the 1e-3 logit gate (bf16 text features alone cost 3.9e-3); 'tf32'/'bf16' are faster
+        self.compute = "fp32"
+        self.dedup = False   # run the tower on unique token rows only (MUSIC-AVQA test: 33 unique questions)
+        self._try_load_local(model_name)
+
+    def _try_load_local(self, name: str):
+        path = os.path.expanduser(os.path.join("~/.cache/clip", name.replace("/", "-").replace("@", "-") + ".pt"))
+        if not os.path.exists(path):
+            warnings.warn(f"CLIP text weights not found at {path}; the text tower is randomly initialised "
+                          "(load a checkpoint with load_state_dict to get real answers)")
+            return
+        try:
+            sd = torch.jit.load(path, map_location="cpu").state_dict()
+        except RuntimeError:
+            sd = torch.load(path, map_location="cpu")
+        own = self.state_dict()
+        self.load_state_dict({k: v.float() for k, v in sd.items() if k in own}, strict=False)
+
+    def freeze(self):
+        for p in self.parameters():
+            p.requires_grad = False
+
+    def _tower(self, text: torch.Tensor):
+        dt = torch.bfloat16 if self.compute == "bf16" else torch.float32
+        x = self.token_embedding(text.long()) + self.positional_embedding[: text.shape[1]]
+        x = self.transformer(x.to(dt))
+        x = F.layer_norm(x.float(), (x.shape[-1],), self.ln_final.weight, self.ln_final.bias, 1e-5)
+        eot = text.long().argmax(dim=-1)
+        return x[torch.arange(x.shape[0], device=x.device), eot] @ self.text_projection, x
+
+    def forward(self, text: torch.Tensor):
+        if text.is_cuda and self.compute in ("fp32", "tf32"):
+            prev = torch.backends.cuda.matmul.allow_tf32
+            torch.backends.cuda.matmul.allow_tf32 = self.compute == "tf32"
+            try:
+                return self._forward(text)
+            finally:
+                torch.backends.cuda.matmul.allow_tf32 = prev
+        return self._forward(text)
+
+    def _forward(self, text):
+        if self.dedup:
+            uniq, inv = torch.unique(text, dim=0, return_inverse=True)
+            q, w = self._tower(uniq)
+            return q[inv], w[inv]
+        return self._tower(text)

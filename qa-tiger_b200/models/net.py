@@ -1,0 +1,91 @@
+"""Drop-in mirror of /root/reference/src/models/net.py:20-144 (QA_TIGER) on the B200 path.
+
+Same constructor signature, sub-module names (=> identical state_dict keys: the 136 hot-path keys +
+the 150 `quest_encoder.*` keys), construction order, `forward(reshaped_data) -> {'out': [B,42]}`.
+Differences (all inside the module, invisible to `trainutils.test`, trainutils.py:411-423):
+  * patch_proj (net.py:124) is fused into the PatchSelecter call;
+  * the second QstGrounding pass, ReLU and the head (net.py:138-142) are one C-ABI call.
+"""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+import torch.nn as nn
+from torch import Tensor
+
+from .encoders import CLIP_TEncoder
+from .modules import AVQCrossAttn, PatchSelecter, Projection, QstGrounding, TempMoE
+
+
+class QA_TIGER(nn.Module):
+    def __init__(self, d_model: int = 512, video_dim: int = 512, patch_dim: int = 768, audio_dim: int = 128,
+                 topK: int = 3, num_experts: int = 10, late_fusion: bool = False, nce_loss: bool = False,
+                 encoder_type: str = "ViT-L/14@336px", **kwargs):
+        super().__init__()
+        self.nce_loss = nce_loss
+        self.late_fusion = late_fusion
+        self.audio_proj = Projection(audio_dim, d_model)
+        self.video_proj = Projection(video_dim, d_model)
+        self.patch_proj = Projection(patch_dim, d_model)
+        self.words_proj = Projection(video_dim, d_model)
+        self.quest_proj = Projection(video_dim, d_model)
+        self.quest_encoder = CLIP_TEncoder(encoder_type)
+        self.quest_encoder.freeze()
+        self.crs_attn = AVQCrossAttn(d_model, 8)
+        self.patch_selecter = PatchSelecter(d_model, 8)
+        self.quest_grounding = QstGrounding(d_model, 8)
+        self.at_aggregator = TempMoE(d_model, 8, topK=topK, n_experts=num_experts)
+        self.vt_aggregator = TempMoE(d_model, 8, topK=topK, n_experts=num_experts, vis_branch=True)
+        self.head_act = nn.ReLU()
+        self.dropout = nn.Dropout(0.1)
+        self.head = nn.Linear(d_model, 42)
+        for m in (self.audio_proj, self.video_proj, self.words_proj, self.quest_proj, self.patch_proj, self.head):
+            m.apply(self.init_weight)
+
+    def init_weight(self, m):
+        if isinstance(m, nn.Linear):
+            nn.init.kaiming_normal_(m.weight)
+            if m.bias is not None:
+                nn.init.constant_(m.bias, 0)
+
+    def set_precision(self, name: str):
+        """'fp32' | 'bf16' for every block of the hot path (the text tower has its own `.compute`)."""
+        for m in self.modules():
+            if hasattr(m, "_prec"):
+                m.precision = name
+        return self
+
+    def sub_forward(self, reshaped_data: Dict[str, Tensor], prefix: str = ""):
+        quest = reshaped_data[f"{prefix}quest"]
+        audio = reshaped_data[f"{prefix}audio"]
+        video = reshaped_data[f"{prefix}video"]
+        patch = reshaped_data[f"{prefix}patch"] if f"{prefix}patch" in reshaped_data else None
+        if prefix == "n_":
+            words, quest = None, None
+        elif quest.dtype in (torch.float32, torch.float64):
+            # the reference sets words=None here and then crashes at net.py:122; be explicit instead
+            raise RuntimeError("QA_TIGER: `quest` must be CLIP token ids (int [B,77]); pre-computed float question "
+                               "features go through forward_features(quest768, words768, ...)")
+        else:
+            quest, words = self.quest_encoder(quest)
+            quest = quest.squeeze(1)
+        return quest, words, audio, video, patch
+
+    def forward_features(self, quest: Tensor, words: Tensor, audio: Tensor, video: Tensor, patch: Tensor) -> Tensor:
+        """The hot path proper (net.py:120-142) on text-tower outputs quest [B,768], words [B,77,768]."""
+        audio = self.audio_proj(audio)
+        video = self.video_proj(video)
+        words = self.words_proj(words.contiguous())
+        quest = self.quest_proj(quest.contiguous())
+        audio, video = self.crs_attn(audio, video, words)
+        patch = self.patch_selecter(patch, audio, video, proj=self.patch_proj)
+        a_global = self.at_aggregator(quest, audio)
+        ap_global, vp_global = self.vt_aggregator(quest, video, patch)
+        fusion = self.quest_grounding(quest, [ap_global, vp_global])
+        _, logits = self.quest_grounding(quest, [fusion.unsqueeze(1), a_global], head=self.head)
+        return logits
+
+    def forward(self, reshaped_data: Dict[str, Tensor]):
+        quest, words, audio, video, patch = self.sub_forward(reshaped_data, prefix="")
+        return {"out": self.forward_features(quest, words, audio, video, patch)}
