@@ -23,13 +23,15 @@ struct AttnP {
 };
 
 constexpr int HD = 64;
+// floats taken by a [Lk][65] K tile, rounded up so the V tile behind it stays 16-byte aligned
+__host__ __device__ inline int ks_floats(int Lk) { return (Lk * 65 + 3) & ~3; }
 
 // ---- one CTA (4 warps) per (sequence, head); Lk <= 128 --------------------------------------------
 __global__ void __launch_bounds__(128) attn_block_kernel(AttnP p) {
   extern __shared__ __align__(16) float smem[];
   const int Lk = p.Lk;
   float* Ks = smem;                   // [Lk][65]
-  float* Vs = Ks + Lk * 65;           // [Lk][64]
+  float* Vs = Ks + ks_floats(Lk);     // [Lk][64]
   float* Ps = Vs + Lk * 64;           // [4][128]
   const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
   const int kn = (n + p.k_shift) % p.k_mod;
@@ -105,8 +107,8 @@ __global__ void __launch_bounds__(32 * WPB) attn_warp_kernel(AttnP p) {
   if (prob >= (long long)p.nseq * p.H) return;
   const int n = (int)(prob / p.H), h = (int)(prob % p.H);
   const int kn = (n + p.k_shift) % p.k_mod;
-  float* Ks = smem + w * (Lk * (65 + 64));  // [Lk][65]
-  float* Vs = Ks + Lk * 65;                 // [Lk][64]
+  float* Ks = smem + w * (ks_floats(Lk) + Lk * 64);  // [Lk][65]
+  float* Vs = Ks + ks_floats(Lk);                    // [Lk][64]
   const float* kb = p.k + kn * p.k_sn + h * HD;
   const float* vb = p.v + kn * p.k_sn + h * HD;
   for (int f = lane; f < Lk * 16; f += 32) {
@@ -152,14 +154,14 @@ inline int attention(Ctx& c, const AttnP& p) {
   if (c.dry || p.nseq == 0) return QAT_OK;
   if (p.Lk <= 32) {
     constexpr int WPB = 8;
-    size_t smem = size_t(WPB) * p.Lk * (65 + 64) * 4;
+    size_t smem = size_t(WPB) * (ks_floats(p.Lk) + p.Lk * 64) * 4;
     if (smem > 48 * 1024)
       QAT_CUDA(cudaFuncSetAttribute(attn_warp_kernel<WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long probs = (long long)p.nseq * p.H;
     attn_warp_kernel<WPB><<<(unsigned)((probs + WPB - 1) / WPB), 32 * WPB, smem, c.stream>>>(p);
     return check_launch("attn_warp_kernel");
   }
-  size_t smem = (size_t(p.Lk) * (65 + 64) + 4 * 128) * 4;
+  size_t smem = (size_t(ks_floats(p.Lk)) + size_t(p.Lk) * 64 + 4 * 128) * 4;
   if (smem > 48 * 1024)
     QAT_CUDA(cudaFuncSetAttribute(attn_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   attn_block_kernel<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
