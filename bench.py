@@ -1,0 +1,368 @@
+"""bench.py -- questions/sec of the QA-TIGER eval hot path on N x B200 (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--precision bf16|fp32] [--batch 256]
+  python bench.py --impl reference ...      # the reference algorithm's CPU port, timed on the host cores
+
+One "step" = one pass of the hot path (net.py:120-142 = SURVEY 8a rows P1,A1-A3,S1,M1-M4,G1,H1) over one
+synthetic MUSIC-AVQA-shaped batch of `--batch` questions per GPU (configs[1]: bs=256, T=60, bf16 mode).
+  value : whole-job questions/s, inputs resident in HBM (text-tower outputs precomputed: the frozen CLIP
+          tower is outside the kernel scope), device-timed, max over ranks.
+  e2e   : the same metric through the public API `QA_TIGER.forward(reshaped_data)` from PINNED HOST
+          buffers: H2D of the batch + text tower (PyTorch) + hot path + argmax + D2H, every step.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+For N>1 launch with torchrun (one rank per GPU); ranks only meet in a barrier and a MAX all-reduce of the
+elapsed time (the path shards by question, no data-path collective).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+import warnings
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "questions/sec"
+T, P, E, K_TOP = 60, 14, 7, 7
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d["bf16_tflops_sustained"], "measured (MEASURED_PEAKS.json)"
+    return 6650.0, 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_forward(B: int, reps: int, warm: int, with_text: bool):
+    """The reference algorithm's CPU port (oracle/qat_oracle.py, pinned against the real reference by
+    tests/golden/) on the host cores.  Returns (q/s, threads, seconds per forward)."""
+    import torch
+
+    from oracle import qat_oracle as O
+    from oracle import synth
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.make_state_dict(713, num_experts=E)
+    batch = synth.make_batch(1, B, T)
+    with torch.no_grad():
+        tf = None if with_text else O.clip_text_encoder(sd, "quest_encoder", batch["quest"])
+        ts = []
+        for i in range(warm + reps):
+            t0 = time.perf_counter()
+            O.qa_tiger_forward(sd, batch, K=K_TOP, E=E, text_feats=tf)
+            if i >= warm:
+                ts.append(time.perf_counter() - t0)
+    med = statistics.median(ts)
+    return B / med, torch.get_num_threads(), med
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B = 8
+    t0 = time.perf_counter()
+    qps, cores, sec = cpu_reference_forward(B, max(1, args.steps), max(1, min(args.warmup, 3)), with_text=False)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": qps, "unit": "questions/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "QA-TIGER eval forward hot path (net.py:120-142), synthetic MUSIC-AVQA batch, T=60, E=K=7",
+                   "sample": f"B={B} questions per step (configs[0], the reference's own CPU-runnable case)",
+                   "text_tower": "excluded (precomputed), as in the GPU arm's `value`"},
+        "cpu_baseline": {"value": qps, "unit": "questions/s", "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} forwards of B={B}, T=60 after {min(args.warmup, 3)} warm-up; oracle/qat_oracle.py "
+                                   "(CPU restatement pinned to reference-generated goldens; the reference itself is "
+                                   "Python and cannot travel to the GPU box)"},
+        "e2e": {"value": qps, "unit": "questions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from oracle import synth          # seeded weights/batches only (no oracle math on this path)
+    from qa_tiger_b200 import _cabi
+    from qa_tiger_b200.models.net import QA_TIGER
+    from qa_tiger_b200.models.modules import gauss_reduce
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU for --impl ours (there is no CPU fallback); use --impl reference on CPU")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _cabi.lib()
+    B = args.batch
+    hbm_peak, tf_burst, tf_sust, peak_src = peaks()
+
+    sd = synth.make_state_dict(713, num_experts=E)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = QA_TIGER(d_model=512, video_dim=768, patch_dim=1024, audio_dim=128, topK=K_TOP, num_experts=E)
+    model.load_state_dict(sd)
+    model = model.to(dev).eval().set_precision(args.precision)
+
+    # ---- synthetic batch of this rank (seed = 1234 + rank: every rank has its own questions) ----------
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    audio = torch.randn(B, T, 128, device=dev, generator=g)
+    video = torch.randn(B, T, 768, device=dev, generator=g)
+    patch = torch.randn(B, T, P, 1024, device=dev, generator=g)
+    quest = synth.make_batch(1234 + rank, B, T, with_patch=False)["quest"].to(dev)
+    with torch.no_grad():
+        q768, w768 = model.quest_encoder(quest)
+        q768, w768 = q768.contiguous(), w768.contiguous()
+
+    def hot():
+        return model.forward_features(q768, w768, audio, video, patch)
+
+    lib = _cabi.lib()
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            out = hot()
+        torch.cuda.synchronize()
+        lib.qat_launch_count(1)
+        hot()
+        launches_per_step = lib.qat_launch_count(1)
+        # CUDA graph of the whole hot path (the library never allocates or synchronises => capturable)
+        graph = None
+        if not args.no_graph:
+            try:
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    hot()
+                torch.cuda.current_stream().wait_stream(s)
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    gout = hot()
+                graph.replay()
+                torch.cuda.synchronize()
+                if not torch.equal(gout, out):
+                    graph = None
+            except Exception as e:   # noqa: BLE001 -- report, then time the eager path
+                sys.stderr.write(f"[bench] CUDA graph capture failed ({e}); timing eager launches\n")
+                graph = None
+                torch.cuda.synchronize()
+
+        def step():
+            if graph is not None:
+                graph.replay()
+            else:
+                hot()
+
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+
+        # ---- e2e: public API from pinned host memory, text tower included ---------------------------
+        host = {k: v.cpu().pin_memory() for k, v in (("quest", quest), ("audio", audio), ("video", video), ("patch", patch))}
+        h2d = sum(v.numel() * v.element_size() for v in host.values())
+        pred_host = torch.empty(B, dtype=torch.int64).pin_memory()
+
+        def e2e_step():
+            data = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+            o = model(data)["out"]
+            pred_host.copy_(o.argmax(1), non_blocking=True)
+
+        e2e_steps = max(3, min(args.steps, 10))
+        for _ in range(2):
+            e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(e2e_steps):
+            e2e_step()
+        f1.record()
+        torch.cuda.synchronize()
+        ms_e2e = f0.elapsed_time(f1)
+
+        # ---- per-kernel rooflines, timed live with CUDA events on the launching stream ---------------
+        def time_ms(fn, n=20, warm=3):
+            for _ in range(warm):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+
+        rooflines = {}
+        if rank == 0:
+            # (1) fused Gaussian-expert kernel, reference layout [T,B,E,C] (E*T*C*s bytes per question)
+            for nm, dt, s in (("gauss_reduce_f32", torch.float32, 4), ("gauss_reduce_bf16", torch.bfloat16, 2)):
+                xs = [torch.randn(T, B, E, 512, device=dev).to(dt) for _ in range(3)]   # 3 x 110/220 MB rotate > L2
+                rl, gr = torch.randn(B, E, device=dev), torch.randn(B, 2 * E, device=dev)
+                it = [0]
+
+                def fn():
+                    it[0] += 1
+                    gauss_reduce(xs[it[0] % 3], rl, gr, K_TOP)
+                t_ms = time_ms(fn)
+                byts = B * (E * T * 512 * s + 3 * E * 4 + 512 * 4) + T * K_TOP * 0
+                ach = byts / (t_ms * 1e-3) / 1e9
+                rooflines[nm] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                 "traffic": None, "ms": t_ms, "bytes": byts}
+                del xs
+            # (2) the two tensor-core GEMM kinds at the largest shapes of the step (nominal 2*M*N*K FLOPs):
+            #     tf32 : PatchSelecter self-attention in-proj [B*T*P,512] x [1536,512]^T  (peak = sustained bf16 / 2)
+            #     bf16x3: AVQ packed in-proj [B*T,512] x [3584,512]^T, 3 MMAs per product (peak = sustained bf16 / 3)
+            ps = model.patch_selecter._prepared(_cabi.PREC_BF16)
+            cr = model.crs_attn._prepared(_cabi.PREC_BF16)
+            for nm, kind, lin, M_, div in (("gemm_tf32_patch_slf_in", _cabi.GEMM_TF32, ps["slf_in"], B * T * P, 2.0),
+                                           ("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], B * T, 3.0)):
+                N_, K_ = lin.w.shape
+                xin = torch.randn(M_, K_, device=dev)
+                planes = _cabi.split_planes(xin) if kind == _cabi.GEMM_BF16X3 else None
+                t_ms = time_ms(lambda: _cabi.gemm(kind, xin, lin, a_planes=planes), n=10)
+                fl = 2.0 * M_ * N_ * K_
+                ach = fl / (t_ms * 1e-3) / 1e12
+                rooflines[nm] = {"bound": "tensor", "achieved": ach, "peak": tf_sust / div, "unit": "TFLOP/s",
+                                 "frac": ach / (tf_sust / div), "traffic": None, "ms": t_ms, "shape": [M_, N_, K_],
+                                 "note": f"nominal FLOPs; peak = sustained bf16 / {div:g} (includes the torch.empty of the output)"}
+                del xin, planes
+
+    tmax = torch.tensor([ms, ms_e2e / e2e_steps * args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms_max, ms_e2e_max = float(tmax[0]), float(tmax[1]) / args.steps
+    if rank == 0:
+        qps = world * B * args.steps / (ms_max * 1e-3)
+        qps_e2e = world * B / (ms_e2e_max * 1e-3)
+        flops_q = 5.618e9            # nominal hot-path FLOPs per question
+        step_ms = ms_max / args.steps
+        line = {
+            "metric": METRIC, "value": qps, "unit": "questions/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": "QA-TIGER eval forward bs=256 T=60 (configs[1]): hot path net.py:120-142, E=K=7, P=14",
+                       "per_gpu_batch": B, "precision_mode": args.precision,
+                       "arithmetic": "tcgen05 kind::f16 bf16 hi+lo x3 (serial chain) + kind::tf32 (patch path), fp32 accumulate; "
+                                     "router/Gaussian/rank path fp32" if args.precision == "bf16" else "fp32 FFMA",
+                       "text_tower": "excluded from `value` (frozen CLIP, PyTorch, out of kernel scope: SURVEY 8a/8d; features "
+                                     "precomputed and resident); included in `e2e`",
+                       "l2": "inputs per step (881 MB patch + 54 MB other) exceed the 126 MB L2; no explicit flush",
+                       "cuda_graph": graph is not None, "parallelism": f"dp{world}, contiguous shards, no data-path collective"},
+            "clocks": clocks,
+            "e2e": {"value": qps_e2e, "unit": "questions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
+                    "ms_per_step": ms_e2e_max, "includes": "H2D from pinned host, CLIP text tower (torch fp32), hot path, argmax, D2H"},
+            "gpu_launches": launches_per_step * args.steps,
+            "launches_per_step": launches_per_step,
+            "hot_path_tensor_frac_nominal": (flops_q * B / (step_ms * 1e-3)) / (tf_sust * 1e12),
+            "peaks": {"hbm_gbs": hbm_peak, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sust, "source": peak_src},
+        }
+        # headline roofline = the kernel north_star names for the HBM class; the tensor-class GEMM rides along
+        key = "gauss_reduce_f32"
+        line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
+        line["roofline"]["kernel"] = "gauss_reduce_kernel<float4> (qat_gauss_reduce_fwd, [T,B,E,C] fp32, B=256)"
+        line["rooflines_all"] = rooflines
+        if world == 1 and not args.no_cpu_baseline:
+            qps_cpu, cores, sec = cpu_reference_forward(8, 5, 2, with_text=False)
+            qps_cpu_t, _, sec_t = cpu_reference_forward(8, 3, 1, with_text=True)
+            line["cpu_baseline"] = {"value": qps_cpu, "unit": "questions/s", "cores": cores, "kind": "port",
+                                    "sample": "5 forwards of B=8,T=60 (configs[0]) after 2 warm-up, hot path only; "
+                                              f"with the text tower: {qps_cpu_t:.1f} questions/s",
+                                    "with_text_tower": qps_cpu_t}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -77,6 +77,30 @@ typedef struct {
 } QatLinearArgs;
 int qat_linear_fwd(const QatLinearArgs* a);
 
+/* ---- one dense contraction on a chosen engine (building block of every entry point below; exported for
+ *      parity tests and roofline timing of the GEMM kernels in isolation) ------------------------- */
+enum { QAT_GEMM_SIMT = 0,   /* fp32 FFMA, reads a / w.w */
+       QAT_GEMM_TF32 = 1,   /* tcgen05 kind::tf32, reads a / w.w */
+       QAT_GEMM_BF16X3 = 2  /* tcgen05 kind::f16 x3, reads (a_hi, a_lo) / (w.w_hi, w.w_lo) */ };
+typedef struct {
+  int32_t kind;
+  int32_t M;
+  void* stream;
+  const float* a;      /* [M, lda] fp32 (SIMT, TF32) */
+  const void* a_hi;    /* [M, lda] bf16 planes (BF16X3) */
+  const void* a_lo;
+  int32_t lda;
+  QatLinearW w;        /* [n, k] */
+  int32_t relu;
+  const float* res;    /* optional residual [M, ldr], added after the activation */
+  int32_t ldr;
+  float* c;            /* any of the three outputs may be NULL */
+  void* c_hi;
+  void* c_lo;
+  int32_t ldc;
+} QatGemmArgs;
+int qat_gemm(const QatGemmArgs* a);
+
 /* ---- A1-A3: AVQCrossAttn.forward, modules.py:239-265 (sub_forward :194-237) ----------------- */
 typedef struct {
   int32_t B, T, L, D, H; /* T frames, L words; D = H*64 */

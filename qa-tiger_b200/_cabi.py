@@ -35,6 +35,12 @@ class LinearArgs(C.Structure):
                 ("workspace_bytes", C.c_size_t)]
 
 
+class GemmArgs(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("M", C.c_int32), ("stream", C.c_void_p), ("a", C.c_void_p), ("a_hi", C.c_void_p),
+                ("a_lo", C.c_void_p), ("lda", C.c_int32), ("w", LinearW), ("relu", C.c_int32), ("res", C.c_void_p),
+                ("ldr", C.c_int32), ("c", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("ldc", C.c_int32)]
+
+
 class AvqArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32), ("D", C.c_int32), ("H", C.c_int32),
                 ("prec", C.c_int32), ("stream", C.c_void_p),
@@ -106,6 +112,7 @@ class TomeChainArgs(C.Structure):
 
 
 EXPORTS = {
+    "qat_gemm": (C.c_int, [C.POINTER(GemmArgs)]),
     "qat_linear_fwd": (C.c_int, [C.POINTER(LinearArgs)]),
     "qat_avq_cross_attn_fwd": (C.c_int, [C.POINTER(AvqArgs)]),
     "qat_patch_select_fwd": (C.c_int, [C.POINTER(PatchArgs)]),
@@ -197,6 +204,42 @@ class LN:
 
 def params_version(module: torch.nn.Module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=True))
+
+
+GEMM_SIMT, GEMM_TF32, GEMM_BF16X3 = 0, 1, 2
+
+
+def split_planes(x: torch.Tensor):
+    hi = x.to(torch.bfloat16)
+    return hi, (x - hi.float()).to(torch.bfloat16)
+
+
+def gemm(kind: int, a: torch.Tensor, lin: "Lin", relu: bool = False, res: Optional[torch.Tensor] = None,
+         out_planes: bool = False, a_planes=None):
+    """One contraction C = act(A W^T + b) + res on the chosen engine (parity tests / roofline timing)."""
+    M, K = a.shape
+    N = lin.w.shape[0]
+    dev = a.device
+    g = GemmArgs()
+    g.kind, g.M, g.stream, g.lda, g.w, g.relu, g.ldc = kind, M, stream_ptr(dev), a.stride(0), lin.c, int(relu), N
+    hold = []
+    if kind == GEMM_BF16X3:
+        hi, lo = a_planes if a_planes is not None else split_planes(a)
+        hold += [hi, lo]
+        g.a_hi, g.a_lo = hi.data_ptr(), lo.data_ptr()
+    else:
+        g.a = a.data_ptr()
+    if res is not None:
+        g.res, g.ldr = res.data_ptr(), res.stride(0)
+    c = torch.empty(M, N, device=dev, dtype=torch.float32)
+    g.c = c.data_ptr()
+    planes = None
+    if out_planes:
+        planes = (torch.empty(M, N, device=dev, dtype=torch.bfloat16), torch.empty(M, N, device=dev, dtype=torch.bfloat16))
+        g.c_hi, g.c_lo = planes[0].data_ptr(), planes[1].data_ptr()
+    with torch.cuda.device(dev):
+        check(lib().qat_gemm(C.byref(g)), "qat_gemm")
+    return (c, planes) if out_planes else c
 
 
 # ---- workspace ----------------------------------------------------------------------------------

@@ -115,6 +115,25 @@ static int run_linear(const QatLinearArgs* a, Ctx& c) {
   return gemm(c, kind, X, a->rows, W, e, act_of(a->y, W.n));
 }
 
+static int run_gemm(const QatGemmArgs* a, Ctx& c) {
+  QAT_REQUIRE(a->kind >= G_SIMT && a->kind <= G_BF16X3, "gemm: unknown kind %d", a->kind);
+  QAT_REQUIRE(a->M >= 0 && a->w.n > 0 && a->w.k > 0 && a->lda >= a->w.k && a->ldc >= a->w.n, "gemm: bad shape");
+  Act A, C;
+  A.f = const_cast<float*>(a->a);
+  A.hi = reinterpret_cast<bf16*>(const_cast<void*>(a->a_hi));
+  A.lo = reinterpret_cast<bf16*>(const_cast<void*>(a->a_lo));
+  A.ld = a->lda;
+  C.f = a->c;
+  C.hi = reinterpret_cast<bf16*>(a->c_hi);
+  C.lo = reinterpret_cast<bf16*>(a->c_lo);
+  C.ld = a->ldc;
+  Epi e;
+  e.relu = a->relu;
+  e.res = a->res;
+  e.ldr = a->ldr;
+  return gemm(c, (GemmKind)a->kind, A, a->M, wview(a->w), e, C);
+}
+
 // =================================================================================================
 // A1-A3  AVQCrossAttn
 // =================================================================================================
@@ -560,6 +579,7 @@ using namespace qat;
 
 extern "C" {
 
+int qat_gemm(const QatGemmArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, run_gemm); }
 int qat_linear_fwd(const QatLinearArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_linear); }
 int qat_avq_cross_attn_fwd(const QatAvqArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_avq); }
 int qat_patch_select_fwd(const QatPatchArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_patch); }

@@ -33,7 +33,7 @@ def test_header_symbols_are_exported():
 def test_struct_layout_matches_c(tmp_path):
     """Compile a tiny C program against qat.h that prints sizeof/offsetof and compare with ctypes."""
     from qa_tiger_b200 import _cabi
-    pairs = {"QatLinearW": _cabi.LinearW, "QatLinearArgs": _cabi.LinearArgs, "QatAvqArgs": _cabi.AvqArgs,
+    pairs = {"QatLinearW": _cabi.LinearW, "QatGemmArgs": _cabi.GemmArgs, "QatLinearArgs": _cabi.LinearArgs, "QatAvqArgs": _cabi.AvqArgs,
              "QatPatchArgs": _cabi.PatchArgs, "QatGaussArgs": _cabi.GaussArgs, "QatMoeArgs": _cabi.MoeArgs,
              "QatGroundArgs": _cabi.GroundArgs, "QatTomeMatchArgs": _cabi.TomeMatchArgs,
              "QatTomeMergeArgs": _cabi.TomeMergeArgs, "QatTomeChainArgs": _cabi.TomeChainArgs}

@@ -1,0 +1,46 @@
+"""GPU parity of the three GEMM engines (fp32 FFMA, tcgen05 tf32, tcgen05 bf16x3) against an fp64 torch
+reference, over tile tails in M, N and K, with bias / ReLU / residual epilogues and bf16-plane outputs."""
+import pytest
+import torch
+
+from gpu_util import dev, relerr
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [(128, 128, 64), (1, 8, 32), (130, 72, 96), (1000, 512, 512), (4096, 1536, 512), (333, 3584, 512), (257, 256, 1856),
+          (15360, 1792, 512), (2048, 512, 1024), (640, 1024, 768), (300, 512, 128)]
+
+
+@pytest.mark.parametrize("kind,tol", [(0, 2e-6), (1, 1.5e-3), (2, 2e-5)])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_gemm_kinds(kind, tol, M, N, K):
+    from qa_tiger_b200 import _cabi
+    if kind == 0 and K % 16:
+        pytest.skip("SIMT engine wants K % 16 == 0")
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev(), generator=g)
+    w = torch.randn(N, K, device=dev(), generator=g) * K ** -0.5
+    b = torch.randn(N, device=dev(), generator=g)
+    res = torch.randn(M, N, device=dev(), generator=g)
+    lin = _cabi.Lin(w, b, _cabi.PREC_BF16)
+    ref = a.double() @ w.double().t() + b.double()
+    got = _cabi.gemm(kind, a, lin)
+    assert relerr(got, ref) < tol
+    got2, (hi, lo) = _cabi.gemm(kind, a, lin, relu=True, res=res, out_planes=True)
+    ref2 = torch.relu(ref) + res.double()
+    assert relerr(got2, ref2) < tol
+    assert relerr(hi.float() + lo.float(), got2) < 1e-4
+    assert torch.equal(hi, got2.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("bn", ["128", "256"])
+def test_gemm_tile_widths(bn, monkeypatch):
+    from qa_tiger_b200 import _cabi
+    monkeypatch.setenv("QAT_GEMM_BN", bn)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a = torch.randn(777, 512, device=dev(), generator=g)
+    w = torch.randn(1024, 512, device=dev(), generator=g) * 512 ** -0.5
+    lin = _cabi.Lin(w, None, _cabi.PREC_BF16)
+    ref = a.double() @ w.double().t()
+    assert relerr(_cabi.gemm(2, a, lin), ref) < 2e-5
+    assert relerr(_cabi.gemm(1, a, lin), ref) < 1.5e-3
