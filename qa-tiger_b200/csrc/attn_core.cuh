@@ -148,10 +148,177 @@ __global__ void __launch_bounds__(32 * WPB) attn_warp_kernel(AttnP p) {
   }
 }
 
+// ---- one THREAD per query row; short sequences (Lq, Lk <= 16), e.g. the 14 patch tokens of a frame ----
+// A CTA owns one sequence and all its heads: K and V of every head are staged once in shared memory with
+// cp.async; a thread keeps its q row, its <=16 scores and its output row in registers, so the softmax
+// needs no shuffles and every K/V shared-memory read is a 128-bit broadcast.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+constexpr int ROWS_MAXL = 16;
+
+__global__ void __launch_bounds__(128) attn_rows_kernel(AttnP p) {
+  extern __shared__ __align__(16) float smem[];
+  const int Lq = p.Lq, Lk = p.Lk, H = p.H;
+  const int n = blockIdx.x;
+  const int kn = (n + p.k_shift) % p.k_mod;
+  const int blk = Lk * HD + 4;                       // +4 floats: heads land on different banks
+  float* Ks = smem;                                  // [H][Lk][64] (+pad)
+  float* Vs = Ks + H * blk;
+  const int tid = threadIdx.x;
+  const float* kb = p.k + kn * p.k_sn;
+  const float* vb = p.v + kn * p.k_sn;
+  for (int f = tid; f < H * Lk * 16; f += blockDim.x) {
+    const int c4 = f & 15, hj = f >> 4;
+    const int j = hj % Lk, h = hj / Lk;
+    cp_async16(Ks + h * blk + j * HD + c4 * 4, kb + j * p.k_si + h * HD + c4 * 4);
+    cp_async16(Vs + h * blk + j * HD + c4 * 4, vb + j * p.k_si + h * HD + c4 * 4);
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  // blockDim >= H*Lq (host check): one row per thread, idle threads only help with the staging above
+  const int r = tid;
+  const bool active = r < H * Lq;
+  const int h = active ? r / Lq : 0, i = active ? r % Lq : 0;
+  float q[HD];
+  if (active) {
+    const float4* qr = reinterpret_cast<const float4*>(p.q + n * p.q_sn + i * p.q_si + h * HD);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float4 t = __ldg(qr + c);
+      q[4 * c] = t.x * p.scale; q[4 * c + 1] = t.y * p.scale; q[4 * c + 2] = t.z * p.scale; q[4 * c + 3] = t.w * p.scale;
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (active) {
+    float sc[ROWS_MAXL];
+    const float* kh = Ks + h * blk;
+#pragma unroll
+    for (int j = 0; j < ROWS_MAXL; ++j) {
+      if (j < Lk) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        const float4* kr = reinterpret_cast<const float4*>(kh + j * HD);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 t = kr[c];
+          a0 = fmaf(q[4 * c], t.x, a0); a1 = fmaf(q[4 * c + 1], t.y, a1);
+          a2 = fmaf(q[4 * c + 2], t.z, a2); a3 = fmaf(q[4 * c + 3], t.w, a3);
+        }
+        sc[j] = (a0 + a1) + (a2 + a3);
+      } else {
+        sc[j] = -INFINITY;
+      }
+    }
+    float mx = sc[0];
+#pragma unroll
+    for (int j = 1; j < ROWS_MAXL; ++j) mx = fmaxf(mx, sc[j]);
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < ROWS_MAXL; ++j) {
+      sc[j] = j < Lk ? expf(sc[j] - mx) : 0.f;
+      sum += sc[j];
+    }
+    const float inv = 1.f / sum;
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    const float* vh = Vs + h * blk;
+#pragma unroll
+    for (int j = 0; j < ROWS_MAXL; ++j) {
+      if (j < Lk) {
+        const float pj = sc[j] * inv;
+        if (p.attw) atomicAdd(p.attw + ((long long)n * Lq + i) * Lk + j, pj / H);
+        const float4* vr = reinterpret_cast<const float4*>(vh + j * HD);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          float4 t = vr[c];
+          o[4 * c] = fmaf(pj, t.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, t.y, o[4 * c + 1]);
+          o[4 * c + 2] = fmaf(pj, t.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, t.w, o[4 * c + 3]);
+        }
+      }
+    }
+    const long long row = n * p.o_rn + i * p.o_ri;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) act_store4(p.o, row, h * HD + 4 * c, make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]));
+  }
+}
+
+// ---- one WARP per (sequence, head), LQ <= 2 query rows, any Lk: streaming, single pass -------------
+// Lane l owns dims (2l, 2l+1): K and V rows are read once, coalesced (256 B per row), scores meet through
+// xor-shuffles, the softmax is the online (running max / running sum) form, exact up to fp32 rounding.
+template <int LQ>
+__global__ void __launch_bounds__(256) attn_fewq_kernel(AttnP p) {
+  const int lane = threadIdx.x & 31;
+  const long long prob = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (prob >= (long long)p.nseq * p.H) return;
+  const int n = (int)(prob / p.H), h = (int)(prob % p.H);
+  const int kn = (n + p.k_shift) % p.k_mod;
+  const float* kb = p.k + kn * p.k_sn + h * HD + 2 * lane;
+  const float* vb = p.v + kn * p.k_sn + h * HD + 2 * lane;
+  float2 q[LQ], o[LQ];
+  float m[LQ], l[LQ];
+#pragma unroll
+  for (int i = 0; i < LQ; ++i) {
+    float2 t = __ldg(reinterpret_cast<const float2*>(p.q + n * p.q_sn + i * p.q_si + h * HD + 2 * lane));
+    q[i] = make_float2(t.x * p.scale, t.y * p.scale);
+    o[i] = make_float2(0.f, 0.f);
+    m[i] = -INFINITY;
+    l[i] = 0.f;
+  }
+  const int Lk = p.Lk;
+  constexpr int UN = 4;
+  for (int j0 = 0; j0 < Lk; j0 += UN) {
+    float2 kk[UN], vv[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int j = j0 + u < Lk ? j0 + u : Lk - 1;
+      kk[u] = __ldg(reinterpret_cast<const float2*>(kb + j * p.k_si));
+      vv[u] = __ldg(reinterpret_cast<const float2*>(vb + j * p.k_si));
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      if (j0 + u < Lk) {
+#pragma unroll
+        for (int i = 0; i < LQ; ++i) {
+          float s = warp_sum(fmaf(q[i].x, kk[u].x, q[i].y * kk[u].y));
+          const float mn = fmaxf(m[i], s);
+          const float corr = expf(m[i] - mn);        // exp(-inf) = 0 on the first key
+          const float e = expf(s - mn);
+          l[i] = l[i] * corr + e;
+          o[i].x = fmaf(e, vv[u].x, o[i].x * corr);
+          o[i].y = fmaf(e, vv[u].y, o[i].y * corr);
+          m[i] = mn;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LQ; ++i) {
+    const long long row = n * p.o_rn + i * p.o_ri;
+    const float inv = 1.f / l[i];
+    act_store1(p.o, row, h * HD + 2 * lane, o[i].x * inv);
+    act_store1(p.o, row, h * HD + 2 * lane + 1, o[i].y * inv);
+  }
+}
+
 inline int attention(Ctx& c, const AttnP& p) {
   QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
   QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
   if (c.dry || p.nseq == 0) return QAT_OK;
+  if (p.Lq <= 2 && p.attw == nullptr) {
+    const long long probs = (long long)p.nseq * p.H;
+    const unsigned grid = (unsigned)((probs + 7) / 8);
+    if (p.Lq == 1) attn_fewq_kernel<1><<<grid, 256, 0, c.stream>>>(p);
+    else attn_fewq_kernel<2><<<grid, 256, 0, c.stream>>>(p);
+    return check_launch("attn_fewq_kernel");
+  }
+  if (p.Lk <= ROWS_MAXL && p.Lq <= ROWS_MAXL && p.H * p.Lq <= 128) {
+    size_t smem = size_t(2) * p.H * (p.Lk * HD + 4) * 4;
+    if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(attn_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int nt = ((p.H * p.Lq + 31) / 32) * 32;
+    attn_rows_kernel<<<(unsigned)p.nseq, nt, smem, c.stream>>>(p);
+    return check_launch("attn_rows_kernel");
+  }
   if (p.Lk <= 32) {
     constexpr int WPB = 8;
     size_t smem = size_t(WPB) * (ks_floats(p.Lk) + p.Lk * 64) * 4;

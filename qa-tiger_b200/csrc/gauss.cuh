@@ -274,9 +274,10 @@ inline int gauss_reduce(Ctx& c, const GaussP& p, int dtype, int tsplit) {
   QAT_REQUIRE((size_t)p.E * p.C <= 16384, "gauss_reduce: E*C=%d exceeds 16384 (one CTA holds a full (b,t) row in flight)", p.E * p.C);
   if (c.dry) return QAT_OK;
   if (tsplit <= 0) {
-    // enough CTAs for >= 4 per SM, but never slices shorter than ~8 time steps; cluster size <= 8
+    // one co-resident wave: ~3 CTAs per SM measured best at B=256 (t_split 2: 4.1 TB/s vs 2.9 at 4, 2.4 at 1),
+    // never slices shorter than ~8 time steps; cluster size <= 8
     tsplit = 1;
-    while (tsplit < 8 && (long long)p.B * tsplit < 148 * 4 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
+    while (tsplit < 8 && (long long)p.B * tsplit * 2 <= 148 * 4 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
   }
   QAT_REQUIRE(tsplit >= 1 && tsplit <= 8, "gauss_reduce: t_split=%d outside [1,8]", tsplit);
   const int nvec = p.E * p.C / VEC;

@@ -130,9 +130,86 @@ __global__ void __launch_bounds__(TY* TX) gemm_simt_kernel(const float* __restri
   }
 }
 
+// Small-M variant (M < 1024: the per-question contractions, M = batch): 32x32 tiles, BK = 32, 64 threads with
+// 4x4 micro-tiles => N/32 * M/32 CTAs keep every SM busy where the 64x64 tiling would launch a few dozen.
+__global__ void __launch_bounds__(64) gemm_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                        Epi epi, Act C, int M, int N, int K) {
+  constexpr int BM = 32, BN = 32, BK = 32, NT = 64, PAD = 4;
+  __shared__ __align__(16) float As[2][BK][BM + PAD];
+  __shared__ __align__(16) float Ws[2][BK][BN + PAD];
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float4 ra[4], rw[4];
+  auto gload = [&](int k0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + i * NT, r = f >> 3, kq = f & 7;
+      const bool kin = k0 + kq * 4 < K;
+      ra[i] = (m0 + r < M && kin) ? __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
+      rw[i] = (n0 + r < N && kin) ? __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ldw + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
+    }
+  };
+  auto sstore = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + i * NT, r = f >> 3, kq = f & 7;
+      As[buf][kq * 4 + 0][r] = ra[i].x; As[buf][kq * 4 + 1][r] = ra[i].y; As[buf][kq * 4 + 2][r] = ra[i].z; As[buf][kq * 4 + 3][r] = ra[i].w;
+      Ws[buf][kq * 4 + 0][r] = rw[i].x; Ws[buf][kq * 4 + 1][r] = rw[i].y; Ws[buf][kq * 4 + 2][r] = rw[i].z; Ws[buf][kq * 4 + 3][r] = rw[i].w;
+    }
+  };
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const int nk = (K + BK - 1) / BK;
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  for (int kt = 0; kt < nk; ++kt) {
+    const int buf = kt & 1;
+    if (kt + 1 < nk) gload((kt + 1) * BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (kt + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const bool vec_ok = ((C.ld & 3) == 0) && (epi.res == nullptr || (epi.ldr & 3) == 0);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long gr = m0 + ty * 4 + i;
+    const int gc = n0 + tx * 4;
+    if (gr >= M || gc >= N) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = acc[i][j];
+      if (gc + j < N) {
+        if (epi.bias) x += __ldg(epi.bias + gc + j);
+        if (epi.relu) x = fmaxf(x, 0.f);
+        if (epi.res) x += __ldg(epi.res + gr * epi.ldr + gc + j);
+      }
+      v[j] = x;
+    }
+    if (vec_ok && gc + 3 < N) act_store4(C, gr, gc, make_float4(v[0], v[1], v[2], v[3]));
+    else
+      for (int j = 0; j < 4 && gc + j < N; ++j) act_store1(C, gr, gc + j, v[j]);
+  }
+}
+
 inline int gemm_simt(Ctx& c, const float* A, int lda, long long M, const float* W, int N, int K, const Epi& epi, Act C) {
   if (M == 0 || N == 0) return QAT_OK;
-  QAT_REQUIRE(K % 16 == 0 && lda % 4 == 0, "gemm_simt: K=%d must be a multiple of 16 and lda=%d of 4", K, lda);
+  QAT_REQUIRE(K % 4 == 0 && lda % 4 == 0 && (M < 1024 || K % 16 == 0), "gemm_simt: K=%d must be a multiple of 4 (16 for M >= 1024) and lda=%d of 4", K, lda);
   QAT_REQUIRE(M < (1ll << 31), "gemm_simt: M too large");
   if (c.dry) return QAT_OK;
   if (M >= 1024) {
@@ -140,8 +217,8 @@ inline int gemm_simt(Ctx& c, const float* A, int lda, long long M, const float* 
     QAT_REQUIRE(grid.y <= 65535, "gemm_simt: M=%lld exceeds the grid limit; chunk the rows", M);
     gemm_simt_kernel<16, 16><<<grid, 256, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
   } else {
-    dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64));
-    gemm_simt_kernel<8, 8><<<grid, 64, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
+    dim3 grid((N + 31) / 32, (unsigned)((M + 31) / 32));
+    gemm_small_kernel<<<grid, 64, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
   }
   return check_launch("gemm_simt_kernel");
 }

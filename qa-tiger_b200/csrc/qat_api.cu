@@ -236,7 +236,7 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
   const long long BT = (long long)B * T;
   const int Cin = a->has_proj ? a->Cin : D;
   // frames per pass: keep the per-pass intermediates (~ P*D*4*(1+3+1+1+2) bytes per frame) near L2 size
-  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 1024;
+  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 4096;
   if (chunk > BT) chunk = BT;
   const float scale = 0.125f;
   const WView Wp = wview(a->proj), Wsi = wview(a->slf_in), Wso = wview(a->slf_out), Wq = wview(a->crs_q), Wkv = wview(a->crs_kv);
