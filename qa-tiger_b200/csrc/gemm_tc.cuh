@@ -117,10 +117,16 @@ struct Cfg {
   static constexpr int W_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
   static constexpr int EPI_BYTES = 4 * 32 * 36 * 4;                       // 4 warps x [32][36] floats
-  static constexpr int BAR_BYTES = (2 * STAGES + 1) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;   // + alignment slack
+  static constexpr int TMEM_COLS = 2 * BN;                                // two accumulators: epilogue(i) overlaps mainloop(i+1)
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
 };
 
+// Persistent: grid = min(#tiles, #SMs); CTA c walks tiles c, c+grid, ... (n fastest, so co-scheduled CTAs share
+// the A rows through L2).  Three decoupled loops meet only through mbarriers:
+//   full/empty[STAGES]   TMA <-> MMA    (smem ring, continuous across tiles)
+//   tfull/tempty[2]      MMA <-> epilogue (the two TMEM accumulators)
 template <int KIND, int BN, int STAGES>
 __global__ void __launch_bounds__(192, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
@@ -132,13 +138,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   float* epi_smem = reinterpret_cast<float*>(smem + STAGES * G::STAGE_BYTES);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * G::STAGE_BYTES + G::EPI_BYTES);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + STAGES;      // [2]
+  uint64_t* tempty = tfull + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * G::BM;
   const int nkb = (p.K + G::BK - 1) / G::BK;
+  const int tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + G::BM - 1) / G::BM;
+  const int ntiles = tiles_n * tiles_m;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA0)) : "memory");
@@ -151,12 +159,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);          // one arrival per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(BN) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(G::TMEM_COLS) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -167,92 +178,114 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        unsigned char* st = tiles + s * G::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
-        const int k0 = kb * G::BK;
-        tma_load_2d(st, &mA0, &full[s], k0, m0);
-        if (G::PLANES == 2) tma_load_2d(st + G::A_BYTES, &mA1, &full[s], k0, m0);
-        tma_load_2d(st + G::PLANES * G::A_BYTES, &mW0, &full[s], k0, n0);
-        if (G::PLANES == 2) tma_load_2d(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, &full[s], k0, n0);
+      uint32_t it = 0;                                   // running k-block counter across tiles
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          unsigned char* st = tiles + s * G::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
+          const int k0 = kb * G::BK;
+          tma_load_2d(st, &mA0, &full[s], k0, m0);
+          if (G::PLANES == 2) tma_load_2d(st + G::A_BYTES, &mA1, &full[s], k0, m0);
+          tma_load_2d(st + G::PLANES * G::A_BYTES, &mW0, &full[s], k0, n0);
+          if (G::PLANES == 2) tma_load_2d(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, &full[s], k0, n0);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc(KIND == KIND_TF32 ? 2 : 1, G::BM, BN);
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
+      uint32_t it = 0, lt = 0;                           // lt = local tile counter
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+        const uint32_t as = lt & 1;
+        mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = smem_u32(tiles + s * G::STAGE_BYTES);
-        const uint32_t w0 = a0 + G::PLANES * G::A_BYTES;
-        const uint64_t dA0 = umma_desc(a0), dW0 = umma_desc(w0);
-        const uint64_t dA1 = umma_desc(a0 + G::A_BYTES), dW1 = umma_desc(w0 + G::W_BYTES);
+        const uint32_t tacc = tmem_base + as * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (it / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(tiles + s * G::STAGE_BYTES);
+          const uint32_t w0 = a0 + G::PLANES * G::A_BYTES;
+          const uint64_t dA0 = umma_desc(a0), dW0 = umma_desc(w0);
+          const uint64_t dA1 = umma_desc(a0 + G::A_BYTES), dW1 = umma_desc(w0 + G::W_BYTES);
 #pragma unroll
-        for (int k = 0; k < G::BK / G::UK; ++k) {
-          const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
-          if (KIND == KIND_TF32) {
-            umma<KIND>(tmem_base, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
-          } else {
-            umma<KIND>(tmem_base, dA1 + adv, dW0 + adv, idesc, (kb | k) != 0);    // lo * hi
-            umma<KIND>(tmem_base, dA0 + adv, dW1 + adv, idesc, 1);                // hi * lo
-            umma<KIND>(tmem_base, dA0 + adv, dW0 + adv, idesc, 1);                // hi * hi
+          for (int k = 0; k < G::BK / G::UK; ++k) {
+            const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
+            if (KIND == KIND_TF32) {
+              umma<KIND>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
+            } else {
+              umma<KIND>(tacc, dA1 + adv, dW0 + adv, idesc, (kb | k) != 0);    // lo * hi
+              umma<KIND>(tacc, dA0 + adv, dW1 + adv, idesc, 1);                // hi * lo
+              umma<KIND>(tacc, dA0 + adv, dW0 + adv, idesc, 1);                // hi * hi
+            }
           }
+          umma_commit(&empty[s]);            // smem slot reusable once these MMAs have read it
         }
-        umma_commit(&empty[s]);              // smem slot reusable once these MMAs have read it
+        umma_commit(&tfull[as]);             // accumulator complete
       }
-      umma_commit(tmem_full);                // accumulator complete
     }
   } else {
     // ===================== epilogue warps 2..5: TMEM lanes 32*(warp%4) =====================
     const int lg = warp & 3;
     float* tile = epi_smem + (warp - 2) * (32 * 36);
-    mbar_wait(tmem_full, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int rq = lane >> 3, cq = lane & 7;
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      if (n0 + c0 >= p.N) break;
-      uint32_t v[32];
-      tmem_ld32(tmem_base + (uint32_t(lg * 32) << 16) + uint32_t(c0), v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
+      const uint32_t as = lt & 1;
+      mbar_wait(&tfull[as], (lt >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * BN + (uint32_t(lg * 32) << 16);
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        if (n0 + c0 >= p.N) break;
+        uint32_t v[32];
+        tmem_ld32(tacc + uint32_t(c0), v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 >= BN || n0 + c0 + 32 >= p.N) {
+          // last TMEM read of this tile: hand the accumulator back to the MMA warp before the stores
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+        }
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<float4*>(tile + lane * 36 + q * 4) =
-            make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-      __syncwarp();
-      const int col = n0 + c0 + cq * 4;
-      if (col < p.N) {   // N is a multiple of 4 (checked on the host)
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.epi.bias) bv = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col));
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<float4*>(tile + lane * 36 + q * 4) =
+              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + cq * 4;
+        if (col < p.N) {   // N is a multiple of 4 (checked on the host)
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.epi.bias) bv = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col));
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = i * 4 + rq;
-          const long long row = (long long)m0 + lg * 32 + r;
-          if (row < p.M) {
-            float4 x = *reinterpret_cast<const float4*>(tile + r * 36 + cq * 4);
-            x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-            if (p.epi.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-            if (p.epi.res) {
-              float4 rr = __ldg(reinterpret_cast<const float4*>(p.epi.res + row * p.epi.ldr + col));
-              x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rq;
+            const long long row = (long long)m0 + lg * 32 + r;
+            if (row < p.M) {
+              float4 x = *reinterpret_cast<const float4*>(tile + r * 36 + cq * 4);
+              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
+              if (p.epi.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              if (p.epi.res) {
+                float4 rr = __ldg(reinterpret_cast<const float4*>(p.epi.res + row * p.epi.ldr + col));
+                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
+              }
+              act_store4(p.C, row, col, x);
             }
-            act_store4(p.C, row, col, x);
           }
         }
+        __syncwarp();
       }
-      __syncwarp();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
   }
 }
 
@@ -306,13 +339,17 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
   GemmP p;
   p.M = (int)M; p.N = N; p.K = K; p.epi = epi; p.C = C;
-  dim3 grid((N + BN - 1) / BN, (unsigned)((M + G::BM - 1) / G::BM));
+  const long long ntiles = (long long)((N + BN - 1) / BN) * ((M + G::BM - 1) / G::BM);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
   kern<<<grid, 192, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, p);
   return check_launch("gemm_tc_kernel");
 }
 
 inline int check_common(long long M, int N, int K, long long lda, const Epi& epi, const Act& C, int eb) {
-  QAT_REQUIRE(M > 0 && M < (1ll << 31) && (M + 127) / 128 <= 65535, "gemm_tc: M=%lld out of range", M);
+  QAT_REQUIRE(M > 0 && M < (1ll << 31), "gemm_tc: M=%lld out of range", M);
   QAT_REQUIRE(N % 4 == 0, "gemm_tc: N=%d must be a multiple of 4", N);
   QAT_REQUIRE((lda * eb) % 16 == 0 && (K * eb) % 16 == 0, "gemm_tc: row strides must be multiples of 16 bytes");
   QAT_REQUIRE(C.ld % 4 == 0 && (epi.res == nullptr || epi.ldr % 4 == 0), "gemm_tc: output/residual leading dims must be multiples of 4");
