@@ -301,6 +301,148 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(AttnP p) {
   }
 }
 
+// ---- register-tiled core for the 60..128-token sequences of AVQCrossAttn: one CTA (128 threads) per
+// (sequence, head).  S = (Q*scale) K^T and O = P V are both 4x(4*CK4) / 4x8 register-tiled FFMA GEMMs out of
+// shared memory (operands stored transposed so every read is a conflict-free LDS.128); the softmax of a row
+// lives in 8 adjacent lanes (3 xor-shuffles).  Queries are processed in passes of 64 rows.
+template <int CK4>   // key columns per thread = 4*CK4  (Lk <= 32*CK4)
+__global__ void __launch_bounds__(128) attn_tile_kernel(AttnP p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LKP = 32 * CK4;               // padded key count
+  constexpr int QS = 68, PS = 68;             // row strides (floats) of the transposed Q / P tiles
+  const int Lq = p.Lq, Lk = p.Lk;
+  float* Qt = smem;                           // [64 d][QS]   Q^T of the current 64-row pass (pre-scaled)
+  float* Kt = Qt + 64 * QS;                   // [64 d][LKP+4] K^T, zero padded
+  float* Vs = Kt + 64 * (LKP + 4);            // [LKP][64]
+  float* Pt = Vs + LKP * 64;                  // [LKP j][PS]  P^T of the current pass
+  const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int kn = (n + p.k_shift) % p.k_mod;
+  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+  const float* kb = p.k + kn * p.k_sn + h * HD;
+  const float* vb = p.v + kn * p.k_sn + h * HD;
+  // stage K^T (lanes walk the key index: conflict-free transposed stores) and V
+  for (int f = tid; f < LKP * 16; f += 128) {
+    const int j = f % LKP, c4 = f / LKP;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (j < Lk) {
+      kv = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
+      vv = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+    }
+    Kt[(c4 * 4 + 0) * (LKP + 4) + j] = kv.x;
+    Kt[(c4 * 4 + 1) * (LKP + 4) + j] = kv.y;
+    Kt[(c4 * 4 + 2) * (LKP + 4) + j] = kv.z;
+    Kt[(c4 * 4 + 3) * (LKP + 4) + j] = kv.w;
+    *reinterpret_cast<float4*>(Vs + j * 64 + c4 * 4) = vv;
+  }
+  const float invH = 1.f / p.H;
+  for (int r0 = 0; r0 < Lq; r0 += 64) {
+    __syncthreads();                           // previous pass done with Qt / Pt (and K/V staged on pass 0)
+    for (int f = tid; f < 64 * 16; f += 128) {
+      const int i = f & 63, c4 = f >> 6;
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + i < Lq) qv = __ldg(reinterpret_cast<const float4*>(p.q + n * p.q_sn + (r0 + i) * p.q_si + h * HD) + c4);
+      Qt[(c4 * 4 + 0) * QS + i] = qv.x * p.scale;
+      Qt[(c4 * 4 + 1) * QS + i] = qv.y * p.scale;
+      Qt[(c4 * 4 + 2) * QS + i] = qv.z * p.scale;
+      Qt[(c4 * 4 + 3) * QS + i] = qv.w * p.scale;
+    }
+    __syncthreads();
+    // ---- S tile: rows ty*4+r, cols tx*4 + 32*c + e ----
+    float acc[4][4 * CK4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4 * CK4; ++c) acc[r][c] = 0.f;
+#pragma unroll 4
+    for (int d = 0; d < 64; ++d) {
+      const float4 a = *reinterpret_cast<const float4*>(Qt + d * QS + ty * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int c = 0; c < CK4; ++c) {
+        const float4 b = *reinterpret_cast<const float4*>(Kt + d * (LKP + 4) + tx * 4 + 32 * c);
+        const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) acc[r][4 * c + e] = fmaf(av[r], bv[e], acc[r][4 * c + e]);
+      }
+    }
+    // ---- softmax over each row (8 lanes share a row) and P^T to shared ----
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < CK4; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (tx * 4 + 32 * c + e < Lk) mx = fmaxf(mx, acc[r][4 * c + e]);
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < CK4; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float ev = (tx * 4 + 32 * c + e < Lk) ? expf(acc[r][4 * c + e] - mx) : 0.f;
+          acc[r][4 * c + e] = ev;
+          sum += ev;
+        }
+      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+      const int i = ty * 4 + r;
+#pragma unroll
+      for (int c = 0; c < CK4; ++c)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int j = tx * 4 + 32 * c + e;
+          const float pj = acc[r][4 * c + e] / sum;
+          Pt[j * PS + i] = pj;
+          if (p.attw && j < Lk && r0 + i < Lq) atomicAdd(p.attw + ((long long)n * Lq + r0 + i) * Lk + j, pj * invH);
+        }
+    }
+    __syncthreads();
+    // ---- O tile: rows ty*4+r, cols tx*4 + 32*c + e (c < 2) ----
+    float o[4][8];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[r][c] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < Lk; ++j) {
+      const float4 a = *reinterpret_cast<const float4*>(Pt + j * PS + ty * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float4 b0 = *reinterpret_cast<const float4*>(Vs + j * 64 + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(Vs + j * 64 + 32 + tx * 4);
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[r][e] = fmaf(av[r], bv[e], o[r][e]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = r0 + ty * 4 + r;
+      if (i < Lq) {
+        const long long row = n * p.o_rn + i * p.o_ri;
+        act_store4(p.o, row, h * HD + tx * 4, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
+        act_store4(p.o, row, h * HD + 32 + tx * 4, make_float4(o[r][4], o[r][5], o[r][6], o[r][7]));
+      }
+    }
+  }
+}
+
+template <int CK4>
+inline int attn_tile_launch(Ctx& c, const AttnP& p) {
+  constexpr int LKP = 32 * CK4;
+  size_t smem = (size_t)(64 * 68 + 64 * (LKP + 4) + LKP * 64 + LKP * 68) * 4;
+  auto kern = attn_tile_kernel<CK4>;
+  if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
+  return check_launch("attn_tile_kernel");
+}
+
 inline int attention(Ctx& c, const AttnP& p) {
   QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
   QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
@@ -318,6 +460,11 @@ inline int attention(Ctx& c, const AttnP& p) {
     const int nt = ((p.H * p.Lq + 31) / 32) * 32;
     attn_rows_kernel<<<(unsigned)p.nseq, nt, smem, c.stream>>>(p);
     return check_launch("attn_rows_kernel");
+  }
+  if (p.Lk > 32 || p.Lq >= 32) {
+    if (p.Lk <= 64) return attn_tile_launch<2>(c, p);
+    if (p.Lk <= 96) return attn_tile_launch<3>(c, p);
+    return attn_tile_launch<4>(c, p);
   }
   if (p.Lk <= 32) {
     constexpr int WPB = 8;

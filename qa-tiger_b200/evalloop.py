@@ -1,0 +1,138 @@
+"""Data-parallel eval driver: the B200 counterpart of /root/reference/src/trainutils.py:397-462 (`test`).
+
+What changes against the reference loop:
+  * one process per GPU, contiguous shards [r*ceil(N/W), (r+1)*ceil(N/W)) of the question list, local batches
+    walked in order, no shuffle and no wrap-around padding (the reference's DistributedSampler(shuffle=True)
+    double-counts padded samples, trainutils.py:192).  Because logits depend on the LOCAL batch,
+    this partition is part of the parity contract: `local_batches()` is what an oracle must be evaluated on.
+  * accuracy counters live on the device as one packed int64[20] = (correct, total, tot[9], correct[9]);
+    no per-sample `.item()` (trainutils.py:419-423 does B+1 host syncs per batch).
+  * collectives, once at the end: all_gather of the int64 predictions (padded to the shard length) and ONE
+    all_reduce(SUM) of the packed counters, replacing the 20 scalar all-reduces of trainutils.py:436-440.
+The forward itself never communicates.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from typing import Callable, Dict, Iterator, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+# trainutils.py / dataset.py:22-31 question-type table (modality -> type -> counter slot)
+QTYPE2IDX = {
+    "Audio": {"Counting": 0, "Comparative": 1},
+    "Visual": {"Counting": 2, "Location": 3},
+    "Audio-Visual": {"Existential": 4, "Counting": 5, "Location": 6, "Comparative": 7, "Temporal": 8},
+}
+N_QTYPES = 9
+
+
+def shard_range(n: int, rank: int, world: int) -> Tuple[int, int]:
+    per = math.ceil(n / world) if world > 0 else n
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def local_batches(n: int, rank: int, world: int, batch_size: int) -> List[Tuple[int, int]]:
+    """[start, end) global index ranges of this rank's local batches (last one ragged)."""
+    lo, hi = shard_range(n, rank, world)
+    return [(s, min(hi, s + batch_size)) for s in range(lo, hi, batch_size)]
+
+
+class SyntheticAVQA:
+    """MUSIC-AVQA-test-sized synthetic set: sample i is a pure function of (seed, i), so
+    every sharding sees identical samples.  Features are generated on `device` batch by batch."""
+
+    def __init__(self, n: int = 9129, seed: int = 1234, T: int = 60, P: int = 14, n_unique_questions: int = 0):
+        self.n, self.seed, self.T, self.P = n, seed, T, P
+        self.n_unique = n_unique_questions     # >0: draw questions from a pool (MUSIC-AVQA test has 33 unique strings)
+
+    def _tokens(self, i: int) -> torch.Tensor:
+        key = i if self.n_unique <= 0 else (i * 2654435761) % self.n_unique
+        g = torch.Generator().manual_seed(self.seed * 1000003 + key)
+        q = torch.zeros(77, dtype=torch.int32)
+        L = int(torch.randint(5, 20, (1,), generator=g))
+        q[0] = 49406
+        q[1:1 + L] = torch.randint(1, 49406, (L,), generator=g, dtype=torch.int32)
+        q[1 + L] = 49407
+        return q
+
+    def batch(self, start: int, end: int, device: torch.device) -> Dict[str, torch.Tensor]:
+        B = end - start
+        audio = torch.empty(B, self.T, 128, device=device)
+        video = torch.empty(B, self.T, 768, device=device)
+        patch = torch.empty(B, self.T, self.P, 1024, device=device)
+        g = torch.Generator(device=device)
+        lab = torch.empty(B, dtype=torch.int64)
+        qt = torch.empty(B, dtype=torch.int64)
+        for j, i in enumerate(range(start, end)):
+            g.manual_seed(self.seed * 7919 + i)
+            audio[j].normal_(generator=g)
+            video[j].normal_(generator=g)
+            patch[j].normal_(generator=g)
+            h = (i * 1103515245 + self.seed) & 0x7FFFFFFF
+            lab[j], qt[j] = h % 42, (h // 42) % N_QTYPES
+        quest = torch.stack([self._tokens(i) for i in range(start, end)])
+        return dict(quest=quest.to(device), audio=audio, video=video, patch=patch, label=lab.to(device), qtype_label=qt.to(device))
+
+
+def pack_counters(pred: torch.Tensor, target: torch.Tensor, qtype: torch.Tensor, acc: torch.Tensor) -> None:
+    """acc int64[20] += (correct, total, tot[9], correct[9]) -- all on `acc.device`, no host sync."""
+    hit = (pred == target).to(torch.int64)
+    acc[0] += hit.sum()
+    acc[1] += pred.numel()
+    acc[2:2 + N_QTYPES].index_add_(0, qtype, torch.ones_like(hit))
+    acc[2 + N_QTYPES:].index_add_(0, qtype, hit)
+
+
+@torch.no_grad()
+def evaluate(forward_fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], dataset, device: torch.device, batch_size: int = 256,
+             rank: int = 0, world: int = 1, group=None, logger: Optional[logging.Logger] = None) -> Dict[str, object]:
+    """forward_fn(batch dict) -> logits [B,42].  Returns accuracy, the packed counters and ALL predictions (global order)."""
+    n = dataset.n
+    lo, hi = shard_range(n, rank, world)
+    per = math.ceil(n / world)
+    counters = torch.zeros(2 + 2 * N_QTYPES, dtype=torch.int64, device=device)
+    preds = torch.full((per,), -1, dtype=torch.int64, device=device)
+    for (s, e) in local_batches(n, rank, world, batch_size):
+        b = dataset.batch(s, e, device)
+        logits = forward_fn(b)
+        p = logits.argmax(dim=1)
+        preds[s - lo:e - lo] = p
+        pack_counters(p, b["label"].reshape(-1), b["qtype_label"].reshape(-1), counters)
+    if world > 1:
+        gathered = torch.empty(world * per, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gathered, preds, group=group)
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM, group=group)
+        all_preds = torch.cat([gathered[r * per:r * per + (shard_range(n, r, world)[1] - shard_range(n, r, world)[0])] for r in range(world)])
+    else:
+        all_preds = preds[:hi - lo]
+    c = counters.cpu()                                                 # the single host sync of the eval
+    correct, total = int(c[0]), int(c[1])
+    result = dict(acc=100.0 * correct / max(total, 1), correct=correct, total=total, tot=c[2:2 + N_QTYPES].tolist(),
+                  correct_by_type=c[2 + N_QTYPES:].tolist(), predictions=all_preds.cpu())
+    if logger is not None and rank == 0:
+        for line in format_report(result):
+            logger.info(line)
+    return result
+
+
+def format_report(result: Dict[str, object]) -> List[str]:
+    """Same line formats as trainutils.py:442-461 so result files stay comparable."""
+    lines = []
+    tot, cor = result["tot"], result["correct_by_type"]
+    for modality, types in QTYPE2IDX.items():
+        mc = mt = 0
+        for qst_type, idx in types.items():
+            c, t = cor[idx], tot[idx]
+            mc, mt = mc + c, mt + t
+            value = c / t * 100.0 if t else float("nan")
+            key = f"{modality}/{qst_type}"
+            lines.append(f"Test {key:>24} accuracy: {value:.2f}({c}/{t})")
+        macc = mc / mt * 100.0 if mt else float("nan")
+        lines.append(f"Test {modality:>24} accuracy: {macc:.2f}({mc}/{mt})")
+    key = "Total avg"
+    lines.append(f"Test {key:>24} accuracy: {result['acc']:.2f}({result['correct']}/{result['total']})")
+    return lines
