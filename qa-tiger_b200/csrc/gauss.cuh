@@ -6,9 +6,12 @@
 // where perm_t is the rank list of sample (b*T+t) mod B -- the `topk_inds.repeat(T,1)` batch-coupling
 // quirk of modules.py:502, reproduced on purpose.
 //
-// HBM-bound: X is read exactly once with coalesced 128-bit streaming loads (L1 no-allocate), every
-// thread keeps SLOTS independent loads in flight; the t axis of one sample is split over a thread-block
-// cluster whose partial sums meet in distributed shared memory (fixed order => bit-reproducible).
+// HBM-bound: X is read exactly once.  Each (b,t) row (E*C contiguous elements) is pulled by ONE 1-D bulk
+// copy (cp.async.bulk -> UBLKCP) into a ring of shared-memory stages guarded by mbarriers; the first RING
+// copies are issued before the router/Gaussian prologue so HBM is busy from the first cycle, and the bytes
+// in flight per SM (ring depth x row bytes x resident CTAs) do not depend on registers or occupancy.
+// The t axis of one sample can be split over a thread-block cluster whose partial sums meet in
+// distributed shared memory in rank order (=> bit-reproducible).
 #pragma once
 #include <cooperative_groups.h>
 
@@ -31,6 +34,7 @@ struct GaussP {
   long long* topk_inds;  // optional [B,K]
   float* topk_probs;     // optional [B,K]
   float* gauss_weight;   // optional [B,K,T]
+  int ring;              // shared-memory stages (rows in flight per CTA), set by the launcher
 };
 
 __device__ __forceinline__ float linspace_at(float start, float end, int steps, int i) {
@@ -77,7 +81,11 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   const int cvec = C / VEC;       // vectors per expert
 
   // ---- shared layout -------------------------------------------------------------------------
-  float* s_part = reinterpret_cast<float*>(smem_raw);            // [nvec*VEC] partial sums (DSMEM-visible)
+  const int ring = p.ring;
+  const uint32_t row_bytes = (uint32_t)nvec * sizeof(VecT);
+  VecT* s_ring = reinterpret_cast<VecT*>(smem_raw);                                   // [ring][nvec]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ring * row_bytes); // [ring]
+  float* s_part = reinterpret_cast<float*>(s_full + ring);       // [nvec*VEC] partial sums (DSMEM-visible)
   float* s_coef = s_part + (size_t)nvec * VEC;                    // [T][E]
   float* s_G = s_coef + T * E;                                    // [K][T]
   float* s_p = s_G + K * T;                                       // [K]
@@ -85,6 +93,20 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   float* s_w = s_c + K;                                           // [K]
   int* s_idx = reinterpret_cast<int*>(s_w + K);                   // [K]
   unsigned char* s_perm = reinterpret_cast<unsigned char*>(s_idx + K);  // [T][K]
+
+  // ---- start streaming before anything else: arm the ring and issue the first `ring` row copies ----
+  const int t0 = (int)((long long)T * rank / nrank), t1 = (int)((long long)T * (rank + 1) / nrank);
+  const char* xrow0 = reinterpret_cast<const char*>(p.x) + ((long long)b * p.sb) * (long long)(sizeof(VecT) / VEC);
+  const long long row_stride = p.st * (long long)(sizeof(VecT) / VEC);   // bytes between consecutive t
+  if (tid == 0) {
+    for (int s = 0; s < ring; ++s) tc::mbar_init(&s_full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    for (int s = 0; s < ring && t0 + s < t1; ++s) {
+      tc::mbar_arrive_expect_tx(&s_full[s], row_bytes);
+      tc::bulk_load(s_ring + (size_t)s * nvec, xrow0 + (long long)(t0 + s) * row_stride, row_bytes, &s_full[s]);
+    }
+  }
 
   // ---- phase 0: rank lists.  Thread t ranks sample (b*T+t)%B; the last thread ranks sample b. ----
   for (int t = tid; t < T + 1; t += NT) {
@@ -163,8 +185,7 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   }
   __syncthreads();
 
-  // ---- main loop: stream X[t, b, :, :] for my slice of t -------------------------------------
-  const int t0 = (int)((long long)T * rank / nrank), t1 = (int)((long long)T * (rank + 1) / nrank);
+  // ---- main loop: consume ring stages in order, refill each stage as soon as the CTA is done with it ----
   float acc[SLOTS][VEC];
   int je[SLOTS];
 #pragma unroll
@@ -174,20 +195,19 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
     int f = tid + s * NT;
     je[s] = f < nvec ? f / cvec : 0;
   }
-  const VecT* xb = reinterpret_cast<const VecT*>(p.x) + ((long long)b * p.sb) / VEC;
-  const long long stv = p.st / VEC;
-  for (int t = t0; t < t1; ++t) {
-    const VecT* xr = xb + (long long)t * stv;
-    VecT v[SLOTS];
+  for (int t = t0, it = 0; t < t1; ++t, ++it) {
+    const int st = it % ring;
+    tc::mbar_wait(&s_full[st], (uint32_t)(it / ring) & 1u);
+    const VecT* xr = s_ring + (size_t)st * nvec;
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       int f = tid + s * NT;
-      if (f < nvec) v[s] = ldg_stream(xr + f);
+      if (f < nvec) fma_vec<VecT, VEC>(acc[s], xr[f], s_coef[t * E + je[s]]);
     }
-#pragma unroll
-    for (int s = 0; s < SLOTS; ++s) {
-      int f = tid + s * NT;
-      if (f < nvec) fma_vec<VecT, VEC>(acc[s], v[s], s_coef[t * E + je[s]]);
+    __syncthreads();                       // every thread has read stage `st`
+    if (tid == 0 && t + ring < t1) {
+      tc::mbar_arrive_expect_tx(&s_full[st], row_bytes);
+      tc::bulk_load(s_ring + (size_t)st * nvec, xrow0 + (long long)(t + ring) * row_stride, row_bytes, &s_full[st]);
     }
   }
 #pragma unroll
@@ -232,14 +252,31 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   if (CLUSTER) cg::this_cluster().sync();   // keep every CTA's smem alive until rank 0 has read it
 }
 
-inline size_t gauss_smem_bytes(const GaussP& p) {
+inline size_t gauss_smem_bytes(const GaussP& p, size_t row_bytes) {
   size_t f = (size_t)p.E * p.C + (size_t)p.T * p.E + (size_t)p.K * p.T + 3 * (size_t)p.K;
-  return f * 4 + (size_t)p.K * 4 + (size_t)p.T * p.K + 16;
+  return (size_t)p.ring * (row_bytes + 8) + f * 4 + (size_t)p.K * 4 + (size_t)p.T * p.K + 16;
 }
 
 template <typename VecT, int VEC, int SLOTS, int NT>
-inline int gauss_launch(Ctx& c, const GaussP& p, int tsplit) {
-  size_t smem = gauss_smem_bytes(p);
+inline int gauss_launch(Ctx& c, const GaussP& p_in, int tsplit) {
+  GaussP p = p_in;
+  const size_t row_bytes = (size_t)p.E * p.C * (sizeof(VecT) / VEC);
+  // ring depth: all CTAs should be co-resident (one wave), so the per-CTA shared-memory budget is the SM's
+  // 227 KB divided by the CTAs each SM has to host; 2..8 stages, never more than the slice length
+  const long long ctas = (long long)p.B * tsplit;
+  int per_sm = (int)((ctas + 147) / 148);
+  per_sm = per_sm > 8 ? 8 : per_sm;
+  p.ring = 0;
+  const size_t fixed = gauss_smem_bytes(p, row_bytes) + 1024;
+  const size_t budget = (size_t)(225 * 1024) / per_sm;
+  int ring = budget > fixed ? (int)((budget - fixed) / (row_bytes + 8)) : 2;
+  const int slice = (p.T + tsplit - 1) / tsplit;
+  ring = ring > 8 ? 8 : ring;
+  ring = ring > slice ? slice : ring;
+  ring = ring < 2 ? 2 : ring;
+  p.ring = ring;
+  size_t smem = gauss_smem_bytes(p, row_bytes);
+  QAT_REQUIRE(smem <= 220 * 1024, "gauss_reduce: row of %zu bytes does not fit the shared-memory ring", row_bytes);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(p.B, tsplit, 1);
   cfg.blockDim = dim3(NT, 1, 1);
@@ -248,7 +285,7 @@ inline int gauss_launch(Ctx& c, const GaussP& p, int tsplit) {
   cudaLaunchAttribute attr[1];
   if (tsplit > 1) {
     auto kern = gauss_reduce_kernel<VecT, VEC, SLOTS, NT, true>;
-    if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 1;
     attr[0].val.clusterDim.y = tsplit;
@@ -258,7 +295,7 @@ inline int gauss_launch(Ctx& c, const GaussP& p, int tsplit) {
     QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   } else {
     auto kern = gauss_reduce_kernel<VecT, VEC, SLOTS, NT, false>;
-    if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   }
   return check_launch("gauss_reduce_kernel");
@@ -271,13 +308,14 @@ inline int gauss_reduce(Ctx& c, const GaussP& p, int dtype, int tsplit) {
   const int VEC = dtype == QAT_DT_BF16 ? 8 : 4;
   QAT_REQUIRE(dtype == QAT_DT_F32 || dtype == QAT_DT_BF16, "gauss_reduce: unknown dtype %d", dtype);
   QAT_REQUIRE(p.C % VEC == 0 && p.st % VEC == 0 && p.sb % VEC == 0, "gauss_reduce: C and strides must be multiples of %d elements", VEC);
+  QAT_REQUIRE(reinterpret_cast<uintptr_t>(p.x) % 16 == 0, "gauss_reduce: experts tensor must be 16-byte aligned");
   QAT_REQUIRE((size_t)p.E * p.C <= 16384, "gauss_reduce: E*C=%d exceeds 16384 (one CTA holds a full (b,t) row in flight)", p.E * p.C);
   if (c.dry) return QAT_OK;
   if (tsplit <= 0) {
-    // one co-resident wave: ~3 CTAs per SM measured best at B=256 (t_split 2: 4.1 TB/s vs 2.9 at 4, 2.4 at 1),
-    // never slices shorter than ~8 time steps; cluster size <= 8
+    // bytes in flight come from the bulk-copy ring, not from occupancy: split t only until every SM has a CTA
+    // (cluster size <= 8, slices of at least ~8 time steps)
     tsplit = 1;
-    while (tsplit < 8 && (long long)p.B * tsplit * 2 <= 148 * 4 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
+    while (tsplit < 8 && (long long)p.B * tsplit * 2 <= 148 * 2 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
   }
   QAT_REQUIRE(tsplit >= 1 && tsplit <= 8, "gauss_reduce: t_split=%d outside [1,8]", tsplit);
   const int nvec = p.E * p.C / VEC;
