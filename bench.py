@@ -251,40 +251,70 @@ def run_ours(args):
                                   "launches_per_step": launches_per_step, "hot_only": True, "cuda_graph": graph is not None}))
             return
         # ---- e2e: public API from pinned host memory, text tower included ---------------------------
+        # Every step: H2D of THAT step's batch (pinned -> device, on a copy stream, double-buffered so the copy of
+        # step i+1 overlaps the compute of step i), CLIP text tower, hot path, argmax, D2H of the predictions.
+        model.quest_encoder.compute = "bf16x3"       # text-tower Linear layers through the tcgen05 bf16 hi/lo GEMM
         host = {k: v.cpu().pin_memory() for k, v in (("quest", quest), ("audio", audio), ("video", video), ("patch", patch))}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         pred_host = torch.empty(B, dtype=torch.int64).pin_memory()
+        bufs = [{k: torch.empty_like(v, device=dev) for k, v in host.items()} for _ in range(2)]
+        copy_stream = torch.cuda.Stream()
+        ready = [torch.cuda.Event() for _ in range(2)]
+        freed = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step():
-            data = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-            o = model(data)["out"]
-            pred_host.copy_(o.argmax(1), non_blocking=True)
+        def issue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])
+                for k, v in host.items():
+                    bufs[i % 2][k].copy_(v, non_blocking=True)
+                ready[i % 2].record(copy_stream)
 
-        e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            e2e_step()
+        def e2e_run(nsteps):
+            cur = torch.cuda.current_stream()
+            for ev in freed:
+                ev.record(cur)
+            issue_copy(0)
+            for i in range(nsteps):
+                if i + 1 < nsteps:
+                    issue_copy(i + 1)
+                cur.wait_event(ready[i % 2])
+                o = model(bufs[i % 2])["out"]
+                pred_host.copy_(o.argmax(1), non_blocking=True)
+                freed[i % 2].record(cur)
+
+        e2e_steps = max(4, min(args.steps, 12))
+        e2e_run(2)
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for _ in range(e2e_steps):
-            e2e_step()
+        e2e_run(e2e_steps)
         f1.record()
         torch.cuda.synchronize()
         ms_e2e = f0.elapsed_time(f1)
+        e2e_parity = float((model(bufs[0])["out"] - out).norm() / out.norm())   # same batch: bf16x3 tower vs fp32 tower
 
         # ---- per-kernel rooflines, timed live with CUDA events on the launching stream ---------------
-        def time_ms(fn, n=20, warm=3):
+        def time_ms(fn, n=10, warm=2):
+            """Average device time of one fn() launch: n launches captured into a CUDA graph (no CPU launch
+            overhead between them), replayed 3x between CUDA events on the current stream."""
             for _ in range(warm):
                 fn()
+            torch.cuda.synchronize()
+            gr_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr_):
+                for _ in range(n):
+                    fn()
+            gr_.replay()
+            torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
-            for _ in range(n):
-                fn()
+            for _ in range(3):
+                gr_.replay()
             b.record()
             torch.cuda.synchronize()
-            return a.elapsed_time(b) / n
+            return a.elapsed_time(b) / (3 * n)
 
         rooflines = {}
         if rank == 0:
@@ -297,8 +327,8 @@ def run_ours(args):
                 def fn():
                     it[0] += 1
                     gauss_reduce(xs[it[0] % 3], rl, gr, K_TOP)
-                t_ms = time_ms(fn)
-                byts = B * (E * T * 512 * s + 3 * E * 4 + 512 * 4) + T * K_TOP * 0
+                t_ms = time_ms(fn, n=9)
+                byts = B * (E * T * 512 * s + 3 * E * 4 + 512 * 4)
                 ach = byts / (t_ms * 1e-3) / 1e9
                 rooflines[nm] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                                  "traffic": None, "ms": t_ms, "bytes": byts}
@@ -308,17 +338,18 @@ def run_ours(args):
             #     bf16x3: AVQ packed in-proj [B*T,512] x [3584,512]^T, 3 MMAs per product (peak = sustained bf16 / 3)
             ps = model.patch_selecter._prepared(_cabi.PREC_BF16)
             cr = model.crs_attn._prepared(_cabi.PREC_BF16)
-            for nm, kind, lin, M_, div in (("gemm_tf32_patch_slf_in", _cabi.GEMM_TF32, ps["slf_in"], B * T * P, 2.0),
+            chunk_rows = min(B * T, 4096) * P          # rows of one PatchSelecter pass (chunk_frames default 4096)
+            for nm, kind, lin, M_, div in (("gemm_tf32_patch_slf_in", _cabi.GEMM_TF32, ps["slf_in"], chunk_rows, 2.0),
                                            ("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], B * T, 3.0)):
                 N_, K_ = lin.w.shape
                 xin = torch.randn(M_, K_, device=dev)
                 planes = _cabi.split_planes(xin) if kind == _cabi.GEMM_BF16X3 else None
-                t_ms = time_ms(lambda: _cabi.gemm(kind, xin, lin, a_planes=planes), n=10)
+                t_ms = time_ms(lambda: _cabi.gemm(kind, xin, lin, a_planes=planes), n=6)
                 fl = 2.0 * M_ * N_ * K_
                 ach = fl / (t_ms * 1e-3) / 1e12
                 rooflines[nm] = {"bound": "tensor", "achieved": ach, "peak": tf_sust / div, "unit": "TFLOP/s",
                                  "frac": ach / (tf_sust / div), "traffic": None, "ms": t_ms, "shape": [M_, N_, K_],
-                                 "note": f"nominal FLOPs; peak = sustained bf16 / {div:g} (includes the torch.empty of the output)"}
+                                 "note": f"nominal 2MNK FLOPs; peak = sustained bf16 / {div:g}"}
                 del xin, planes
 
     tmax = torch.tensor([ms, ms_e2e / e2e_steps * args.steps], device=dev)
@@ -344,16 +375,26 @@ def run_ours(args):
                        "cuda_graph": graph is not None, "parallelism": f"dp{world}, contiguous shards, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": qps_e2e, "unit": "questions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
-                    "ms_per_step": ms_e2e_max, "includes": "H2D from pinned host, CLIP text tower (torch fp32), hot path, argmax, D2H"},
+                    "ms_per_step": ms_e2e_max, "text_tower_vs_fp32_logit_relerr": e2e_parity,
+                    "includes": "per step: H2D of the batch from pinned host (copy stream, double-buffered), CLIP text tower "
+                                "(PyTorch; Linear layers via the bf16x3 tcgen05 GEMM), hot path, argmax, D2H of predictions"},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "hot_path_tensor_frac_nominal": (flops_q * B / (step_ms * 1e-3)) / (tf_sust * 1e12),
             "peaks": {"hbm_gbs": hbm_peak, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sust, "source": peak_src},
         }
-        # headline roofline = the kernel north_star names for the HBM class; the tensor-class GEMM rides along
-        key = "gauss_reduce_f32"
+        # per-launch DRAM traffic from the committed `ncu --set full` captures (profiles/r1_traffic.json), if present
+        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tpath):
+            for k, v in json.load(open(tpath)).items():
+                if k in rooflines:
+                    rooflines[k]["traffic"] = v
+        # headline roofline = the dominant kernel of the step (tcgen05 tf32 GEMM: ~40% of the step in the ncu launch
+        # list, profiles/r1_launches_step_v4.txt), at its largest shape; the HBM-class kernel north_star names and
+        # the bf16x3 kind ride along in rooflines_all
+        key = "gemm_tf32_patch_slf_in"
         line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
-        line["roofline"]["kernel"] = "gauss_reduce_kernel<float4> (qat_gauss_reduce_fwd, [T,B,E,C] fp32, B=256)"
+        line["roofline"]["kernel"] = "tc::gemm_tc_kernel<KIND_TF32,256,4> PatchSelecter slf in-proj [57344,512]x[1536,512]^T"
         line["rooflines_all"] = rooflines
         if world == 1 and not args.no_cpu_baseline:
             qps_cpu, cores, sec = cpu_reference_forward(8, 5, 2, with_text=False)

@@ -312,10 +312,10 @@ inline int gauss_reduce(Ctx& c, const GaussP& p, int dtype, int tsplit) {
   QAT_REQUIRE((size_t)p.E * p.C <= 16384, "gauss_reduce: E*C=%d exceeds 16384 (one CTA holds a full (b,t) row in flight)", p.E * p.C);
   if (c.dry) return QAT_OK;
   if (tsplit <= 0) {
-    // bytes in flight come from the bulk-copy ring, not from occupancy: split t only until every SM has a CTA
-    // (cluster size <= 8, slices of at least ~8 time steps)
+    // measured at B=256,T=60,E=7 (CUDA-graph replay): t_split 1 -> 4.44 TB/s, 2 -> 4.75 TB/s, 4 -> 3.3 TB/s:
+    // ~4 co-resident CTAs per SM with a short ring beat 2 CTAs with a deep one; cluster size <= 8, slices >= ~8 steps
     tsplit = 1;
-    while (tsplit < 8 && (long long)p.B * tsplit * 2 <= 148 * 2 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
+    while (tsplit < 8 && (long long)p.B * tsplit * 2 <= 148 * 4 && p.T / (tsplit * 2) >= 8) tsplit *= 2;
   }
   QAT_REQUIRE(tsplit >= 1 && tsplit <= 8, "gauss_reduce: t_split=%d outside [1,8]", tsplit);
   const int nvec = p.E * p.C / VEC;

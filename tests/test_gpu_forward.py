@@ -59,6 +59,11 @@ def test_text_tower_matches_oracle():
         q, w = model.quest_encoder(batch["quest"].to(dev()))
         rq, rw = O.clip_text_encoder(sd, "quest_encoder", batch["quest"])
     assert relerr(q, rq) < 2e-5 and relerr(w, rw) < 2e-5
+    model.quest_encoder.compute = "bf16x3"        # Linear layers through the tcgen05 bf16 hi/lo GEMM
+    with torch.no_grad():
+        q3, w3 = model.quest_encoder(batch["quest"].to(dev()))
+    assert relerr(q3, rq) < 1e-4 and relerr(w3, rw) < 1e-4
+    model.quest_encoder.compute = "fp32"
     model.quest_encoder.dedup = True
     rep = batch["quest"][[0, 1, 0, 2, 1, 0]].to(dev())
     with torch.no_grad():
