@@ -4,6 +4,8 @@
 // Semantics: torch MHA slow path, F.multi_head_attention_forward -- q is scaled by hd^-0.5 BEFORE the
 // dot product, softmax = exp(s - max)/sum, no masks (modules.py:217-221,338,562,688,698).
 #pragma once
+#include <stdlib.h>
+
 #include "qat_common.cuh"
 
 namespace qat {
@@ -443,6 +445,176 @@ inline int attn_tile_launch(Ctx& c, const AttnP& p) {
   return check_launch("attn_tile_kernel");
 }
 
+// ---- tensor-core core for the 60..128-token sequences: mma.sync m16n8k8 TF32 with the 3xTF32 split
+// (x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi); D += lo*hi + hi*lo + hi*hi => fp32-faithful, the
+// serial chain into the router needs it).  These sequences are far too short for a 128-row
+// tcgen05 tile per (sample, head); the warp-level MMA keeps Q/K/V/P in shared memory and S/O in registers.
+// One CTA (4 warps) per (sequence, head); warp w owns query rows 16w..16w+15 of each 64-row pass.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
+                                     const uint32_t (&bl)[2]) {
+  mma_tf32(d, al, bh);
+  mma_tf32(d, ah, bl);
+  mma_tf32(d, ah, bh);
+}
+
+template <int NT8>   // key tiles of 8 columns: Lk <= 8*NT8
+__global__ void __launch_bounds__(128) attn_mma_kernel(AttnP p) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int LKP = 8 * NT8;
+  constexpr int QS = 68, KS = 68, VS = 72, PS = LKP + 4;   // strides chosen so every fragment load hits 32 banks
+  const int Lq = p.Lq, Lk = p.Lk;
+  float* Qs = smem;                 // [64][QS]  pre-scaled queries of the current pass
+  float* Ks = Qs + 64 * QS;         // [LKP][KS]
+  float* Vs = Ks + LKP * KS;        // [LKP][VS]
+  float* Ps = Vs + LKP * VS;        // [64][PS]  probabilities of the current pass
+  const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int kn = (n + p.k_shift) % p.k_mod;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float* kb = p.k + kn * p.k_sn + h * HD;
+  const float* vb = p.v + kn * p.k_sn + h * HD;
+  for (int f = tid; f < LKP * 16; f += 128) {
+    const int j = f >> 4, c4 = f & 15;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (j < Lk) {
+      kv = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
+      vv = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+    }
+    *reinterpret_cast<float4*>(Ks + j * KS + c4 * 4) = kv;
+    *reinterpret_cast<float4*>(Vs + j * VS + c4 * 4) = vv;
+  }
+  const float invH = 1.f / p.H;
+  const int rb = warp * 16;
+  for (int r0 = 0; r0 < Lq; r0 += 64) {
+    __syncthreads();
+    for (int f = tid; f < 64 * 16; f += 128) {
+      const int i = f >> 4, c4 = f & 15;
+      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + i < Lq) qv = __ldg(reinterpret_cast<const float4*>(p.q + n * p.q_sn + (r0 + i) * p.q_si + h * HD) + c4);
+      qv.x *= p.scale; qv.y *= p.scale; qv.z *= p.scale; qv.w *= p.scale;
+      *reinterpret_cast<float4*>(Qs + i * QS + c4 * 4) = qv;
+    }
+    __syncthreads();
+    // ---- S = Q K^T : C fragments, rows rb+g / rb+g+8, cols nt*8 + 2t + {0,1} ----
+    float sacc[NT8][4];
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
+#pragma unroll
+    for (int k0 = 0; k0 < HD; k0 += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(Qs[(rb + g) * QS + k0 + t], ah[0], al[0]);
+      split_tf32(Qs[(rb + g + 8) * QS + k0 + t], ah[1], al[1]);
+      split_tf32(Qs[(rb + g) * QS + k0 + t + 4], ah[2], al[2]);
+      split_tf32(Qs[(rb + g + 8) * QS + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+      for (int nt = 0; nt < NT8; ++nt) {
+        uint32_t bh[2], bl[2];
+        split_tf32(Ks[(nt * 8 + g) * KS + k0 + t], bh[0], bl[0]);
+        split_tf32(Ks[(nt * 8 + g) * KS + k0 + t + 4], bh[1], bl[1]);
+        mma3(sacc[nt], ah, al, bh, bl);
+      }
+    }
+    // ---- softmax over the two rows this thread shares with its 3 quad neighbours ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c < Lk) { mx0 = fmaxf(mx0, sacc[nt][0]); mx1 = fmaxf(mx1, sacc[nt][2]); }
+      if (c + 1 < Lk) { mx0 = fmaxf(mx0, sacc[nt][1]); mx1 = fmaxf(mx1, sacc[nt][3]); }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      sacc[nt][0] = c < Lk ? expf(sacc[nt][0] - mx0) : 0.f;
+      sacc[nt][1] = c + 1 < Lk ? expf(sacc[nt][1] - mx0) : 0.f;
+      sacc[nt][2] = c < Lk ? expf(sacc[nt][2] - mx1) : 0.f;
+      sacc[nt][3] = c + 1 < Lk ? expf(sacc[nt][3] - mx1) : 0.f;
+      s0 += sacc[nt][0] + sacc[nt][1];
+      s1 += sacc[nt][2] + sacc[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+#pragma unroll
+    for (int nt = 0; nt < NT8; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      const float p00 = sacc[nt][0] / s0, p01 = sacc[nt][1] / s0, p10 = sacc[nt][2] / s1, p11 = sacc[nt][3] / s1;
+      *reinterpret_cast<float2*>(Ps + (rb + g) * PS + c) = make_float2(p00, p01);
+      *reinterpret_cast<float2*>(Ps + (rb + g + 8) * PS + c) = make_float2(p10, p11);
+      if (p.attw) {
+        const int i0 = r0 + rb + g, i1 = i0 + 8;
+        float* w0 = p.attw + ((long long)n * Lq + i0) * Lk;
+        float* w1 = p.attw + ((long long)n * Lq + i1) * Lk;
+        if (i0 < Lq && c < Lk) atomicAdd(w0 + c, p00 * invH);
+        if (i0 < Lq && c + 1 < Lk) atomicAdd(w0 + c + 1, p01 * invH);
+        if (i1 < Lq && c < Lk) atomicAdd(w1 + c, p10 * invH);
+        if (i1 < Lq && c + 1 < Lk) atomicAdd(w1 + c + 1, p11 * invH);
+      }
+    }
+    __syncwarp();    // P rows of this warp are private to it
+    // ---- O = P V : C fragments, rows rb+g / rb+g+8, cols dt*8 + 2t + {0,1} ----
+    float oacc[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.f;
+    const int kend = (Lk + 7) & ~7;
+    for (int k0 = 0; k0 < kend; k0 += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(Ps[(rb + g) * PS + k0 + t], ah[0], al[0]);
+      split_tf32(Ps[(rb + g + 8) * PS + k0 + t], ah[1], al[1]);
+      split_tf32(Ps[(rb + g) * PS + k0 + t + 4], ah[2], al[2]);
+      split_tf32(Ps[(rb + g + 8) * PS + k0 + t + 4], ah[3], al[3]);
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        uint32_t bh[2], bl[2];
+        split_tf32(Vs[(k0 + t) * VS + dt * 8 + g], bh[0], bl[0]);
+        split_tf32(Vs[(k0 + t + 4) * VS + dt * 8 + g], bh[1], bl[1]);
+        mma3(oacc[dt], ah, al, bh, bl);
+      }
+    }
+    const int i0 = r0 + rb + g, i1 = i0 + 8;
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = h * HD + dt * 8 + 2 * t;
+      if (i0 < Lq) act_store2(p.o, n * p.o_rn + i0 * p.o_ri, col, oacc[dt][0], oacc[dt][1]);
+      if (i1 < Lq) act_store2(p.o, n * p.o_rn + i1 * p.o_ri, col, oacc[dt][2], oacc[dt][3]);
+    }
+  }
+}
+
+template <int NT8>
+inline int attn_mma_launch(Ctx& c, const AttnP& p) {
+  constexpr int LKP = 8 * NT8;
+  size_t smem = (size_t)(64 * 68 + LKP * 68 + LKP * 72 + 64 * (LKP + 4)) * 4;
+  auto kern = attn_mma_kernel<NT8>;
+  QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
+  return check_launch("attn_mma_kernel");
+}
+
 inline int attention(Ctx& c, const AttnP& p) {
   QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
   QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
@@ -462,6 +634,12 @@ inline int attention(Ctx& c, const AttnP& p) {
     return check_launch("attn_rows_kernel");
   }
   if (p.Lk > 32 || p.Lq >= 32) {
+    const char* ffma = getenv("QAT_ATTN_FFMA");     // A/B switch: the register-tiled FFMA core instead of mma.sync
+    if (!(ffma && ffma[0] == '1')) {
+      if (p.Lk <= 64) return attn_mma_launch<8>(c, p);
+      if (p.Lk <= 96) return attn_mma_launch<12>(c, p);
+      return attn_mma_launch<16>(c, p);
+    }
     if (p.Lk <= 64) return attn_tile_launch<2>(c, p);
     if (p.Lk <= 96) return attn_tile_launch<3>(c, p);
     return attn_tile_launch<4>(c, p);

@@ -130,20 +130,22 @@ __global__ void __launch_bounds__(TY* TX) gemm_simt_kernel(const float* __restri
   }
 }
 
-// Small-M variant (M < 1024: the per-question contractions, M = batch): 32x32 tiles, BK = 32, 64 threads with
-// 4x4 micro-tiles => N/32 * M/32 CTAs keep every SM busy where the 64x64 tiling would launch a few dozen.
-__global__ void __launch_bounds__(64) gemm_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
-                                                        Epi epi, Act C, int M, int N, int K) {
-  constexpr int BM = 32, BN = 32, BK = 32, NT = 64, PAD = 4;
-  __shared__ __align__(16) float As[2][BK][BM + PAD];
-  __shared__ __align__(16) float Ws[2][BK][BN + PAD];
-  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
+// Small-M variant (M < 1024: the per-question contractions, M = batch): 32x32 output tiles so N/32 * M/32 CTAs
+// cover the SMs, and the K loop is split over KG groups of 64 threads inside the CTA (named barriers per group,
+// fixed-order reduction through shared memory => deterministic) so each SM holds 8 warps of independent work.
+constexpr int SMALL_KG = 4;
+__global__ void __launch_bounds__(64 * SMALL_KG) gemm_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
+                                                                    Epi epi, Act C, int M, int N, int K) {
+  constexpr int BM = 32, BN = 32, BK = 16, NT = 64, PAD = 4;
+  __shared__ __align__(16) float As[SMALL_KG][2][BK][BM + PAD];
+  __shared__ __align__(16) float Ws[SMALL_KG][2][BK][BN + PAD];
+  const int g = threadIdx.x / NT, tid = threadIdx.x % NT, tx = tid & 7, ty = tid >> 3;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float4 ra[4], rw[4];
+  float4 ra[2], rw[2];
   auto gload = [&](int k0) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = tid + i * NT, r = f >> 3, kq = f & 7;
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * NT, r = f >> 2, kq = f & 3;
       const bool kin = k0 + kq * 4 < K;
       ra[i] = (m0 + r < M && kin) ? __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
       rw[i] = (n0 + r < N && kin) ? __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ldw + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
@@ -151,39 +153,59 @@ __global__ void __launch_bounds__(64) gemm_small_kernel(const float* __restrict_
   };
   auto sstore = [&](int buf) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = tid + i * NT, r = f >> 3, kq = f & 7;
-      As[buf][kq * 4 + 0][r] = ra[i].x; As[buf][kq * 4 + 1][r] = ra[i].y; As[buf][kq * 4 + 2][r] = ra[i].z; As[buf][kq * 4 + 3][r] = ra[i].w;
-      Ws[buf][kq * 4 + 0][r] = rw[i].x; Ws[buf][kq * 4 + 1][r] = rw[i].y; Ws[buf][kq * 4 + 2][r] = rw[i].z; Ws[buf][kq * 4 + 3][r] = rw[i].w;
+    for (int i = 0; i < 2; ++i) {
+      const int f = tid + i * NT, r = f >> 2, kq = f & 3;
+      As[g][buf][kq * 4 + 0][r] = ra[i].x; As[g][buf][kq * 4 + 1][r] = ra[i].y; As[g][buf][kq * 4 + 2][r] = ra[i].z; As[g][buf][kq * 4 + 3][r] = ra[i].w;
+      Ws[g][buf][kq * 4 + 0][r] = rw[i].x; Ws[g][buf][kq * 4 + 1][r] = rw[i].y; Ws[g][buf][kq * 4 + 2][r] = rw[i].z; Ws[g][buf][kq * 4 + 3][r] = rw[i].w;
     }
   };
+  auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(NT) : "memory"); };
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const int nk = (K + BK - 1) / BK;
-  gload(0);
-  sstore(0);
-  __syncthreads();
-  for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) gload((kt + 1) * BK);
+  const int my = (nk - g + SMALL_KG - 1) / SMALL_KG;      // k-tiles g, g+KG, ... of this group
+  if (my > 0) {
+    gload(g * BK);
+    sstore(0);
+    group_sync();
+    for (int it = 0; it < my; ++it) {
+      const int buf = it & 1;
+      if (it + 1 < my) gload((g + (it + 1) * SMALL_KG) * BK);
 #pragma unroll
-    for (int k = 0; k < BK; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      for (int k = 0; k < BK; ++k) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[g][buf][k][ty * 4]);
+        const float4 b = *reinterpret_cast<const float4*>(&Ws[g][buf][k][tx * 4]);
+        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    if (kt + 1 < nk) {
-      sstore(buf ^ 1);
-      __syncthreads();
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+      }
+      if (it + 1 < my) {
+        sstore(buf ^ 1);
+        group_sync();
+      }
     }
   }
+  // fixed-order reduction over the K groups: groups 1.. park their tiles in their own (now idle) A buffers
+  __syncthreads();
+  if (g > 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      *reinterpret_cast<float4*>(&As[g][0][0][0] + (ty * 4 + i) * 32 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  __syncthreads();
+  if (g > 0) return;
+#pragma unroll
+  for (int gg = 1; gg < SMALL_KG; ++gg)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = *reinterpret_cast<const float4*>(&As[gg][0][0][0] + (ty * 4 + i) * 32 + tx * 4);
+      acc[i][0] += t.x; acc[i][1] += t.y; acc[i][2] += t.z; acc[i][3] += t.w;
+    }
   const bool vec_ok = ((C.ld & 3) == 0) && (epi.res == nullptr || (epi.ldr & 3) == 0);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -218,7 +240,7 @@ inline int gemm_simt(Ctx& c, const float* A, int lda, long long M, const float* 
     gemm_simt_kernel<16, 16><<<grid, 256, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
   } else {
     dim3 grid((N + 31) / 32, (unsigned)((M + 31) / 32));
-    gemm_small_kernel<<<grid, 64, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
+    gemm_small_kernel<<<grid, 64 * SMALL_KG, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
   }
   return check_launch("gemm_simt_kernel");
 }

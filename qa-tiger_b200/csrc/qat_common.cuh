@@ -96,6 +96,19 @@ __device__ __forceinline__ void act_store4(const Act& a, long long row, int col,
   }
 }
 
+// store 2 consecutive values (col even)
+__device__ __forceinline__ void act_store2(const Act& a, long long row, int col, float v0, float v1) {
+  long long off = row * a.ld + col;
+  if (a.f) *reinterpret_cast<float2*>(a.f + off) = make_float2(v0, v1);
+  if (a.hi) {
+    bf16 h0, h1, l0, l1;
+    split_bf16(v0, h0, l0);
+    split_bf16(v1, h1, l1);
+    *reinterpret_cast<__nv_bfloat162*>(a.hi + off) = __halves2bfloat162(h0, h1);
+    if (a.lo) *reinterpret_cast<__nv_bfloat162*>(a.lo + off) = __halves2bfloat162(l0, l1);
+  }
+}
+
 __device__ __forceinline__ void act_store1(const Act& a, long long row, int col, float v) {
   long long off = row * a.ld + col;
   if (a.f) a.f[off] = v;

@@ -1,0 +1,26 @@
+"""Profiling aid (not a test): the tcgen05 GEMM kinds at the step's largest shapes, CUDA-graph timed."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from qa_tiger_b200 import _cabi
+dev = torch.device("cuda:0")
+shapes = {"tf32_slf_in": (1, 57344, 1536, 512), "tf32_proj": (1, 57344, 512, 1024), "tf32_slf_out": (1, 57344, 512, 512),
+          "x3_in_src": (2, 15360, 3584, 512), "x3_w1": (2, 15360, 1792, 512)}
+which = sys.argv[1:] or list(shapes)
+for nm in which:
+    kind, M, N, K = shapes[nm]
+    a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * K ** -0.5
+    lin = _cabi.Lin(w, torch.randn(N, device=dev), _cabi.PREC_BF16)
+    planes = _cabi.split_planes(a) if kind == 2 else None
+    for _ in range(2): _cabi.gemm(kind, a, lin, a_planes=planes)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(5): _cabi.gemm(kind, a, lin, a_planes=planes)
+    g.replay(); torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4): g.replay()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    print(f"{nm}: [{M},{K}]x[{N},{K}]^T kind={kind}  {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.0f} TFLOP/s nominal")
