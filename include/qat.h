@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define QAT_ABI_VERSION 1
+#define QAT_ABI_VERSION 2
 
 enum {
   QAT_OK = 0,
@@ -40,20 +40,25 @@ enum {
 /* Arithmetic mode of the dense contractions (error budget in DESIGN.md). */
 enum {
   QAT_PREC_FP32 = 0, /* fp32 FFMA on CUDA cores: the 1e-5 parity gate */
-  QAT_PREC_BF16 = 1  /* "bf16 mode": tcgen05 tensor cores, fp32 accumulate in TMEM; operands are
-                        bf16 hi+lo pairs (3 MMAs per product) on the serial chain and tf32 on the
-                        patch path; router / Gaussian / rank path stays fp32: the 1e-3 gate */
+  QAT_PREC_BF16 = 1  /* "bf16 mode" (16-bit tensor-core operands): tcgen05, fp32 accumulate in TMEM;
+                        bf16 hi+lo pairs (3 MMAs per product) on the serial chain that feeds the router,
+                        tf32 for patch_proj (straight from the fp32 input) and single fp16 planes
+                        (round-to-nearest) inside PatchSelecter; router / Gaussian / rank path stays
+                        fp32: the 1e-3 gate */
 };
 
 /* Element type of the streamed tensor of qat_gauss_reduce_fwd. */
 enum { QAT_DT_F32 = 0, QAT_DT_BF16 = 1 };
 
 /* One nn.Linear: y = x W^T + b.  `w` is the reference parameter itself ([n,k] row-major fp32);
- * `w_hi`/`w_lo` are its bf16 split (w ~= hi + lo), required only with QAT_PREC_BF16. */
+ * `w_hi`/`w_lo` are its bf16 split (w ~= hi + lo) and `w_f16` its fp16 rounding; they are read only
+ * with QAT_PREC_BF16 (w_f16 only by the PatchSelecter weights slf_in / slf_out / crs_kv; without it
+ * that block runs tf32 on fp32 activations). */
 typedef struct {
   const float* w;
   const void* w_hi;
   const void* w_lo;
+  const void* w_f16;
   const float* bias; /* [n] or NULL */
   int32_t n, k;
 } QatLinearW;
@@ -81,7 +86,8 @@ int qat_linear_fwd(const QatLinearArgs* a);
  *      parity tests and roofline timing of the GEMM kernels in isolation) ------------------------- */
 enum { QAT_GEMM_SIMT = 0,   /* fp32 FFMA, reads a / w.w */
        QAT_GEMM_TF32 = 1,   /* tcgen05 kind::tf32, reads a / w.w */
-       QAT_GEMM_BF16X3 = 2  /* tcgen05 kind::f16 x3, reads (a_hi, a_lo) / (w.w_hi, w.w_lo) */ };
+       QAT_GEMM_BF16X3 = 2, /* tcgen05 kind::f16 x3, reads (a_hi, a_lo) / (w.w_hi, w.w_lo) */
+       QAT_GEMM_F16 = 3     /* tcgen05 kind::f16, reads a_f16 / w.w_f16 */ };
 typedef struct {
   int32_t kind;
   int32_t M;
@@ -89,14 +95,17 @@ typedef struct {
   const float* a;      /* [M, lda] fp32 (SIMT, TF32) */
   const void* a_hi;    /* [M, lda] bf16 planes (BF16X3) */
   const void* a_lo;
+  const void* a_f16;   /* [M, lda] fp16 plane (F16) */
   int32_t lda;
   QatLinearW w;        /* [n, k] */
   int32_t relu;
   const float* res;    /* optional residual [M, ldr], added after the activation */
+  const void* res_f16; /* the same as an fp16 plane (tensor-core kinds only; `res` wins if both are set) */
   int32_t ldr;
-  float* c;            /* any of the three outputs may be NULL */
+  float* c;            /* any of the outputs may be NULL */
   void* c_hi;
   void* c_lo;
+  void* c_f16;         /* fp16 plane; when it is the only output the tile leaves through a TMA store */
   int32_t ldc;
 } QatGemmArgs;
 int qat_gemm(const QatGemmArgs* a);

@@ -21,7 +21,7 @@ c_f32p = C.c_void_p  # all device pointers travel as void*
 
 
 class LinearW(C.Structure):
-    _fields_ = [("w", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p),
+    _fields_ = [("w", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("w_f16", C.c_void_p), ("bias", C.c_void_p),
                 ("n", C.c_int32), ("k", C.c_int32)]
 
 
@@ -37,8 +37,9 @@ class LinearArgs(C.Structure):
 
 class GemmArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("M", C.c_int32), ("stream", C.c_void_p), ("a", C.c_void_p), ("a_hi", C.c_void_p),
-                ("a_lo", C.c_void_p), ("lda", C.c_int32), ("w", LinearW), ("relu", C.c_int32), ("res", C.c_void_p),
-                ("ldr", C.c_int32), ("c", C.c_void_p), ("c_hi", C.c_void_p), ("c_lo", C.c_void_p), ("ldc", C.c_int32)]
+                ("a_lo", C.c_void_p), ("a_f16", C.c_void_p), ("lda", C.c_int32), ("w", LinearW), ("relu", C.c_int32),
+                ("res", C.c_void_p), ("res_f16", C.c_void_p), ("ldr", C.c_int32), ("c", C.c_void_p), ("c_hi", C.c_void_p),
+                ("c_lo", C.c_void_p), ("c_f16", C.c_void_p), ("ldc", C.c_int32)]
 
 
 class AvqArgs(C.Structure):
@@ -149,7 +150,7 @@ def lib():
                 for name, (res, args) in EXPORTS.items():
                     fn = getattr(l, name)
                     fn.restype, fn.argtypes = res, args
-                if l.qat_abi_version() != 1:
+                if l.qat_abi_version() != 2:
                     raise RuntimeError("libqat_b200.so ABI version mismatch")
                 _lib = l
     return _lib
@@ -184,15 +185,17 @@ class Lin:
     """A prepared nn.Linear operand: fp32 weight (+ bf16 hi/lo split when prec == bf16) and bias.
     Holds the tensors alive; `.c` is the C struct."""
 
-    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], prec: int):
+    def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], prec: int, f16: bool = False):
         w = w.detach().contiguous().float()
         self.w = w
         self.b = None if b is None else b.detach().contiguous().float()
-        self.hi = self.lo = None
+        self.hi = self.lo = self.h = None
         if prec == PREC_BF16:
             self.hi = w.to(torch.bfloat16)
             self.lo = (w - self.hi.float()).to(torch.bfloat16)
-        self.c = LinearW(ptr(w), ptr(self.hi), ptr(self.lo), ptr(self.b), w.shape[0], w.shape[1])
+            if f16:
+                self.h = w.to(torch.float16)
+        self.c = LinearW(ptr(w), ptr(self.hi), ptr(self.lo), ptr(self.h), ptr(self.b), w.shape[0], w.shape[1])
 
 
 class LN:
@@ -206,7 +209,7 @@ def params_version(module: torch.nn.Module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=True))
 
 
-GEMM_SIMT, GEMM_TF32, GEMM_BF16X3 = 0, 1, 2
+GEMM_SIMT, GEMM_TF32, GEMM_BF16X3, GEMM_F16 = 0, 1, 2, 3
 
 
 def split_planes(x: torch.Tensor):
@@ -215,8 +218,9 @@ def split_planes(x: torch.Tensor):
 
 
 def gemm(kind: int, a: torch.Tensor, lin: "Lin", relu: bool = False, res: Optional[torch.Tensor] = None,
-         out_planes: bool = False, a_planes=None):
-    """One contraction C = act(A W^T + b) + res on the chosen engine (parity tests / roofline timing)."""
+         out_planes: bool = False, a_planes=None, out_f16: bool = False):
+    """One contraction C = act(A W^T + b) + res on the chosen engine (parity tests / roofline timing).
+    out_f16: the only output is an fp16 plane (TMA-store epilogue); `res` may then be an fp16 tensor."""
     M, K = a.shape
     N = lin.w.shape[0]
     dev = a.device
@@ -227,10 +231,23 @@ def gemm(kind: int, a: torch.Tensor, lin: "Lin", relu: bool = False, res: Option
         hi, lo = a_planes if a_planes is not None else split_planes(a)
         hold += [hi, lo]
         g.a_hi, g.a_lo = hi.data_ptr(), lo.data_ptr()
+    elif kind == GEMM_F16:
+        ah = a if a.dtype == torch.float16 else a.to(torch.float16)
+        hold.append(ah)
+        g.a_f16, g.lda = ah.data_ptr(), ah.stride(0)
     else:
         g.a = a.data_ptr()
     if res is not None:
-        g.res, g.ldr = res.data_ptr(), res.stride(0)
+        if res.dtype == torch.float16:
+            g.res_f16, g.ldr = res.data_ptr(), res.stride(0)
+        else:
+            g.res, g.ldr = res.data_ptr(), res.stride(0)
+    if out_f16:
+        c = torch.empty(M, N, device=dev, dtype=torch.float16)
+        g.c_f16 = c.data_ptr()
+        with torch.cuda.device(dev):
+            check(lib().qat_gemm(C.byref(g)), "qat_gemm")
+        return c
     c = torch.empty(M, N, device=dev, dtype=torch.float32)
     g.c = c.data_ptr()
     planes = None

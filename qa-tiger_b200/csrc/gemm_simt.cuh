@@ -11,6 +11,7 @@ struct Epi {
   int relu = 0;
   const float* res = nullptr;   // [M, ldr] added after the activation
   int ldr = 0;
+  const __half* res_h = nullptr;  // the same residual as an fp16 plane (tensor-core GEMMs only; res wins if both are set)
 };
 
 // Tile = (8*TY) x (8*TX), BK = 16, TY*TX threads; each thread owns two 4-row and two 4-col strips

@@ -2,6 +2,7 @@
 // Every entry point: validate -> carve the caller's workspace -> enqueue kernels on the caller's stream.
 // No allocation, no synchronisation, no global mutable state.
 #include "attn_core.cuh"
+#include "attn_f16.cuh"
 #include "gauss.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -19,6 +20,7 @@ struct WView {
   const float* w = nullptr;
   const bf16* hi = nullptr;
   const bf16* lo = nullptr;
+  const __half* h16 = nullptr;
   const float* bias = nullptr;
   int n = 0, k = 0;
 };
@@ -31,6 +33,7 @@ static WView wview(const QatLinearW& W, int n0 = 0, int n = -1) {
   v.w = W.w ? W.w + (size_t)n0 * W.k : nullptr;
   v.hi = W.w_hi ? reinterpret_cast<const bf16*>(W.w_hi) + (size_t)n0 * W.k : nullptr;
   v.lo = W.w_lo ? reinterpret_cast<const bf16*>(W.w_lo) + (size_t)n0 * W.k : nullptr;
+  v.h16 = W.w_f16 ? reinterpret_cast<const __half*>(W.w_f16) + (size_t)n0 * W.k : nullptr;
   v.bias = W.bias ? W.bias + n0 : nullptr;
   return v;
 }
@@ -43,7 +46,7 @@ static int check_w(const QatLinearW& W, int n, int k, const char* name, int prec
 }
 
 // Which engine runs a given contraction (DESIGN.md "precision policy").
-enum GemmKind { G_SIMT = 0, G_TF32 = 1, G_BF16X3 = 2 };
+enum GemmKind { G_SIMT = 0, G_TF32 = 1, G_BF16X3 = 2, G_F16 = 3 };
 
 static GemmKind pick_kind(const Ctx& c, long long M, int N, int K, bool patch_path, const WView& W) {
   if (c.prec != QAT_PREC_BF16) return G_SIMT;
@@ -67,6 +70,9 @@ static int gemm(Ctx& c, GemmKind kind, const Act& A, long long M, const WView& W
     case G_BF16X3:
       QAT_REQUIRE(c.dry || (A.hi && A.lo && W.hi && W.lo), "gemm: bf16 hi/lo operand planes missing");
       return gemm_tc_bf16x3(c, A.hi, A.lo, A.ld, M, W.hi, W.lo, W.n, W.k, epi, C);
+    case G_F16:
+      QAT_REQUIRE(c.dry || (A.h && W.h16), "gemm: fp16 operand plane missing");
+      return gemm_tc_f16(c, A.h, A.ld, M, W.h16, W.n, W.k, epi, C);
   }
   return QAT_EINVAL;
 }
@@ -116,21 +122,25 @@ static int run_linear(const QatLinearArgs* a, Ctx& c) {
 }
 
 static int run_gemm(const QatGemmArgs* a, Ctx& c) {
-  QAT_REQUIRE(a->kind >= G_SIMT && a->kind <= G_BF16X3, "gemm: unknown kind %d", a->kind);
+  QAT_REQUIRE(a->kind >= G_SIMT && a->kind <= G_F16, "gemm: unknown kind %d", a->kind);
   QAT_REQUIRE(a->M >= 0 && a->w.n > 0 && a->w.k > 0 && a->lda >= a->w.k && a->ldc >= a->w.n, "gemm: bad shape");
   Act A, C;
   A.f = const_cast<float*>(a->a);
   A.hi = reinterpret_cast<bf16*>(const_cast<void*>(a->a_hi));
   A.lo = reinterpret_cast<bf16*>(const_cast<void*>(a->a_lo));
+  A.h = reinterpret_cast<__half*>(const_cast<void*>(a->a_f16));
   A.ld = a->lda;
   C.f = a->c;
   C.hi = reinterpret_cast<bf16*>(a->c_hi);
   C.lo = reinterpret_cast<bf16*>(a->c_lo);
+  C.h = reinterpret_cast<__half*>(a->c_f16);
   C.ld = a->ldc;
   Epi e;
   e.relu = a->relu;
   e.res = a->res;
+  e.res_h = reinterpret_cast<const __half*>(a->res_f16);
   e.ldr = a->ldr;
+  QAT_REQUIRE(a->kind != G_SIMT || !e.res_h, "gemm: the SIMT engine takes fp32 residuals only");
   return gemm(c, (GemmKind)a->kind, A, a->M, wview(a->w), e, C);
 }
 
@@ -237,6 +247,7 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
   const int Cin = a->has_proj ? a->Cin : D;
   // frames per pass: keep the per-pass intermediates (~ P*D*4*(1+3+1+1+2) bytes per frame) near L2 size
   long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 4096;
+  if (a->chunk_frames <= 0 && getenv("QAT_PATCH_CHUNK")) chunk = atoll(getenv("QAT_PATCH_CHUNK")) > 0 ? atoll(getenv("QAT_PATCH_CHUNK")) : chunk;
   if (chunk > BT) chunk = BT;
   const float scale = 0.125f;
   const WView Wp = wview(a->proj), Wsi = wview(a->slf_in), Wso = wview(a->slf_out), Wq = wview(a->crs_q), Wkv = wview(a->crs_kv);
@@ -257,13 +268,50 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
   const GemmKind k_m2 = pick_kind(c, 2 * BT, D, D / 2, false, Wm2);
   QAT_TRY(act_alloc(c, O2, 2 * BT, D, !reads_planes(k_co), reads_planes(k_co)));
 
+  // bf16 mode, P <= 16: activations between the kernels of a pass are single fp16 planes (half the bytes of
+  // fp32, tf32-grade operands at twice the tf32 MMA rate), attention through mma.sync; DESIGN.md section 3.
+  const bool f16_path = c.prec == QAT_PREC_BF16 && P <= 16 && H <= 8 && D % 64 == 0 && Wsi.h16 && Wso.h16 && Wkv.h16 &&
+                        !(getenv("QAT_PATCH_FP32_PLANES") && getenv("QAT_PATCH_FP32_PLANES")[0] == '1');
   const size_t mark = c.mark();
   for (long long f0 = 0; f0 < BT; f0 += chunk) {
     const long long nf = (BT - f0 < chunk) ? BT - f0 : chunk;
     const long long rows = nf * P;
     c.release(mark);
-    Act Pp, QKV, Oa, P2, KV;
     const float* pin = a->patch + (size_t)f0 * P * Cin;
+    AttnP q;
+    q.nseq = (int)nf; q.H = H; q.Lq = 2; q.Lk = P; q.scale = scale;
+    q.q = Q2.f + (size_t)f0 * 2 * D; q.q_sn = 2 * D; q.q_si = D;
+    q.k_sn = (long long)P * 2 * D; q.k_si = 2 * D; q.k_shift = 0; q.k_mod = (int)nf;
+    q.o = O2.rows(2 * f0); q.o_rn = 2; q.o_ri = 1; q.attw = nullptr;
+    if (f16_path) {
+      Act Pp, QKV, Oa, P2, KV;
+      QAT_TRY(act_alloc_h(c, Pp, rows, D));
+      if (a->has_proj) {
+        const GemmKind kp = (Cin % 32 == 0) ? G_TF32 : G_SIMT;
+        QAT_TRY(gemm(c, kp, act_of(pin, Cin), rows, Wp, Epi(), Pp));
+      } else {
+        QAT_TRY(add_rows(c, pin, D, nullptr, 0, Pp, rows, D));
+      }
+      QAT_TRY(act_alloc_h(c, QKV, rows, 3 * D));
+      QAT_TRY(gemm(c, G_F16, Pp, rows, Wsi, Epi(), QKV));
+      QAT_TRY(act_alloc_h(c, Oa, rows, D));
+      AttnHP hp;
+      hp.q = QKV.h; hp.k = QKV.h + D; hp.v = QKV.h + 2 * D; hp.ld = 3 * D;
+      hp.o = Oa.h; hp.ldo = D; hp.nseq = (int)nf; hp.H = H; hp.L = P; hp.scale = scale;
+      QAT_TRY(attention_small_f16(c, hp));
+      // p' = p + slf_attn(p)   (:688, no LayerNorm)
+      QAT_TRY(act_alloc_h(c, P2, rows, D));
+      {
+        Epi e;
+        e.res_h = Pp.h; e.ldr = Pp.ld;
+        QAT_TRY(gemm(c, G_F16, Oa, rows, Wso, e, P2));
+      }
+      QAT_TRY(act_alloc_h(c, KV, rows, 2 * D));
+      QAT_TRY(gemm(c, G_F16, P2, rows, Wkv, Epi(), KV));
+      QAT_TRY(attention_fewq_f16(c, q, KV.h, KV.h + D));
+      continue;
+    }
+    Act Pp, QKV, Oa, P2, KV;
     if (a->has_proj) {
       QAT_TRY(act_alloc(c, Pp, rows, D, true, false));
       QAT_TRY(gemm(c, pick_kind(c, rows, D, Cin, true, Wp), act_of(pin, Cin), rows, Wp, Epi(), Pp));
@@ -288,11 +336,7 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
     }
     QAT_TRY(act_alloc(c, KV, rows, 2 * D, true, false));
     QAT_TRY(gemm(c, pick_kind(c, rows, 2 * D, D, true, Wkv), P2, rows, Wkv, Epi(), KV));
-    AttnP q;
-    q.nseq = (int)nf; q.H = H; q.Lq = 2; q.Lk = P; q.scale = scale;
-    q.q = Q2.f + (size_t)f0 * 2 * D; q.q_sn = 2 * D; q.q_si = D;
-    q.k = KV.f; q.v = KV.f + D; q.k_sn = (long long)P * 2 * D; q.k_si = 2 * D; q.k_shift = 0; q.k_mod = (int)nf;
-    q.o = O2.rows(2 * f0); q.o_rn = 2; q.o_ri = 1; q.attw = nullptr;
+    q.k = KV.f; q.v = KV.f + D;
     QAT_TRY(attention(c, q));
   }
   c.release(mark);

@@ -1,6 +1,7 @@
 // Shared host/device helpers for libqat_b200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -43,19 +44,22 @@ extern thread_local long long g_launches;
   } while (0)
 
 // ------------------------------------------------------------------------------------------------
-// An activation as the kernels see it: fp32 and/or a bf16 (hi, lo) pair, all with the same leading
-// dimension.  x ~= hi + lo carries 16 mantissa bits, which is what the bf16x3 tensor-core GEMMs eat.
+// An activation as the kernels see it: fp32 and/or a bf16 (hi, lo) pair and/or one fp16 plane, all with
+// the same leading dimension.  x ~= hi + lo carries 16 mantissa bits, which is what the bf16x3 tensor-core
+// GEMMs eat; the fp16 plane (11 significant bits, round-to-nearest) is the storage format of the patch path.
 // ------------------------------------------------------------------------------------------------
 struct Act {
   float* f = nullptr;
   bf16* hi = nullptr;
   bf16* lo = nullptr;
+  __half* h = nullptr;
   int ld = 0;
   __host__ __device__ Act cols(int c0) const {
     Act a = *this;
     if (a.f) a.f += c0;
     if (a.hi) a.hi += c0;
     if (a.lo) a.lo += c0;
+    if (a.h) a.h += c0;
     return a;
   }
   __host__ __device__ Act rows(long long r0) const {
@@ -63,9 +67,18 @@ struct Act {
     if (a.f) a.f += r0 * ld;
     if (a.hi) a.hi += r0 * ld;
     if (a.lo) a.lo += r0 * ld;
+    if (a.h) a.h += r0 * ld;
     return a;
   }
 };
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  __half2 t = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
 
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
   hi = __float2bfloat16_rn(v);
@@ -94,6 +107,7 @@ __device__ __forceinline__ void act_store4(const Act& a, long long row, int col,
       *reinterpret_cast<uint2*>(a.lo + off) = u;
     }
   }
+  if (a.h) *reinterpret_cast<uint2*>(a.h + off) = make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
 }
 
 // store 2 consecutive values (col even)
@@ -107,6 +121,7 @@ __device__ __forceinline__ void act_store2(const Act& a, long long row, int col,
     *reinterpret_cast<__nv_bfloat162*>(a.hi + off) = __halves2bfloat162(h0, h1);
     if (a.lo) *reinterpret_cast<__nv_bfloat162*>(a.lo + off) = __halves2bfloat162(l0, l1);
   }
+  if (a.h) *reinterpret_cast<uint32_t*>(a.h + off) = pack_half2(v0, v1);
 }
 
 __device__ __forceinline__ void act_store1(const Act& a, long long row, int col, float v) {
@@ -118,6 +133,7 @@ __device__ __forceinline__ void act_store1(const Act& a, long long row, int col,
     a.hi[off] = h;
     if (a.lo) a.lo[off] = l;
   }
+  if (a.h) a.h[off] = __float2half_rn(v);
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -235,6 +251,15 @@ inline int act_alloc(Ctx& c, Act& a, long long rows, int ld, bool want_f, bool w
     a.lo = reinterpret_cast<bf16*>(c.alloc(size_t(rows) * ld * 2));
     if (!a.hi || !a.lo) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
   }
+  return QAT_OK;
+}
+
+// a single fp16 plane [rows, ld] (patch-path storage format)
+inline int act_alloc_h(Ctx& c, Act& a, long long rows, int ld) {
+  a = Act();
+  a.ld = ld;
+  a.h = reinterpret_cast<__half*>(c.alloc(size_t(rows) * ld * 2));
+  if (!a.h) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
   return QAT_OK;
 }
 

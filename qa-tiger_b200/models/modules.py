@@ -353,10 +353,10 @@ class PatchSelecter(_QatModule):
         D = self.d_model
         s, c = self.slf_attn, self.crs_attn
         return dict(
-            slf_in=cabi.Lin(s.in_proj_weight, s.in_proj_bias, prec),
-            slf_out=cabi.Lin(s.out_proj.weight, s.out_proj.bias, prec),
+            slf_in=cabi.Lin(s.in_proj_weight, s.in_proj_bias, prec, f16=True),
+            slf_out=cabi.Lin(s.out_proj.weight, s.out_proj.bias, prec, f16=True),
             crs_q=cabi.Lin(c.in_proj_weight[:D], c.in_proj_bias[:D], prec),
-            crs_kv=cabi.Lin(c.in_proj_weight[D:], c.in_proj_bias[D:], prec),
+            crs_kv=cabi.Lin(c.in_proj_weight[D:], c.in_proj_bias[D:], prec, f16=True),
             crs_out=cabi.Lin(c.out_proj.weight, c.out_proj.bias, prec),
             mlp0=cabi.Lin(self.mlp[0].weight, self.mlp[0].bias, prec),
             mlp2=cabi.Lin(self.mlp[2].weight, self.mlp[2].bias, prec),

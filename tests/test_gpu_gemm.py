@@ -44,3 +44,45 @@ def test_gemm_tile_widths(bn, monkeypatch):
     ref = a.double() @ w.double().t()
     assert relerr(_cabi.gemm(2, a, lin), ref) < 2e-5
     assert relerr(_cabi.gemm(1, a, lin), ref) < 1.5e-3
+
+
+F16_SHAPES = [(128, 128, 64), (1, 8, 64), (130, 72, 128), (1000, 512, 512), (4096, 1536, 512), (14 * 50, 1024, 512), (257, 256, 1856),
+              (57344, 512, 512), (126, 1536, 512)]
+
+
+@pytest.mark.parametrize("M,N,K", F16_SHAPES)
+def test_gemm_f16_kind(M, N, K):
+    """tcgen05 kind::f16 on single fp16 planes: exact products of the fp16-rounded operands, fp32 accumulate."""
+    from qa_tiger_b200 import _cabi
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev(), generator=g).half()
+    w = torch.randn(N, K, device=dev(), generator=g) * K ** -0.5
+    b = torch.randn(N, device=dev(), generator=g)
+    res = torch.randn(M, N, device=dev(), generator=g).half()
+    lin = _cabi.Lin(w, b, _cabi.PREC_BF16, f16=True)
+    ref = a.double() @ lin.h.double().t() + b.double()
+    got = _cabi.gemm(_cabi.GEMM_F16, a, lin)                       # generic epilogue, fp32 out
+    assert relerr(got, ref) < 2e-6
+    got_h = _cabi.gemm(_cabi.GEMM_F16, a, lin, out_f16=True)       # TMA-store epilogue
+    assert got_h.dtype == torch.float16
+    assert torch.equal(got_h, got.half())
+    ref2 = torch.relu(ref) + res.double()
+    got2 = _cabi.gemm(_cabi.GEMM_F16, a, lin, relu=True, res=res, out_f16=True)
+    assert relerr(got2, ref2) < 4e-4
+    got3 = _cabi.gemm(_cabi.GEMM_F16, a, lin, relu=True, res=res)  # fp16 residual through the generic epilogue
+    assert relerr(got3, ref2) < 2e-6
+    assert torch.equal(got2, got3.half())
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 512, 1024), (14 * 300, 512, 1024), (77, 256, 96)])
+def test_gemm_tf32_to_f16_plane(M, N, K):
+    """patch_proj form: tf32 contraction of fp32 operands whose only output is an fp16 plane (TMA store)."""
+    from qa_tiger_b200 import _cabi
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device=dev(), generator=g)
+    w = torch.randn(N, K, device=dev(), generator=g) * K ** -0.5
+    b = torch.randn(N, device=dev(), generator=g)
+    lin = _cabi.Lin(w, b, _cabi.PREC_BF16)
+    full = _cabi.gemm(_cabi.GEMM_TF32, a, lin)
+    got = _cabi.gemm(_cabi.GEMM_TF32, a, lin, out_f16=True)
+    assert torch.equal(got, full.half())
