@@ -9,15 +9,15 @@
 //                 tf32 MMA rate and half the bytes).  Used inside PatchSelecter, whose activations live in HBM/L2
 //                 as fp16 planes (error budget in DESIGN.md).
 //
-// Epilogues: the generic one (any mix of fp32 / bf16 hi,lo / fp16 output planes, smem transpose -> 16-byte
-// stores) and, when the only output is an fp16 plane, a TMA-store one: the warp packs its 32 x 64 sub-tile into
-// a 128B-swizzled smem box and one lane issues cp.async.bulk.tensor (row / column tails clipped by the TMA unit).
+// Epilogue: every output plane (fp32 / bf16 hi, lo / fp16) leaves through the TMA unit: an epilogue warp packs its
+// 32 x 32 sub-tile into a swizzled smem box and one lane issues cp.async.bulk.tensor (row / column tails clipped
+// by the TMA unit, no strided LSU stores).
 //
-// Structure (one 128 x BN output tile per CTA, 192 threads):
+// Structure (one 128 x BN output tile per CTA, 320 threads):
 //   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (128B swizzle) into a STAGES-deep smem ring
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem slots
-//   warps 2..5  : epilogue - tcgen05.ld (32 lanes x 32 columns) -> smem transpose -> bias/ReLU/residual
-//                 -> coalesced 16-byte stores of fp32 and/or bf16 (hi, lo) planes
+//   warps 2..9  : epilogue - tcgen05.ld (32 lanes x 32 columns) -> bias/ReLU/residual in registers -> swizzled
+//                 smem box -> TMA store per plane (two warps per TMEM lane quarter, one per column half)
 // Both operands are K-major; smem tiles are rows of 128 bytes (32 tf32 / 64 bf16), 8-row 1024-byte swizzle atoms.
 #pragma once
 #include <cuda.h>
@@ -80,11 +80,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "memory");
 }
 
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 struct GemmP {
   int M, N, K;
   Epi epi;
   Act C;
-  int tma_store;   // 1: the only output is C.h and it leaves through the mC tensor map
+  int dbg;         // profiling switches (QAT_GEMM_DBG): 1 = epilogue releases the accumulator without reading it,
+                   // 2 = MMA issuer skips the MMAs, 4 = epilogue skips its global stores
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -103,7 +108,7 @@ struct Cfg {
   static constexpr int A_BYTES = BM * ROW_BYTES;                          // per plane
   static constexpr int W_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
-  static constexpr int EPI_BYTES = 4 * 2 * 4096;                          // generic: 4 warps x [32][36] floats; TMA store: 4 warps x 2 boxes x 4 KB
+  static constexpr int EPI_BYTES = 8 * 4096;                              // 8 epilogue warps x one 4 KB TMA-store box
   static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                                // two accumulators: epilogue(i) overlaps mainloop(i+1)
@@ -115,10 +120,11 @@ struct Cfg {
 //   full/empty[STAGES]   TMA <-> MMA    (smem ring, continuous across tiles)
 //   tfull/tempty[2]      MMA <-> epilogue (the two TMEM accumulators)
 template <int KIND, int BN, int STAGES>
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mW0, const __grid_constant__ CUtensorMap mW1,
-               const __grid_constant__ CUtensorMap mC, GemmP p) {
+               const __grid_constant__ CUtensorMap mCf, const __grid_constant__ CUtensorMap mChi,
+               const __grid_constant__ CUtensorMap mClo, const __grid_constant__ CUtensorMap mCh, GemmP p) {
   typedef Cfg<KIND, BN, STAGES> G;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -149,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);          // one arrival per epilogue warp
+      mbar_init(&tempty[a], 8);          // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -204,6 +210,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           const uint64_t dA1 = umma_desc(a0 + G::A_BYTES), dW1 = umma_desc(w0 + G::W_BYTES);
 #pragma unroll
           for (int k = 0; k < G::BK / G::UK; ++k) {
+            if (p.dbg & 2) break;
             const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
             if (G::PLANES == 1) {
               umma<KIND>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
@@ -219,124 +226,154 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue warps 2..5: TMEM lanes 32*(warp%4) =====================
+    // ===================== epilogue warps 2..9 =====================
+    // warp w may touch TMEM lanes 32*(w%4)..+31; warps 2..5 take columns [0, BN/2) of the tile, warps 6..9 the rest.
+    // Per 32-column chunk: tcgen05.ld (lane = row) -> bias / ReLU / residual in registers -> the warp's 32 x 32 box in
+    // shared memory in the TMA swizzle layout -> one lane issues cp.async.bulk.tensor stores (one per output plane);
+    // the TMA unit clips row / column tails, so the LSU never sees the (row-strided) output.
+    const int ew = warp - 2;
     const int lg = warp & 3;
-    float* tile = epi_smem + (warp - 2) * (32 * 36);
-    const int rq = lane >> 3, cq = lane & 7;
+    const int half = ew >> 2;
+    constexpr int HALF_N = BN / 2;
+    constexpr int NCH = HALF_N / 32;
+    unsigned char* box = reinterpret_cast<unsigned char*>(epi_smem) + ew * 4096;
+    const uint32_t sbox = smem_u32(box);
+    const uint32_t sw128 = uint32_t(lane & 7), sw64 = uint32_t((lane >> 1) & 3);
     uint32_t lt = 0;
-    if (p.tma_store) {
-      // ---- fp16-only output through the TMA unit: lane = row of the warp's 32 x 64 box ----
-      unsigned char* stg = reinterpret_cast<unsigned char*>(epi_smem) + (warp - 2) * 8192;
-      uint32_t nbox = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-        const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
-        const uint32_t as = lt & 1;
-        mbar_wait(&tfull[as], (lt >> 1) & 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + as * BN + (uint32_t(lg * 32) << 16);
-        const long long row = (long long)m0 + lg * 32 + lane;
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          if (n0 + c0 >= p.N) break;
-          uint32_t v[32], u[32];
-          tmem_ld32(tacc + uint32_t(c0), v);
-          tmem_ld32(tacc + uint32_t(c0 + 32), u);
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-          if (c0 + 64 >= BN || n0 + c0 + 64 >= p.N) {
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
-          }
-          unsigned char* box = stg + (nbox & 1) * 4096;
-          ++nbox;
-          // the box written two stores ago must have been read out by the TMA unit
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncwarp();
-          const int colb = n0 + c0;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {          // 8 columns = one 16-byte chunk of the row
-            float x[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(q < 4 ? v[8 * q + e] : u[8 * (q - 4) + e]);
-            const int col = colb + 8 * q;
-            if (col < p.N) {                     // N is a multiple of 8 on this path (host check)
-              if (p.epi.bias) {
-                const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col));
-                const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col + 4));
-                x[0] += b0.x; x[1] += b0.y; x[2] += b0.z; x[3] += b0.w;
-                x[4] += b1.x; x[5] += b1.y; x[6] += b1.z; x[7] += b1.w;
-              }
-              if (p.epi.relu) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) x[e] = fmaxf(x[e], 0.f);
-              }
-              if (p.epi.res_h && row < p.M) {
-                const uint4 r = __ldg(reinterpret_cast<const uint4*>(p.epi.res_h + row * p.epi.ldr + col));
-                const float2 r0 = unpack_half2(r.x), r1 = unpack_half2(r.y), r2 = unpack_half2(r.z), r3 = unpack_half2(r.w);
-                x[0] += r0.x; x[1] += r0.y; x[2] += r1.x; x[3] += r1.y;
-                x[4] += r2.x; x[5] += r2.y; x[6] += r3.x; x[7] += r3.y;
-              }
-            }
-            const uint4 o = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]), pack_half2(x[6], x[7]));
-            *reinterpret_cast<uint4*>(box + lane * 128 + ((q ^ (lane & 7)) << 4)) = o;
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&mC, box, colb, m0 + lg * 32);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-        }
-      }
-      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-    } else
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = lt & 1;
       mbar_wait(&tfull[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + as * BN + (uint32_t(lg * 32) << 16);
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= p.N) break;
+      const uint32_t tacc = tmem_base + as * BN + half * HALF_N + (uint32_t(lg * 32) << 16);
+      const long long row = (long long)m0 + lg * 32 + lane;
+      const bool row_ok = row < p.M;
+      if (p.dbg & 1) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+        continue;
+      }
+#pragma unroll 1
+      for (int c = 0; c < NCH; ++c) {
+        const int col0 = n0 + half * HALF_N + c * 32;
+        const bool live = col0 < p.N;                       // warp-uniform
         uint32_t v[32];
-        tmem_ld32(tacc + uint32_t(c0), v);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= BN || n0 + c0 + 32 >= p.N) {
-          // last TMEM read of this tile: hand the accumulator back to the MMA warp before the stores
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+        if (live) tmem_ld32(tacc + uint32_t(c * 32), v);
+        // operands of the epilogue are fetched while the TMEM load is in flight
+        float4 bb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          bb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && p.epi.bias && col0 + 4 * q < p.N) bb[q] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col0 + 4 * q));
         }
+        float4 rr[8];
+        if (p.epi.res) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          *reinterpret_cast<float4*>(tile + lane * 36 + q * 4) =
-              make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
-        __syncwarp();
-        const int col = n0 + c0 + cq * 4;
-        if (col < p.N) {   // N is a multiple of 4 (checked on the host)
-          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (p.epi.bias) bv = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col));
+          for (int q = 0; q < 8; ++q) {
+            rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && row_ok && col0 + 4 * q < p.N) rr[q] = __ldg(reinterpret_cast<const float4*>(p.epi.res + row * p.epi.ldr + col0 + 4 * q));
+          }
+        } else if (p.epi.res_h) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int r = i * 4 + rq;
-            const long long row = (long long)m0 + lg * 32 + r;
-            if (row < p.M) {
-              float4 x = *reinterpret_cast<const float4*>(tile + r * 36 + cq * 4);
-              x.x += bv.x; x.y += bv.y; x.z += bv.z; x.w += bv.w;
-              if (p.epi.relu) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
-              if (p.epi.res) {
-                float4 rr = __ldg(reinterpret_cast<const float4*>(p.epi.res + row * p.epi.ldr + col));
-                x.x += rr.x; x.y += rr.y; x.z += rr.z; x.w += rr.w;
-              } else if (p.epi.res_h) {
-                const uint2 rr = __ldg(reinterpret_cast<const uint2*>(p.epi.res_h + row * p.epi.ldr + col));
-                const float2 r0 = unpack_half2(rr.x), r1 = unpack_half2(rr.y);
-                x.x += r0.x; x.y += r0.y; x.z += r1.x; x.w += r1.y;
-              }
-              act_store4(p.C, row, col, x);
+          for (int q = 0; q < 8; ++q) {
+            rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && row_ok && col0 + 4 * q < p.N) {
+              const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.epi.res_h + row * p.epi.ldr + col0 + 4 * q));
+              const float2 r0 = unpack_half2(u.x), r1 = unpack_half2(u.y);
+              rr[q] = make_float4(r0.x, r0.y, r1.x, r1.y);
             }
           }
         }
-        __syncwarp();
+        if (live) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == NCH - 1) {
+          // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+        }
+        if (!live) continue;
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          x[4 * q] = __uint_as_float(v[4 * q]) + bb[q].x;
+          x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb[q].y;
+          x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb[q].z;
+          x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb[q].w;
+        }
+        if (p.epi.relu) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = fmaxf(x[e], 0.f);
+        }
+        if (p.epi.res || p.epi.res_h) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            x[4 * q] += rr[q].x; x[4 * q + 1] += rr[q].y; x[4 * q + 2] += rr[q].z; x[4 * q + 3] += rr[q].w;
+          }
+        }
+        const int crow = m0 + lg * 32;
+        if (p.C.f) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the box is free again
+          __syncwarp();
+#pragma unroll
+          for (uint32_t q = 0; q < 8; ++q)
+            sts128(sbox + lane * 128 + ((q ^ sw128) << 4), __float_as_uint(x[4 * q]), __float_as_uint(x[4 * q + 1]),
+                   __float_as_uint(x[4 * q + 2]), __float_as_uint(x[4 * q + 3]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 4)) {
+            tma_store_2d(&mCf, box, col0, crow);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (p.C.hi) {
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              bf16 h0, h1, l0, l1;
+              split_bf16(x[8 * q + 2 * e], h0, l0);
+              split_bf16(x[8 * q + 2 * e + 1], h1, l1);
+              __nv_bfloat162 hh = __halves2bfloat162(h0, h1), ll = __halves2bfloat162(l0, l1);
+              hw[e] = *reinterpret_cast<uint32_t*>(&hh);
+              lw[e] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+            sts128(sbox + lane * 64 + ((q ^ sw64) << 4), hw[0], hw[1], hw[2], hw[3]);
+            sts128(sbox + 2048 + lane * 64 + ((q ^ sw64) << 4), lw[0], lw[1], lw[2], lw[3]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 4)) {
+            tma_store_2d(&mChi, box, col0, crow);
+            if (p.C.lo) tma_store_2d(&mClo, box + 2048, col0, crow);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (p.C.h) {
+          // an fp16 box is 2 KB: when it is the only plane the two halves of the warp's 4 KB slot alternate
+          const bool solo = !p.C.f && !p.C.hi;
+          const uint32_t hb = solo ? uint32_t(c & 1) * 2048u : 0u;
+          if (lane == 0) {
+            if (solo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          __syncwarp();
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q)
+            sts128(sbox + hb + lane * 64 + ((q ^ sw64) << 4), pack_half2(x[8 * q], x[8 * q + 1]), pack_half2(x[8 * q + 2], x[8 * q + 3]),
+                   pack_half2(x[8 * q + 4], x[8 * q + 5]), pack_half2(x[8 * q + 6], x[8 * q + 7]));
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          __syncwarp();
+          if (lane == 0 && !(p.dbg & 4)) {
+            tma_store_2d(&mCh, box + hb, col0, crow);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
       }
     }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -377,8 +414,23 @@ inline int make_map(CUtensorMap* m, const void* base, CUtensorMapDataType dt, lo
   return QAT_OK;
 }
 
-inline bool tma_store_ok(const Act& C) {
-  return C.h && !C.f && !C.hi && !C.lo && C.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(C.h) & 15) == 0;
+// a [rows, cols] output plane with leading dimension ld; box = 32 rows x 32 columns (128 B rows: SWIZZLE_128B for 4-byte
+// elements, 64 B rows: SWIZZLE_64B for 2-byte elements)
+inline int make_store_map(CUtensorMap* m, const void* base, CUtensorMapDataType dt, long long rows, int cols, long long ld) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) QAT_FAIL(QAT_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  const int eb = dt == CU_TENSOR_MAP_DATA_TYPE_FLOAT32 ? 4 : 2;
+  QAT_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (ld * eb) % 16 == 0,
+              "gemm_tc: output planes must be 16-byte aligned with a 16-byte multiple row pitch (ld=%lld)", ld);
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * eb};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  eb == 4 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) QAT_FAIL(QAT_ECUDA, "cuTensorMapEncodeTiled (store map) failed with code %d (rows=%lld cols=%d ld=%lld)", (int)r, rows, cols, ld);
+  return QAT_OK;
 }
 
 template <int KIND, int BN, int STAGES>
@@ -387,7 +439,7 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   typedef Cfg<KIND, BN, STAGES> G;
   const CUtensorMapDataType dt = KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : (KIND == KIND_BF16X3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
-  CUtensorMap mA0, mA1, mW0, mW1, mC;
+  CUtensorMap mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh;
   QAT_TRY(make_map(&mA0, A0, dt, M, K, lda, G::BM));
   QAT_TRY(make_map(&mW0, W0, dt, N, K, K, BN));
   if (G::PLANES == 2) {
@@ -397,13 +449,17 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
     mA1 = mA0;
     mW1 = mW0;
   }
+  QAT_REQUIRE(C.f || C.hi || C.h, "gemm_tc: no output plane");
+  QAT_REQUIRE(!C.lo || C.hi, "gemm_tc: a lo plane needs its hi plane");
+  mCf = mChi = mClo = mCh = mA0;
+  if (C.f) QAT_TRY(make_store_map(&mCf, C.f, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, M, N, C.ld));
+  if (C.hi) QAT_TRY(make_store_map(&mChi, C.hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
+  if (C.lo) QAT_TRY(make_store_map(&mClo, C.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
+  if (C.h) QAT_TRY(make_store_map(&mCh, C.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
   GemmP p;
   p.M = (int)M; p.N = N; p.K = K; p.epi = epi; p.C = C;
-  p.tma_store = (tma_store_ok(C) && N % 8 == 0 && (epi.res == nullptr) && (epi.res_h == nullptr || epi.ldr % 8 == 0)) ? 1 : 0;
-  const char* no_tma = getenv("QAT_GEMM_NO_TMA_STORE");     // A/B switch for profiling
-  if (no_tma && no_tma[0] == '1') p.tma_store = 0;
-  if (p.tma_store) QAT_TRY(make_map(&mC, C.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld, 32));
-  else mC = mA0;
+  const char* dbg = getenv("QAT_GEMM_DBG");
+  p.dbg = dbg ? atoi(dbg) : 0;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES>;
   QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
   const long long ntiles = (long long)((N + BN - 1) / BN) * ((M + G::BM - 1) / G::BM);
@@ -411,7 +467,7 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, 192, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mC, p);
+  kern<<<grid, 320, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, p);
   return check_launch("gemm_tc_kernel");
 }
 

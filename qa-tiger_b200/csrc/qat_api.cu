@@ -246,7 +246,7 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
   const long long BT = (long long)B * T;
   const int Cin = a->has_proj ? a->Cin : D;
   // frames per pass: keep the per-pass intermediates (~ P*D*4*(1+3+1+1+2) bytes per frame) near L2 size
-  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 4096;
+  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 8192;
   if (a->chunk_frames <= 0 && getenv("QAT_PATCH_CHUNK")) chunk = atoll(getenv("QAT_PATCH_CHUNK")) > 0 ? atoll(getenv("QAT_PATCH_CHUNK")) : chunk;
   if (chunk > BT) chunk = BT;
   const float scale = 0.125f;
