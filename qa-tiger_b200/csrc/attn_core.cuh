@@ -615,6 +615,196 @@ inline int attn_mma_launch(Ctx& c, const AttnP& p) {
   return check_launch("attn_mma_kernel");
 }
 
+// ---- fp16 tensor-core fragments (mma.sync m16n8k16, fp32 accumulate) -----------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t saddr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// D += (ah + al) (bh + bl) without the lo*lo term
+__device__ __forceinline__ void mma3_f16(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
+                                         uint32_t bl0, uint32_t bl1) {
+  mma_f16(d, al, bh0, bh1);
+  mma_f16(d, ah, bl0, bl1);
+  mma_f16(d, ah, bh0, bh1);
+}
+
+// ---- tensor-core core for the 60..128-token sequences of AVQCrossAttn, second generation --------------------
+// mma.sync m16n8k16 on fp16 (hi, lo) pairs (x = hi + lo keeps 22 bits: fp32-faithful, the serial chain into the
+// router needs it): K and V are split ONCE while they are staged into shared memory (fp16 planes,
+// 144-byte rows: conflict-free ldmatrix), Q is split in registers straight from global memory, P never leaves
+// registers (the S accumulator fragments of two key tiles are exactly the A fragment of one P*V k-step).
+// One CTA (4 warps) per (sequence, head); warp w owns query rows 16w..16w+15 of each 64-row pass.
+template <int NT16>   // key tiles of 16: Lk <= 16*NT16
+__global__ void __launch_bounds__(128) attn_mma16_kernel(AttnP p) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  constexpr int LKP = 16 * NT16, RSB = 144;              // padded key count, row stride in bytes (72 halves)
+  const int Lq = p.Lq, Lk = p.Lk;
+  unsigned char* Kh = smraw;
+  unsigned char* Kl = Kh + LKP * RSB;
+  unsigned char* Vh = Kl + LKP * RSB;
+  unsigned char* Vl = Vh + LKP * RSB;
+  const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
+  const int kn = (n + p.k_shift) % p.k_mod;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const float* kb = p.k + kn * p.k_sn + h * HD;
+  const float* vb = p.v + kn * p.k_sn + h * HD;
+  for (int f = tid; f < LKP * 16; f += 128) {
+    const int j = f >> 4, c4 = f & 15;
+    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+    if (j < Lk) {
+      kv = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
+      vv = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+    }
+    uint2 hi, lo;
+    split_half2(kv.x, kv.y, hi.x, lo.x);
+    split_half2(kv.z, kv.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(Kh + j * RSB + c4 * 8) = hi;
+    *reinterpret_cast<uint2*>(Kl + j * RSB + c4 * 8) = lo;
+    split_half2(vv.x, vv.y, hi.x, lo.x);
+    split_half2(vv.z, vv.w, hi.y, lo.y);
+    *reinterpret_cast<uint2*>(Vh + j * RSB + c4 * 8) = hi;
+    *reinterpret_cast<uint2*>(Vl + j * RSB + c4 * 8) = lo;
+  }
+  __syncthreads();
+  const uint32_t sKh = tc::smem_u32(Kh), sKl = tc::smem_u32(Kl), sVh = tc::smem_u32(Vh), sVl = tc::smem_u32(Vl);
+  const int m8 = lane >> 3, r8 = lane & 7;
+  const uint32_t koff = uint32_t((r8 + (m8 >> 1) * 8) * RSB + (m8 & 1) * 16);   // + np*16 rows, + ks*32 bytes
+  const uint32_t voff = uint32_t((r8 + (m8 & 1) * 8) * RSB + (m8 >> 1) * 16);   // + kk*16 rows, + dp*32 bytes
+  const float invH = 1.f / p.H;
+  for (int r0 = warp * 16; r0 < Lq; r0 += 64) {
+    // ---- Q fragments (pre-scaled), rows r0+g / r0+g+8 ----
+    const int i0 = r0 + g, i1 = r0 + g + 8;
+    const float* q0 = p.q + n * p.q_sn + (long long)min(i0, Lq - 1) * p.q_si + h * HD + 2 * t;
+    const float* q1 = p.q + n * p.q_sn + (long long)min(i1, Lq - 1) * p.q_si + h * HD + 2 * t;
+    uint32_t qh[4][4], ql[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const float2 a0 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16));
+      const float2 a1 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16));
+      const float2 a2 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16 + 8));
+      const float2 a3 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16 + 8));
+      split_half2(a0.x * p.scale, a0.y * p.scale, qh[ks][0], ql[ks][0]);
+      split_half2(a1.x * p.scale, a1.y * p.scale, qh[ks][1], ql[ks][1]);
+      split_half2(a2.x * p.scale, a2.y * p.scale, qh[ks][2], ql[ks][2]);
+      split_half2(a3.x * p.scale, a3.y * p.scale, qh[ks][3], ql[ks][3]);
+    }
+    // ---- S = Q K^T ----
+    float s[2 * NT16][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT16; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+      for (int np = 0; np < NT16; ++np) {
+        uint32_t bh[4], bl[4];
+        ldsm_x4(bh, sKh + koff + np * 16 * RSB + ks * 32);
+        ldsm_x4(bl, sKl + koff + np * 16 * RSB + ks * 32);
+        mma3_f16(s[2 * np], qh[ks], ql[ks], bh[0], bh[1], bl[0], bl[1]);
+        mma3_f16(s[2 * np + 1], qh[ks], ql[ks], bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+    // ---- softmax over the two rows this thread shares with its quad ----
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT16; ++nt) {
+      const int c = nt * 8 + 2 * t;
+      if (c >= Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
+      if (c + 1 >= Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+      mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT16; ++nt) {
+      s[nt][0] = expf(s[nt][0] - mx0);
+      s[nt][1] = expf(s[nt][1] - mx0);
+      s[nt][2] = expf(s[nt][2] - mx1);
+      s[nt][3] = expf(s[nt][3] - mx1);
+      s0 += s[nt][0] + s[nt][1];
+      s1 += s[nt][2] + s[nt][3];
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+#pragma unroll
+    for (int nt = 0; nt < 2 * NT16; ++nt) {
+      s[nt][0] /= s0; s[nt][1] /= s0; s[nt][2] /= s1; s[nt][3] /= s1;
+    }
+    if (p.attw) {
+      float* w0 = p.attw + ((long long)n * Lq + i0) * Lk;
+      float* w1 = p.attw + ((long long)n * Lq + i1) * Lk;
+#pragma unroll
+      for (int nt = 0; nt < 2 * NT16; ++nt) {
+        const int c = nt * 8 + 2 * t;
+        if (i0 < Lq && c < Lk) atomicAdd(w0 + c, s[nt][0] * invH);
+        if (i0 < Lq && c + 1 < Lk) atomicAdd(w0 + c + 1, s[nt][1] * invH);
+        if (i1 < Lq && c < Lk) atomicAdd(w1 + c, s[nt][2] * invH);
+        if (i1 < Lq && c + 1 < Lk) atomicAdd(w1 + c + 1, s[nt][3] * invH);
+      }
+    }
+    // ---- O = P V ----
+    float o[8][4];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < NT16; ++kk) {
+      uint32_t ph[4], pl[4];
+      split_half2(s[2 * kk][0], s[2 * kk][1], ph[0], pl[0]);
+      split_half2(s[2 * kk][2], s[2 * kk][3], ph[1], pl[1]);
+      split_half2(s[2 * kk + 1][0], s[2 * kk + 1][1], ph[2], pl[2]);
+      split_half2(s[2 * kk + 1][2], s[2 * kk + 1][3], ph[3], pl[3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t bh[4], bl[4];
+        ldsm_x4_t(bh, sVh + voff + kk * 16 * RSB + dp * 32);
+        ldsm_x4_t(bl, sVl + voff + kk * 16 * RSB + dp * 32);
+        mma3_f16(o[2 * dp], ph, pl, bh[0], bh[1], bl[0], bl[1]);
+        mma3_f16(o[2 * dp + 1], ph, pl, bh[2], bh[3], bl[2], bl[3]);
+      }
+    }
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      const int col = h * HD + dt * 8 + 2 * t;
+      if (i0 < Lq) act_store2(p.o, n * p.o_rn + i0 * p.o_ri, col, o[dt][0], o[dt][1]);
+      if (i1 < Lq) act_store2(p.o, n * p.o_rn + i1 * p.o_ri, col, o[dt][2], o[dt][3]);
+    }
+  }
+}
+
+template <int NT16>
+inline int attn_mma16_launch(Ctx& c, const AttnP& p) {
+  const size_t smem = (size_t)4 * 16 * NT16 * 144;
+  auto kern = attn_mma16_kernel<NT16>;
+  if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
+  return check_launch("attn_mma16_kernel");
+}
+
 inline int attention(Ctx& c, const AttnP& p) {
   QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
   QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
@@ -634,8 +824,14 @@ inline int attention(Ctx& c, const AttnP& p) {
     return check_launch("attn_rows_kernel");
   }
   if (p.Lk > 32 || p.Lq >= 32) {
-    const char* ffma = getenv("QAT_ATTN_FFMA");     // A/B switch: the register-tiled FFMA core instead of mma.sync
-    if (!(ffma && ffma[0] == '1')) {
+    const char* ffma = getenv("QAT_ATTN_FFMA");     // A/B switches: 1 = register-tiled FFMA core, 2 = 3xTF32 m16n8k8 core
+    if (!ffma || ffma[0] == '0') {
+      if (p.Lk <= 64) return attn_mma16_launch<4>(c, p);
+      if (p.Lk <= 80) return attn_mma16_launch<5>(c, p);
+      if (p.Lk <= 96) return attn_mma16_launch<6>(c, p);
+      return attn_mma16_launch<8>(c, p);
+    }
+    if (ffma[0] == '2') {
       if (p.Lk <= 64) return attn_mma_launch<8>(c, p);
       if (p.Lk <= 96) return attn_mma_launch<12>(c, p);
       return attn_mma_launch<16>(c, p);
