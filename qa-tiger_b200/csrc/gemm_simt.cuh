@@ -132,102 +132,115 @@ __global__ void __launch_bounds__(TY* TX) gemm_simt_kernel(const float* __restri
 }
 
 // Small-M variant (M < 1024: the per-question contractions, M = batch): 32x32 output tiles so N/32 * M/32 CTAs
-// cover the SMs, and the K loop is split over KG groups of 64 threads inside the CTA (named barriers per group,
-// fixed-order reduction through shared memory => deterministic) so each SM holds 8 warps of independent work.
+// cover the SMs; the K loop is split over KG groups of 64 threads inside the CTA, each group streaming its
+// k-tiles (g, g+KG, ...) through its own 3-stage cp.async ring (named barrier per group), so an SM keeps
+// KG * 2 tiles of global loads in flight instead of one.  Partial tiles meet in shared memory and are summed in
+// fixed group order (deterministic), then bias / ReLU / residual and coalesced 16-byte stores.
 constexpr int SMALL_KG = 4;
+constexpr int SMALL_NS = 3;
+constexpr int SMALL_BK = 32;
+constexpr int SMALL_LD = 36;   // floats per staged row (32 + 4 pad: rows r, r+1, .. land 4 banks apart)
+constexpr int SMALL_SMEM = SMALL_KG * SMALL_NS * 2 * 32 * SMALL_LD * 4;
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled, the source is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(n) : "memory");
+}
+
 __global__ void __launch_bounds__(64 * SMALL_KG) gemm_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                                                     Epi epi, Act C, int M, int N, int K) {
-  constexpr int BM = 32, BN = 32, BK = 16, NT = 64, PAD = 4;
-  __shared__ __align__(16) float As[SMALL_KG][2][BK][BM + PAD];
-  __shared__ __align__(16) float Ws[SMALL_KG][2][BK][BN + PAD];
+  constexpr int NT = 64, LD = SMALL_LD, BK = SMALL_BK, NS = SMALL_NS;
+  extern __shared__ __align__(16) float sm_small[];
   const int g = threadIdx.x / NT, tid = threadIdx.x % NT, tx = tid & 7, ty = tid >> 3;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float4 ra[2], rw[2];
-  auto gload = [&](int k0) {
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float* gbase = sm_small + g * (NS * 2 * 32 * LD);
+  auto As = [&](int s) { return gbase + s * (2 * 32 * LD); };
+  auto Ws = [&](int s) { return gbase + s * (2 * 32 * LD) + 32 * LD; };
+  const int nk = (K + BK - 1) / BK;
+  const int my = (nk - g + SMALL_KG - 1) / SMALL_KG;      // k-tiles g, g+KG, ... of this group
+  auto load = [&](int it) {
+    const int k0 = (g + it * SMALL_KG) * BK;
+    float* as = As(it % NS);
+    float* ws = Ws(it % NS);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int f = tid + i * NT, r = f >> 2, kq = f & 3;
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + i * NT, r = f >> 3, kq = f & 7;
       const bool kin = k0 + kq * 4 < K;
-      ra[i] = (m0 + r < M && kin) ? __ldg(reinterpret_cast<const float4*>(A + (long long)(m0 + r) * lda + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
-      rw[i] = (n0 + r < N && kin) ? __ldg(reinterpret_cast<const float4*>(W + (long long)(n0 + r) * ldw + k0 + kq * 4)) : make_float4(0, 0, 0, 0);
-    }
-  };
-  auto sstore = [&](int buf) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int f = tid + i * NT, r = f >> 2, kq = f & 3;
-      As[g][buf][kq * 4 + 0][r] = ra[i].x; As[g][buf][kq * 4 + 1][r] = ra[i].y; As[g][buf][kq * 4 + 2][r] = ra[i].z; As[g][buf][kq * 4 + 3][r] = ra[i].w;
-      Ws[g][buf][kq * 4 + 0][r] = rw[i].x; Ws[g][buf][kq * 4 + 1][r] = rw[i].y; Ws[g][buf][kq * 4 + 2][r] = rw[i].z; Ws[g][buf][kq * 4 + 3][r] = rw[i].w;
+      const bool av = kin && m0 + r < M, wv = kin && n0 + r < N;
+      cp_async16_zfill(as + r * LD + kq * 4, av ? A + (long long)(m0 + r) * lda + k0 + kq * 4 : A, av);
+      cp_async16_zfill(ws + r * LD + kq * 4, wv ? W + (long long)(n0 + r) * ldw + k0 + kq * 4 : W, wv);
     }
   };
   auto group_sync = [&]() { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(NT) : "memory"); };
+  // thread (ty, tx) owns rows ty + 8i and columns tx + 8j: its four A rows / W rows sit 4 banks apart per lane group,
+  // so the 128-bit reads below are conflict-free
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const int nk = (K + BK - 1) / BK;
-  const int my = (nk - g + SMALL_KG - 1) / SMALL_KG;      // k-tiles g, g+KG, ... of this group
-  if (my > 0) {
-    gload(g * BK);
-    sstore(0);
+#pragma unroll
+  for (int s = 0; s < NS - 1; ++s) {
+    if (s < my) load(s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int it = 0; it < my; ++it) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(NS - 2) : "memory");
     group_sync();
-    for (int it = 0; it < my; ++it) {
-      const int buf = it & 1;
-      if (it + 1 < my) gload((g + (it + 1) * SMALL_KG) * BK);
+    if (it + NS - 1 < my) load(it + NS - 1);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float* as = As(it % NS);
+    const float* ws = Ws(it % NS);
 #pragma unroll
-      for (int k = 0; k < BK; ++k) {
-        const float4 a = *reinterpret_cast<const float4*>(&As[g][buf][k][ty * 4]);
-        const float4 b = *reinterpret_cast<const float4*>(&Ws[g][buf][k][tx * 4]);
-        const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+    for (int k4 = 0; k4 < BK / 4; ++k4) {
+      float4 a[4], b[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4*>(as + (ty + 8 * i) * LD + k4 * 4);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-      }
-      if (it + 1 < my) {
-        sstore(buf ^ 1);
-        group_sync();
-      }
+      for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4*>(ws + (tx + 8 * j) * LD + k4 * 4);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          acc[i][j] = fmaf(a[i].x, b[j].x, acc[i][j]);
+          acc[i][j] = fmaf(a[i].y, b[j].y, acc[i][j]);
+          acc[i][j] = fmaf(a[i].z, b[j].z, acc[i][j]);
+          acc[i][j] = fmaf(a[i].w, b[j].w, acc[i][j]);
+        }
     }
   }
-  // fixed-order reduction over the K groups: groups 1.. park their tiles in their own (now idle) A buffers
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // fixed-order reduction over the K groups through shared memory (each group parks its tile in its own ring)
   __syncthreads();
-  if (g > 0) {
+  float* red = gbase;                                     // [32][33]
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      *reinterpret_cast<float4*>(&As[g][0][0][0] + (ty * 4 + i) * 32 + tx * 4) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  }
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) red[(ty + 8 * i) * 33 + tx + 8 * j] = acc[i][j];
   __syncthreads();
-  if (g > 0) return;
+  const int r = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
+  const long long gr = m0 + r;
+  const int gc = n0 + c4;
+  if (gr >= M || gc >= N) return;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int gg = 1; gg < SMALL_KG; ++gg)
+  for (int gg = 0; gg < SMALL_KG; ++gg) {
+    const float* rg = sm_small + gg * (NS * 2 * 32 * LD) + r * 33 + c4;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4 t = *reinterpret_cast<const float4*>(&As[gg][0][0][0] + (ty * 4 + i) * 32 + tx * 4);
-      acc[i][0] += t.x; acc[i][1] += t.y; acc[i][2] += t.z; acc[i][3] += t.w;
-    }
-  const bool vec_ok = ((C.ld & 3) == 0) && (epi.res == nullptr || (epi.ldr & 3) == 0);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const long long gr = m0 + ty * 4 + i;
-    const int gc = n0 + tx * 4;
-    if (gr >= M || gc >= N) continue;
-    float v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float x = acc[i][j];
-      if (gc + j < N) {
-        if (epi.bias) x += __ldg(epi.bias + gc + j);
-        if (epi.relu) x = fmaxf(x, 0.f);
-        if (epi.res) x += __ldg(epi.res + gr * epi.ldr + gc + j);
-      }
-      v[j] = x;
-    }
-    if (vec_ok && gc + 3 < N) act_store4(C, gr, gc, make_float4(v[0], v[1], v[2], v[3]));
-    else
-      for (int j = 0; j < 4 && gc + j < N; ++j) act_store1(C, gr, gc + j, v[j]);
+    for (int j = 0; j < 4; ++j) v[j] += rg[j];
   }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (gc + j < N) {
+      if (epi.bias) v[j] += __ldg(epi.bias + gc + j);
+      if (epi.relu) v[j] = fmaxf(v[j], 0.f);
+      if (epi.res) v[j] += __ldg(epi.res + gr * epi.ldr + gc + j);
+    }
+  }
+  const bool vec_ok = ((C.ld & 3) == 0) && gc + 3 < N;
+  if (vec_ok) act_store4(C, gr, gc, make_float4(v[0], v[1], v[2], v[3]));
+  else
+    for (int j = 0; j < 4 && gc + j < N; ++j) act_store1(C, gr, gc + j, v[j]);
 }
 
 inline int gemm_simt(Ctx& c, const float* A, int lda, long long M, const float* W, int N, int K, const Epi& epi, Act C) {
@@ -241,7 +254,9 @@ inline int gemm_simt(Ctx& c, const float* A, int lda, long long M, const float* 
     gemm_simt_kernel<16, 16><<<grid, 256, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
   } else {
     dim3 grid((N + 31) / 32, (unsigned)((M + 31) / 32));
-    gemm_small_kernel<<<grid, 64 * SMALL_KG, 0, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
+    QAT_CUDA(cudaFuncSetAttribute(gemm_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM));
+    QAT_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) % 16 == 0, "gemm_simt: operands must be 16-byte aligned");
+    gemm_small_kernel<<<grid, 64 * SMALL_KG, SMALL_SMEM, c.stream>>>(A, lda, W, K, epi, C, (int)M, N, K);
   }
   return check_launch("gemm_simt_kernel");
 }

@@ -58,6 +58,25 @@ static GemmKind pick_kind(const Ctx& c, long long M, int N, int K, bool patch_pa
 
 static bool reads_planes(GemmKind k) { return k == G_BF16X3; }
 
+// allocate an activation in the storage format the consuming engine reads (fp32 / bf16 hi,lo planes / fp16 plane)
+static int act_alloc_for(Ctx& c, Act& a, long long rows, int ld, GemmKind consumer) {
+  if (consumer == G_F16) return act_alloc_h(c, a, rows, ld);
+  return act_alloc(c, a, rows, ld, !reads_planes(consumer), reads_planes(consumer));
+}
+// module input -> the operand view an engine reads (conversion pass only when the engine does not read fp32)
+static int operand_of(Ctx& c, const float* x, long long rows, int cols, GemmKind k, Act& out) {
+  out = Act();
+  out.f = const_cast<float*>(x);
+  out.ld = cols;
+  if (k == G_BF16X3 || k == G_F16) {
+    Act pl;
+    QAT_TRY(act_alloc_for(c, pl, rows, cols, k));
+    QAT_TRY(add_rows(c, x, cols, nullptr, 0, pl, rows, cols));
+    out.hi = pl.hi; out.lo = pl.lo; out.h = pl.h;
+  }
+  return QAT_OK;
+}
+
 static int gemm(Ctx& c, GemmKind kind, const Act& A, long long M, const WView& W, Epi epi, Act C) {
   if (!epi.bias) epi.bias = W.bias;
   switch (kind) {
@@ -253,20 +272,28 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
   const WView Wp = wview(a->proj), Wsi = wview(a->slf_in), Wso = wview(a->slf_out), Wq = wview(a->crs_q), Wkv = wview(a->crs_kv);
   const WView Wco = wview(a->crs_out), Wm0 = wview(a->mlp0), Wm2 = wview(a->mlp2);
 
+  // The whole block is off the router path (its outputs reach the logits only through the vt experts), so in bf16 mode
+  // its remaining contractions run single-pass fp16 as well when the fp16 weights are supplied.
+  const bool sel16 = c.prec == QAT_PREC_BF16 && BT >= 512 && D % 64 == 0 &&
+                     !(getenv("QAT_PATCH_FP32_PLANES") && getenv("QAT_PATCH_FP32_PLANES")[0] == '1');
   // per-frame query rows [video; audio] -> q2 [BT, 2, D]  (modules.py:692: video first)
   Act Q2, O2, O3, Hm, Mo;
   QAT_TRY(act_alloc(c, Q2, BT, 2 * D, true, false));
   {
     GemmKind kq = pick_kind(c, BT, D, D, false, Wq);
+    if (sel16 && Wq.h16) kq = G_F16;
     Act Xv, Xa;
-    QAT_TRY(planes_of(c, a->video, BT, D, reads_planes(kq), Xv));
-    QAT_TRY(planes_of(c, a->audio, BT, D, reads_planes(kq), Xa));
+    QAT_TRY(operand_of(c, a->video, BT, D, kq, Xv));
+    QAT_TRY(operand_of(c, a->audio, BT, D, kq, Xa));
     QAT_TRY(gemm(c, kq, Xv, BT, Wq, Epi(), Q2.cols(0)));
     QAT_TRY(gemm(c, kq, Xa, BT, Wq, Epi(), Q2.cols(D)));
   }
-  const GemmKind k_co = pick_kind(c, 2 * BT, D, D, false, Wco), k_m0 = pick_kind(c, 2 * BT, D / 2, D, false, Wm0);
-  const GemmKind k_m2 = pick_kind(c, 2 * BT, D, D / 2, false, Wm2);
-  QAT_TRY(act_alloc(c, O2, 2 * BT, D, !reads_planes(k_co), reads_planes(k_co)));
+  GemmKind k_co = pick_kind(c, 2 * BT, D, D, false, Wco), k_m0 = pick_kind(c, 2 * BT, D / 2, D, false, Wm0);
+  GemmKind k_m2 = pick_kind(c, 2 * BT, D, D / 2, false, Wm2);
+  if (sel16 && Wco.h16) k_co = G_F16;
+  if (sel16 && Wm0.h16) k_m0 = G_F16;
+  if (sel16 && Wm2.h16) k_m2 = G_F16;
+  QAT_TRY(act_alloc_for(c, O2, 2 * BT, D, k_co));
 
   // bf16 mode, P <= 16: activations between the kernels of a pass are single fp16 planes (half the bytes of
   // fp32, tf32-grade operands at twice the tf32 MMA rate), attention through mma.sync; DESIGN.md section 3.
@@ -340,9 +367,9 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
     QAT_TRY(attention(c, q));
   }
   c.release(mark);
-  QAT_TRY(act_alloc(c, O3, 2 * BT, D, !reads_planes(k_m0), reads_planes(k_m0)));
+  QAT_TRY(act_alloc_for(c, O3, 2 * BT, D, k_m0));
   QAT_TRY(gemm(c, k_co, O2, 2 * BT, Wco, Epi(), O3));
-  QAT_TRY(act_alloc(c, Hm, 2 * BT, D / 2, !reads_planes(k_m2), reads_planes(k_m2)));
+  QAT_TRY(act_alloc_for(c, Hm, 2 * BT, D / 2, k_m2));
   {
     Epi e;
     e.relu = 1;

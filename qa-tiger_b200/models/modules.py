@@ -355,11 +355,11 @@ class PatchSelecter(_QatModule):
         return dict(
             slf_in=cabi.Lin(s.in_proj_weight, s.in_proj_bias, prec, f16=True),
             slf_out=cabi.Lin(s.out_proj.weight, s.out_proj.bias, prec, f16=True),
-            crs_q=cabi.Lin(c.in_proj_weight[:D], c.in_proj_bias[:D], prec),
+            crs_q=cabi.Lin(c.in_proj_weight[:D], c.in_proj_bias[:D], prec, f16=True),
             crs_kv=cabi.Lin(c.in_proj_weight[D:], c.in_proj_bias[D:], prec, f16=True),
-            crs_out=cabi.Lin(c.out_proj.weight, c.out_proj.bias, prec),
-            mlp0=cabi.Lin(self.mlp[0].weight, self.mlp[0].bias, prec),
-            mlp2=cabi.Lin(self.mlp[2].weight, self.mlp[2].bias, prec),
+            crs_out=cabi.Lin(c.out_proj.weight, c.out_proj.bias, prec, f16=True),
+            mlp0=cabi.Lin(self.mlp[0].weight, self.mlp[0].bias, prec, f16=True),
+            mlp2=cabi.Lin(self.mlp[2].weight, self.mlp[2].bias, prec, f16=True),
             anorm=cabi.LN(self.anorm), vnorm=cabi.LN(self.vnorm))
 
     def forward(self, patch: Tensor, audio: Tensor, video: Tensor, proj: Optional[Projection] = None) -> List[Tensor]:

@@ -96,3 +96,18 @@ if __name__ == "__main__":
             return (ident, ident, ident)
         return (rn_fp16, rn_fp16, ident)
     report("everything fp16 RN single pass (router chain fp32)", run(allfp16, B), ref)
+
+    # ---- round-1b: which other contractions tolerate single-pass fp16 (RN) operands? ----
+    P16 = PATCH_TAGS + ("patch_selecter.crs.q", "patch_selecter.crs.o", "patch_selecter.mlp0", "patch_selecter.mlp2")
+    def pol_sel(extra=(), store=()):
+        def pol(tag):
+            if tag.startswith("patch_proj"):
+                return (tf32_trunc, tf32_trunc, rn_fp16)
+            if tag.startswith(P16) or tag.startswith(extra):
+                return (rn_fp16, rn_fp16, rn_fp16 if tag.startswith(PATCH_TAGS + store) else ident)
+            return chain(tag)
+        return pol
+    report("current GPU path (proj tf32, slf/kv fp16 planes)", run(mk_cur := (lambda tag: (tf32_trunc, tf32_trunc, rn_fp16) if tag.startswith("patch_proj") else ((rn_fp16, rn_fp16, rn_fp16) if is_patch(tag) else chain(tag))), B), ref)
+    report("+ whole PatchSelecter fp16 single pass (crs.q/o, mlp0/2)", run(pol_sel(), B), ref)
+    report("+ experts first layer (e1) fp16 single pass", run(pol_sel((("at_aggregator.e1", "vt_aggregator.e1"))), B), ref)
+    report("+ experts e1 only (selecter small GEMMs stay bf16x3)", run(lambda tag: (rn_fp16, rn_fp16, ident) if tag.endswith(".e1") else mk_cur(tag), B), ref)
