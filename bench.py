@@ -269,18 +269,23 @@ def run_ours(args):
                     bufs[i % 2][k].copy_(v, non_blocking=True)
                 ready[i % 2].record(copy_stream)
 
-        def e2e_run(nsteps):
+        def e2e_run(nsteps, copies=True, compute=True):
             cur = torch.cuda.current_stream()
             for ev in freed:
                 ev.record(cur)
-            issue_copy(0)
+            if copies:
+                issue_copy(0)
             for i in range(nsteps):
-                if i + 1 < nsteps:
+                if copies and i + 1 < nsteps:
                     issue_copy(i + 1)
-                cur.wait_event(ready[i % 2])
-                o = model(bufs[i % 2])["out"]
-                pred_host.copy_(o.argmax(1), non_blocking=True)
+                if copies:
+                    cur.wait_event(ready[i % 2])
+                if compute:
+                    o = model(bufs[i % 2])["out"]
+                    pred_host.copy_(o.argmax(1), non_blocking=True)
                 freed[i % 2].record(cur)
+            if copies:
+                cur.wait_stream(copy_stream)
 
         e2e_steps = max(4, min(args.steps, 12))
         e2e_run(2)
@@ -293,6 +298,18 @@ def run_ours(args):
         f1.record()
         torch.cuda.synchronize()
         ms_e2e = f0.elapsed_time(f1)
+        # breakdown of the e2e step (explains the number; not part of it): copies alone, compute alone
+        parts = {}
+        for nm, kw in (("h2d_only_ms", dict(compute=False)), ("compute_only_ms", dict(copies=False))):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            f0.record()
+            e2e_run(e2e_steps, **kw)
+            f1.record()
+            t_issue = time.perf_counter() - t0
+            torch.cuda.synchronize()
+            parts[nm] = f0.elapsed_time(f1) / e2e_steps
+            parts[nm.replace("_ms", "_cpu_issue_ms")] = t_issue * 1e3 / e2e_steps
         e2e_parity = float((model(bufs[0])["out"] - out).norm() / out.norm())   # same batch: bf16x3 tower vs fp32 tower
 
         # ---- per-kernel rooflines, timed live with CUDA events on the launching stream ---------------
@@ -375,7 +392,7 @@ def run_ours(args):
                        "cuda_graph": graph is not None, "parallelism": f"dp{world}, contiguous shards, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": qps_e2e, "unit": "questions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
-                    "ms_per_step": ms_e2e_max, "text_tower_vs_fp32_logit_relerr": e2e_parity,
+                    "ms_per_step": ms_e2e_max, "breakdown": parts, "text_tower_vs_fp32_logit_relerr": e2e_parity,
                     "includes": "per step: H2D of the batch from pinned host (copy stream, double-buffered), CLIP text tower "
                                 "(PyTorch; Linear layers via the bf16x3 tcgen05 GEMM), hot path, argmax, D2H of predictions"},
             "gpu_launches": launches_per_step * args.steps,

@@ -576,9 +576,12 @@ static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
     xb[i] = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * C * 4));
     sb[i] = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * 4));
   }
-  float* metric = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * 64 * 4));
+  float* metric[2];
+  for (int i = 0; i < 2; ++i) metric[i] = reinterpret_cast<float*>(c.alloc((size_t)N * a->t0 * 64 * 4));
+  int mp = 0;
+  bool have_metric = false;
   int* idx = reinterpret_cast<int*>(c.alloc((size_t)N * ((a->t0 + 1) / 2 + 2 * (a->t0 / 2)) * 4));
-  if (!c.dry && (!xb[1] || !sb[1] || !metric || !idx)) QAT_FAIL(QAT_EWORKSPACE, "tome_chain: workspace too small (need %zu)", c.peak);
+  if (!c.dry && (!xb[1] || !sb[1] || !metric[1] || !idx)) QAT_FAIL(QAT_EWORKSPACE, "tome_chain: workspace too small (need %zu)", c.peak);
   if (a->group && !c.dry) {
     long long tot = (long long)N * a->t0;
     iota_rows_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.stream>>>(a->group, N, a->t0);
@@ -601,9 +604,17 @@ static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
       dst = src + (size_t)N * r;
     }
     trace_off += (size_t)N * (n_unm + 2 * r);
-    QAT_TRY(tome_metric(c, xcur, metric, (long long)N * t, C));
-    QAT_TRY(tome_match(c, metric, N, t, 64, r, a->class_token, unm, src, dst));
-    QAT_TRY(tome_merge(c, xcur, scur, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, xb[pp], sb[pp], a->group, a->t0));
+    // the metric of step s+1 comes out of step s's merge pass (fused); only the first step reads x for it
+    const bool fused = tome_merge_wavg_supported(C);
+    if (!fused || !have_metric) QAT_TRY(tome_metric(c, xcur, metric[mp], (long long)N * t, C));
+    QAT_TRY(tome_match(c, metric[mp], N, t, 64, r, a->class_token, unm, src, dst));
+    if (fused) {
+      QAT_TRY(tome_merge_wavg(c, xcur, scur, N, t, C, r, unm, src, dst, xb[pp], sb[pp], metric[mp ^ 1], a->group, a->t0));
+      mp ^= 1;
+      have_metric = true;
+    } else {
+      QAT_TRY(tome_merge(c, xcur, scur, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, xb[pp], sb[pp], a->group, a->t0));
+    }
     xcur = xb[pp];
     scur = sb[pp];
     pp ^= 1;

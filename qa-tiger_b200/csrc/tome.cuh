@@ -245,6 +245,105 @@ __global__ void __launch_bounds__(256) tome_merge_kernel(const float* __restrict
   }
 }
 
+// ---- T2 for the 577->14 chain: size-weighted merge of C = 64*G channel rows (G <= 16) with the NEXT step's stand-in
+// metric fused into the output pass.  A half-warp owns one output row: lane l holds float4 chunks l + 16 g (g < G), i.e.
+// all G channel groups of 4 metric channels, so the metric ((x_0 + x_1) + ...) / G falls out of its registers in the
+// reference's summation order and the merged tokens are never re-read.  All loads of a row are issued back to back.
+// Arithmetic order is the one of tome_merge_kernel (bit-exact with torch CPU, see the header of this file).
+template <int G>
+__global__ void __launch_bounds__(256) tome_merge_wavg_kernel(const float* __restrict__ x, const float* __restrict__ size, int t, int r,
+                                                              const int* __restrict__ unm_idx, const int* __restrict__ src_idx,
+                                                              const int* __restrict__ dst_idx, float* __restrict__ x_out,
+                                                              float* __restrict__ size_out, float* __restrict__ metric_out,
+                                                              int* __restrict__ group, int T0) {
+  extern __shared__ __align__(16) int smi[];
+  constexpr int C = 64 * G;
+  const int ta = (t + 1) / 2, tb = t / 2, n_unm = ta - r, t_out = t - r;
+  int* s_src = smi;               // [r]
+  int* s_dst = s_src + r;         // [r]
+  int* s_newpos = s_dst + r;      // [t]   (only when group != null)
+  const int n = blockIdx.x, tid = threadIdx.x;
+  for (int k = tid; k < r; k += blockDim.x) {
+    s_src[k] = src_idx[(size_t)n * r + k];
+    s_dst[k] = dst_idx[(size_t)n * r + k];
+  }
+  __syncthreads();
+  const float* xf = x + (size_t)n * t * C;
+  const float* sf = size ? size + (size_t)n * t : nullptr;
+  const int l16 = tid & 15, hw = tid >> 4, nhw = blockDim.x >> 4;
+  const unsigned hmask = 0xFFFFu << (tid & 16);               // the lanes of this half-warp
+  auto load_row = [&](int tok, float4 (&v)[G]) {
+    const float4* p = reinterpret_cast<const float4*>(xf + (size_t)tok * C) + l16;
+#pragma unroll
+    for (int g = 0; g < G; ++g) v[g] = ldg_stream(p + 16 * g);
+  };
+  for (int row = blockIdx.y * nhw + hw; row < t_out; row += gridDim.y * nhw) {
+    float4 v[G];
+    float stot;
+    if (row < n_unm) {
+      const int tok = 2 * unm_idx[(size_t)n * n_unm + row];
+      load_row(tok, v);
+      stot = sf ? sf[tok] : 1.f;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        v[g].x = __fmul_rn(v[g].x, stot); v[g].y = __fmul_rn(v[g].y, stot); v[g].z = __fmul_rn(v[g].z, stot); v[g].w = __fmul_rn(v[g].w, stot);
+      }
+    } else {
+      const int j = row - n_unm;
+      const int tok = 2 * j + 1;
+      load_row(tok, v);
+      const float s0 = sf ? sf[tok] : 1.f;
+      stot = s0;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        v[g].x = __fmul_rn(v[g].x, s0); v[g].y = __fmul_rn(v[g].y, s0); v[g].z = __fmul_rn(v[g].z, s0); v[g].w = __fmul_rn(v[g].w, s0);
+      }
+      // sources of this dst row, in ascending edge order (the CPU scatter order): 16 edges per ballot
+      for (int k0 = 0; k0 < r; k0 += 16) {
+        const int k = k0 + l16;
+        const bool hit = k < r && s_dst[k] == j;
+        unsigned m = (__ballot_sync(hmask, hit) >> (tid & 16)) & 0xFFFFu;
+        while (m) {
+          const int kk = k0 + __ffs(m) - 1;
+          m &= m - 1;
+          const int st = 2 * s_src[kk];
+          const float ss = sf ? sf[st] : 1.f;
+          float4 u[G];
+          load_row(st, u);
+          stot = __fadd_rn(stot, ss);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            v[g].x = __fadd_rn(v[g].x, __fmul_rn(u[g].x, ss)); v[g].y = __fadd_rn(v[g].y, __fmul_rn(u[g].y, ss));
+            v[g].z = __fadd_rn(v[g].z, __fmul_rn(u[g].z, ss)); v[g].w = __fadd_rn(v[g].w, __fmul_rn(u[g].w, ss));
+          }
+        }
+      }
+    }
+    float4* xo = reinterpret_cast<float4*>(x_out + ((size_t)n * t_out + row) * C) + l16;
+    float4 ms = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      v[g].x = __fdiv_rn(v[g].x, stot); v[g].y = __fdiv_rn(v[g].y, stot); v[g].z = __fdiv_rn(v[g].z, stot); v[g].w = __fdiv_rn(v[g].w, stot);
+      xo[16 * g] = v[g];
+      ms.x = __fadd_rn(ms.x, v[g].x); ms.y = __fadd_rn(ms.y, v[g].y); ms.z = __fadd_rn(ms.z, v[g].z); ms.w = __fadd_rn(ms.w, v[g].w);
+    }
+    if (metric_out) {
+      const float d = (float)G;
+      ms.x = __fdiv_rn(ms.x, d); ms.y = __fdiv_rn(ms.y, d); ms.z = __fdiv_rn(ms.z, d); ms.w = __fdiv_rn(ms.w, d);
+      reinterpret_cast<float4*>(metric_out + ((size_t)n * t_out + row) * 64)[l16] = ms;
+    }
+    if (l16 == 0) size_out[(size_t)n * t_out + row] = stot;
+  }
+  if (group && blockIdx.y == 0) {
+    for (int j = tid; j < tb; j += blockDim.x) s_newpos[2 * j + 1] = n_unm + j;
+    for (int k = tid; k < n_unm; k += blockDim.x) s_newpos[2 * unm_idx[(size_t)n * n_unm + k]] = k;
+    for (int k = tid; k < r; k += blockDim.x) s_newpos[2 * s_src[k]] = n_unm + s_dst[k];
+    __syncthreads();
+    int* g = group + (size_t)n * T0;
+    for (int o = tid; o < T0; o += blockDim.x) g[o] = s_newpos[g[o]];
+  }
+}
+
 // ---- stand-in metric: mean over the C/64 channel groups --------------------
 __global__ void __launch_bounds__(256) tome_metric_kernel(const float* __restrict__ x, float* __restrict__ metric, long long tokens, int C) {
   const int G = C / 64;
@@ -302,6 +401,25 @@ inline int tome_merge(Ctx& c, const float* x, const float* size, int N, int t, i
   else
     tome_merge_kernel<1><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0);
   return check_launch("tome_merge_kernel");
+}
+
+// chain step: merge_wavg + the next step's metric (metric_out may be NULL).  C must be 64*G with G in {4, 8, 16}.
+inline bool tome_merge_wavg_supported(int C) { return C == 256 || C == 512 || C == 1024; }
+inline int tome_merge_wavg(Ctx& c, const float* x, const float* size, int N, int t, int C, int r, const int* unm, const int* src,
+                           const int* dst, float* x_out, float* size_out, float* metric_out, int* group, int T0) {
+  QAT_REQUIRE(tome_merge_wavg_supported(C), "tome_merge_wavg: C=%d unsupported", C);
+  QAT_REQUIRE(r > 0 && r <= t / 2 && size_out, "tome_merge_wavg: bad r=%d for t=%d or size_out missing", r, t);
+  QAT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(metric_out)) % 16 == 0,
+              "tome_merge_wavg: tensors must be 16-byte aligned");
+  if (c.dry || N == 0) return QAT_OK;
+  int rs = 1;
+  while ((long long)N * rs < 148 * 4 && rs < 64) rs *= 2;
+  const size_t smem = ((size_t)2 * r + t) * 4 + 16;
+  dim3 grid(N, rs);
+  if (C == 1024) tome_merge_wavg_kernel<16><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0);
+  else if (C == 512) tome_merge_wavg_kernel<8><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0);
+  else tome_merge_wavg_kernel<4><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0);
+  return check_launch("tome_merge_wavg_kernel");
 }
 
 inline int tome_metric(Ctx& c, const float* x, float* metric, long long tokens, int C) {
