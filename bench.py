@@ -253,7 +253,7 @@ def run_ours(args):
         # ---- e2e: public API from pinned host memory, text tower included ---------------------------
         # Every step: H2D of THAT step's batch (pinned -> device, on a copy stream, double-buffered so the copy of
         # step i+1 overlaps the compute of step i), CLIP text tower, hot path, argmax, D2H of the predictions.
-        model.quest_encoder.compute = "bf16x3"       # text-tower Linear layers through the tcgen05 bf16 hi/lo GEMM
+        model.quest_encoder.compute = "native"       # the CLIP text tower through qat_clip_text_fwd (bf16 hi+lo x3 GEMMs)
         host = {k: v.cpu().pin_memory() for k, v in (("quest", quest), ("audio", audio), ("video", video), ("patch", patch))}
         h2d = sum(v.numel() * v.element_size() for v in host.values())
         pred_host = torch.empty(B, dtype=torch.int64).pin_memory()

@@ -76,7 +76,7 @@ typedef struct {
   const float* x;   /* [rows, w.k] */
   QatLinearW w;
   float* y;         /* [rows, w.n] */
-  int32_t relu;     /* 0/1 */
+  int32_t relu;     /* 0 none, 1 ReLU, 2 QuickGELU x*sigmoid(1.702x) */
   void* workspace;
   size_t workspace_bytes;
 } QatLinearArgs;
@@ -281,9 +281,36 @@ int qat_tome_chain(const QatTomeChainArgs* a);
 int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token);
 size_t qat_tome_chain_trace_len(int N, int t0, int n_steps, const int32_t* r_list, int class_token);
 
+/* ---- N1: frozen CLIP text tower, encoders.py:30-37 + base/clip_base.py:186-254 (ResidualAttentionBlock
+ *      x + attn(ln_1 x), x + c_proj(QuickGELU(c_fc(ln_2 x))), causal mask), ln_final, EOT-row @ text_projection ---- */
+typedef struct {
+  QatLayerNormW ln_1, ln_2;
+  QatLinearW in_proj;       /* attn.in_proj_{weight,bias} [3W, W] */
+  QatLinearW out_proj;      /* attn.out_proj [W, W] */
+  QatLinearW c_fc;          /* mlp.c_fc [4W, W] */
+  QatLinearW c_proj;        /* mlp.c_proj [W, 4W] */
+} QatClipLayerW;
+typedef struct {
+  int32_t B, L, W, H, E;    /* L tokens per question (77), width W = H*64, embed dim E */
+  int32_t n_layers, vocab;
+  int32_t prec;             /* QAT_PREC_FP32: fp32 FFMA; QAT_PREC_BF16: bf16 hi+lo x3 (fp32-faithful: the tower feeds the router) */
+  void* stream;
+  const int32_t* tokens;    /* [B, L] CLIP token ids; the EOT row is the FIRST argmax of the ids (clip_base.py:396) */
+  const float* token_embedding;      /* [vocab, W] */
+  const float* positional_embedding; /* [L, W] */
+  const QatClipLayerW* layers;       /* HOST pointer, n_layers entries */
+  QatLayerNormW ln_final;
+  QatLinearW text_projection;        /* [E, W] = text_projection^T, no bias */
+  float* quest;             /* [B, E] */
+  float* words;             /* [B, L, W] */
+  void* workspace;
+  size_t workspace_bytes;
+} QatClipTextArgs;
+int qat_clip_text_fwd(const QatClipTextArgs* a);
+
 /* ---- bookkeeping ---------------------------------------------------------------------------- */
 enum { QAT_OP_LINEAR = 0, QAT_OP_AVQ = 1, QAT_OP_PATCH = 2, QAT_OP_MOE = 3, QAT_OP_GROUND = 4,
-       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7 };
+       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7, QAT_OP_CLIP_TEXT = 8 };
 /* Pass the same args struct the op will be called with (pointers may be NULL). */
 size_t qat_workspace_bytes(int op, const void* args);
 const char* qat_last_error(void);

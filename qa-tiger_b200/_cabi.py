@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libqat_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
-OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN = range(8)
+OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT = range(9)
 PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 
 c_f32p = C.c_void_p  # all device pointers travel as void*
@@ -112,6 +112,19 @@ class TomeChainArgs(C.Structure):
                 ("idx_trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class ClipLayerW(C.Structure):
+    _fields_ = [("ln_1", LayerNormW), ("ln_2", LayerNormW), ("in_proj", LinearW), ("out_proj", LinearW),
+                ("c_fc", LinearW), ("c_proj", LinearW)]
+
+
+class ClipTextArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("L", C.c_int32), ("W", C.c_int32), ("H", C.c_int32), ("E", C.c_int32),
+                ("n_layers", C.c_int32), ("vocab", C.c_int32), ("prec", C.c_int32), ("stream", C.c_void_p),
+                ("tokens", C.c_void_p), ("token_embedding", C.c_void_p), ("positional_embedding", C.c_void_p),
+                ("layers", C.POINTER(ClipLayerW)), ("ln_final", LayerNormW), ("text_projection", LinearW),
+                ("quest", C.c_void_p), ("words", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 EXPORTS = {
     "qat_gemm": (C.c_int, [C.POINTER(GemmArgs)]),
     "qat_linear_fwd": (C.c_int, [C.POINTER(LinearArgs)]),
@@ -120,6 +133,7 @@ EXPORTS = {
     "qat_gauss_reduce_fwd": (C.c_int, [C.POINTER(GaussArgs)]),
     "qat_temp_moe_fwd": (C.c_int, [C.POINTER(MoeArgs)]),
     "qat_qst_grounding_head_fwd": (C.c_int, [C.POINTER(GroundArgs)]),
+    "qat_clip_text_fwd": (C.c_int, [C.POINTER(ClipTextArgs)]),
     "qat_tome_match": (C.c_int, [C.POINTER(TomeMatchArgs)]),
     "qat_tome_clamp_r": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "qat_tome_merge": (C.c_int, [C.POINTER(TomeMergeArgs)]),

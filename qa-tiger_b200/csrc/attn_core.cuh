@@ -22,6 +22,7 @@ struct AttnP {
   float* attw;           // optional [nseq, Lq, Lk] head-averaged weights (zero-initialised by the caller)
   int nseq, H, Lq, Lk;
   float scale;
+  int causal = 0;        // 1: key j attends only to queries i >= j (CLIP text tower; attn_mma16_kernel only)
 };
 
 constexpr int HD = 64;
@@ -723,11 +724,14 @@ __global__ void __launch_bounds__(128) attn_mma16_kernel(AttnP p) {
     }
     // ---- softmax over the two rows this thread shares with its quad ----
     float mx0 = -INFINITY, mx1 = -INFINITY;
+    const int lim0 = p.causal ? min(Lk, i0 + 1) : Lk, lim1 = p.causal ? min(Lk, i1 + 1) : Lk;
 #pragma unroll
     for (int nt = 0; nt < 2 * NT16; ++nt) {
       const int c = nt * 8 + 2 * t;
-      if (c >= Lk) { s[nt][0] = -INFINITY; s[nt][2] = -INFINITY; }
-      if (c + 1 >= Lk) { s[nt][1] = -INFINITY; s[nt][3] = -INFINITY; }
+      if (c >= lim0) s[nt][0] = -INFINITY;
+      if (c >= lim1) s[nt][2] = -INFINITY;
+      if (c + 1 >= lim0) s[nt][1] = -INFINITY;
+      if (c + 1 >= lim1) s[nt][3] = -INFINITY;
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -809,6 +813,13 @@ inline int attention(Ctx& c, const AttnP& p) {
   QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
   QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
   if (c.dry || p.nseq == 0) return QAT_OK;
+  if (p.causal) {
+    QAT_REQUIRE(p.attw == nullptr, "attention: causal attention has no weights output");
+    if (p.Lk <= 64) return attn_mma16_launch<4>(c, p);
+    if (p.Lk <= 80) return attn_mma16_launch<5>(c, p);
+    if (p.Lk <= 96) return attn_mma16_launch<6>(c, p);
+    return attn_mma16_launch<8>(c, p);
+  }
   if (p.Lq <= 2 && p.attw == nullptr) {
     const long long probs = (long long)p.nseq * p.H;
     const unsigned grid = (unsigned)((probs + 7) / 8);

@@ -8,11 +8,17 @@ namespace qat {
 
 struct Epi {
   const float* bias = nullptr;  // [N]
-  int relu = 0;
+  int relu = 0;                 // 0 none, 1 ReLU, 2 QuickGELU x*sigmoid(1.702 x) (clip_base.py:162-164)
   const float* res = nullptr;   // [M, ldr] added after the activation
   int ldr = 0;
   const __half* res_h = nullptr;  // the same residual as an fp16 plane (tensor-core GEMMs only; res wins if both are set)
 };
+
+__device__ __forceinline__ float epi_act(float x, int mode) {
+  if (mode == 1) return fmaxf(x, 0.f);
+  if (mode == 2) return x / (1.f + expf(-1.702f * x));
+  return x;
+}
 
 // Tile = (8*TY) x (8*TX), BK = 16, TY*TX threads; each thread owns two 4-row and two 4-col strips
 // (rows ty*4+i and BM/2+ty*4+i) so that every shared-memory float4 read is conflict-free.
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(TY* TX) gemm_simt_kernel(const float* __restri
         float x = acc[i][h * 4 + j];
         if (gc + j < N) {
           if (epi.bias) x += __ldg(epi.bias + gc + j);
-          if (epi.relu) x = fmaxf(x, 0.f);
+          x = epi_act(x, epi.relu);
           if (epi.res) x += __ldg(epi.res + gr * epi.ldr + gc + j);
         }
         v[j] = x;
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(64 * SMALL_KG) gemm_small_kernel(const float* 
   for (int j = 0; j < 4; ++j) {
     if (gc + j < N) {
       if (epi.bias) v[j] += __ldg(epi.bias + gc + j);
-      if (epi.relu) v[j] = fmaxf(v[j], 0.f);
+      v[j] = epi_act(v[j], epi.relu);
       if (epi.res) v[j] += __ldg(epi.res + gr * epi.ldr + gc + j);
     }
   }

@@ -299,9 +299,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb[q].z;
           x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb[q].w;
         }
-        if (p.epi.relu) {
+        if (p.epi.relu == 1) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) x[e] = fmaxf(x[e], 0.f);
+        } else if (p.epi.relu == 2) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) x[e] = epi_act(x[e], 2);
         }
         if (p.epi.res || p.epi.res_h) {
 #pragma unroll

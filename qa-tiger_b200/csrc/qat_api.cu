@@ -549,6 +549,81 @@ static int run_ground(const QatGroundArgs* a, Ctx& c) {
 }
 
 // =================================================================================================
+// N1  CLIP text tower (frozen), encoders.py:30-37 / clip_base.py:186-254
+// =================================================================================================
+static int run_clip_text(const QatClipTextArgs* a, Ctx& c) {
+  const int B = a->B, L = a->L, W = a->W, H = a->H, E = a->E;
+  QAT_REQUIRE(B >= 1 && L >= 1 && L <= 128 && H >= 1 && W == H * 64 && E >= 1, "clip_text: need W == H*64 and L <= 128 (W=%d H=%d L=%d)", W, H, L);
+  QAT_REQUIRE(a->n_layers >= 0 && (a->n_layers == 0 || a->layers), "clip_text: layer weights missing");
+  QAT_REQUIRE(c.dry || (a->tokens && a->token_embedding && a->positional_embedding && a->quest && a->words), "clip_text: NULL tensor");
+  QAT_TRY(check_w(a->text_projection, E, W, "clip_text.text_projection", c.prec));
+  const long long BL = (long long)B * L;
+  Act X, Y, QKV, O, Hh, G;
+  QAT_TRY(act_alloc(c, X, BL, W, true, false));
+  if (!c.dry) {
+    const long long n4 = BL * (W / 4);
+    clip_embed_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, c.stream>>>(a->tokens, a->token_embedding, a->positional_embedding, X.f, BL, L,
+                                                                           W / 4, a->vocab);
+    QAT_TRY(check_launch("clip_embed_kernel"));
+  }
+  for (int l = 0; l < a->n_layers; ++l) {
+    const QatClipLayerW& w = a->layers[l];
+    QAT_TRY(check_w(w.in_proj, 3 * W, W, "clip_text.in_proj", c.prec));
+    QAT_TRY(check_w(w.out_proj, W, W, "clip_text.out_proj", c.prec));
+    QAT_TRY(check_w(w.c_fc, 4 * W, W, "clip_text.c_fc", c.prec));
+    QAT_TRY(check_w(w.c_proj, W, 4 * W, "clip_text.c_proj", c.prec));
+    const WView Wi = wview(w.in_proj), Wo = wview(w.out_proj), Wf = wview(w.c_fc), Wp = wview(w.c_proj);
+    const GemmKind k_i = pick_kind(c, BL, 3 * W, W, false, Wi), k_o = pick_kind(c, BL, W, W, false, Wo);
+    const GemmKind k_f = pick_kind(c, BL, 4 * W, W, false, Wf), k_p = pick_kind(c, BL, W, 4 * W, false, Wp);
+    const size_t mark = c.mark();
+    // x = x + out_proj(attn(ln_1 x))
+    QAT_TRY(act_alloc_for(c, Y, BL, W, k_i));
+    QAT_TRY(ln(c, X.f, W, nullptr, 0, nullptr, 0, 1.f, w.ln_1, Y, BL, W));
+    QAT_TRY(act_alloc(c, QKV, BL, 3 * W, true, false));
+    QAT_TRY(gemm(c, k_i, Y, BL, Wi, Epi(), QKV));
+    QAT_TRY(act_alloc_for(c, O, BL, W, k_o));
+    AttnP p;
+    p.nseq = B; p.H = H; p.Lq = L; p.Lk = L; p.scale = 0.125f; p.causal = 1;
+    p.q = QKV.f; p.k = QKV.f + W; p.v = QKV.f + 2 * W;
+    p.q_sn = (long long)L * 3 * W; p.q_si = 3 * W; p.k_sn = p.q_sn; p.k_si = 3 * W; p.k_shift = 0; p.k_mod = B;
+    p.o = O; p.o_rn = L; p.o_ri = 1; p.attw = nullptr;
+    QAT_TRY(attention(c, p));
+    {
+      Epi e;
+      e.res = X.f; e.ldr = W;
+      QAT_TRY(gemm(c, k_o, O, BL, Wo, e, X));           // in place: a tile's residual is read before the tile is stored
+    }
+    c.release(mark);
+    // x = x + c_proj(QuickGELU(c_fc(ln_2 x)))
+    QAT_TRY(act_alloc_for(c, Y, BL, W, k_f));
+    QAT_TRY(ln(c, X.f, W, nullptr, 0, nullptr, 0, 1.f, w.ln_2, Y, BL, W));
+    QAT_TRY(act_alloc_for(c, Hh, BL, 4 * W, k_p));
+    {
+      Epi e;
+      e.relu = 2;
+      QAT_TRY(gemm(c, k_f, Y, BL, Wf, e, Hh));
+      Epi e2;
+      e2.res = X.f; e2.ldr = W;
+      QAT_TRY(gemm(c, k_p, Hh, BL, Wp, e2, X));
+    }
+    c.release(mark);
+  }
+  // words = ln_final(x); quest = words[eot] @ text_projection
+  QAT_TRY(ln(c, X.f, W, nullptr, 0, nullptr, 0, 1.f, a->ln_final, act_of(a->words, W), BL, W));
+  QAT_TRY(act_alloc(c, G, B, W, true, false));
+  if (!c.dry) {
+    clip_eot_gather_kernel<<<B, 256, 0, c.stream>>>(a->tokens, a->words, G.f, L, W / 4);
+    QAT_TRY(check_launch("clip_eot_gather_kernel"));
+  }
+  {
+    WView wp = wview(a->text_projection);
+    wp.bias = nullptr;
+    QAT_TRY(gemm(c, G_SIMT, G, B, wp, Epi(), act_of(a->quest, E)));
+  }
+  return QAT_OK;
+}
+
+// =================================================================================================
 // T1-T3, T0
 // =================================================================================================
 static int run_tome_match(const QatTomeMatchArgs* a, Ctx& c) {
@@ -672,6 +747,8 @@ int qat_tome_match(const QatTomeMatchArgs* a) { return dispatch(a, a ? a->stream
 int qat_tome_merge(const QatTomeMergeArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_merge); }
 int qat_tome_chain(const QatTomeChainArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_chain); }
 
+int qat_clip_text_fwd(const QatClipTextArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_clip_text); }
+
 int qat_tome_clamp_r(int t, int r, int class_token) { return tome_clamp_r(t, r, class_token); }
 
 int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token) {
@@ -700,6 +777,7 @@ size_t qat_workspace_bytes(int op, const void* args) {
     case QAT_OP_PATCH: return dry_bytes(reinterpret_cast<const QatPatchArgs*>(args), reinterpret_cast<const QatPatchArgs*>(args)->prec, run_patch);
     case QAT_OP_MOE: return dry_bytes(reinterpret_cast<const QatMoeArgs*>(args), reinterpret_cast<const QatMoeArgs*>(args)->prec, run_moe);
     case QAT_OP_GROUND: return dry_bytes(reinterpret_cast<const QatGroundArgs*>(args), reinterpret_cast<const QatGroundArgs*>(args)->prec, run_ground);
+    case QAT_OP_CLIP_TEXT: return dry_bytes(reinterpret_cast<const QatClipTextArgs*>(args), reinterpret_cast<const QatClipTextArgs*>(args)->prec, run_clip_text);
     case QAT_OP_TOME_MATCH: return 256;
     case QAT_OP_TOME_MERGE: return 256;
     case QAT_OP_TOME_CHAIN: return dry_bytes(reinterpret_cast<const QatTomeChainArgs*>(args), QAT_PREC_FP32, run_tome_chain);

@@ -121,6 +121,40 @@ inline int relu_rows(Ctx& c, const float* x, float* y, long long n) {
   return check_launch("relu_kernel");
 }
 
+// x[b*L + l, :] = token_embedding[tokens[b,l], :] + positional_embedding[l, :]   (clip_base.py:390-391)
+__global__ void __launch_bounds__(256) clip_embed_kernel(const int* __restrict__ tokens, const float* __restrict__ tok_emb,
+                                                         const float* __restrict__ pos_emb, float* __restrict__ x, long long rows, int L,
+                                                         int W4, int vocab) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * W4) return;
+  const long long r = i / W4;
+  const int c4 = (int)(i % W4);
+  int id = tokens[r];
+  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const float4 a = __ldg(reinterpret_cast<const float4*>(tok_emb + (size_t)id * W4 * 4) + c4);
+  const float4 b = __ldg(reinterpret_cast<const float4*>(pos_emb + (size_t)(r % L) * W4 * 4) + c4);
+  reinterpret_cast<float4*>(x)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+
+// out[b, :] = x[b*L + argmax_l tokens[b, l], :]  (first maximum, as torch.argmax; clip_base.py:396)
+__global__ void __launch_bounds__(256) clip_eot_gather_kernel(const int* __restrict__ tokens, const float* __restrict__ x,
+                                                              float* __restrict__ out, int L, int W4) {
+  const int b = blockIdx.x;
+  __shared__ int s_eot;
+  if (threadIdx.x == 0) {
+    int best = tokens[(size_t)b * L], bi = 0;
+    for (int l = 1; l < L; ++l) {
+      const int v = tokens[(size_t)b * L + l];
+      if (v > best) { best = v; bi = l; }
+    }
+    s_eot = bi;
+  }
+  __syncthreads();
+  const float4* src = reinterpret_cast<const float4*>(x) + ((size_t)b * L + s_eot) * W4;
+  float4* dst = reinterpret_cast<float4*>(out) + (size_t)b * W4;
+  for (int c = threadIdx.x; c < W4; c += blockDim.x) dst[c] = src[c];
+}
+
 __global__ void __launch_bounds__(256) ones_kernel(float* __restrict__ y, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = 1.f;

@@ -1,6 +1,8 @@
 """Frozen CLIP text tower (mirror of /root/reference/src/models/encoders.py:7-37 and the text half of
-src/models/base/clip_base.py:186-254,300-460).  Out of kernel scope by BASELINE.json's north_star: it
-stays PyTorch.  Parameter names match the reference (`transformer.resblocks.N.{attn,ln_1,mlp.c_fc,
+src/models/base/clip_base.py:186-254,300-460).  BASELINE.json's north_star keeps it PyTorch (the default
+`compute = "fp32"`); SURVEY 8f-N1 ranks it first among the "next" rows because it is 70 % of the forward's FLOPs,
+so `compute = "native"` runs it through libqat_b200 (`qat_clip_text_fwd`: one C-ABI call, bf16 hi+lo x3 tcgen05
+GEMMs, fp16 hi/lo mma.sync causal attention -- fp32-faithful, it feeds the router).  Parameter names match the reference (`transformer.resblocks.N.{attn,ln_1,mlp.c_fc,
 mlp.c_proj,ln_2}`, `token_embedding`, `positional_embedding`, `ln_final`, `text_projection`,
 `logit_scale`) so a reference checkpoint / CLIP state_dict loads unchanged.
 
@@ -112,8 +114,11 @@ class CLIP_TEncoder(nn.Module):
         # 'fp32'   torch fp32 matmuls (the reference's arithmetic)
         # 'bf16x3' the four Linear layers of every block through libqat_b200's tcgen05 bf16 hi/lo GEMM (fp32-faithful,
         #          ~6x faster than fp32 cuBLAS on B200) -- SURVEY 8f-N1; keeps the 1e-3 logit gate
+        # 'native' the whole tower in ONE C-ABI call (qat_clip_text_fwd; `native_precision` = 'bf16' -> bf16x3 tensor-core
+        #          GEMMs, 'fp32' -> fp32 FFMA), no per-op CPU launch cost
         # 'tf32' / 'bf16' torch reduced precision: measured to BREAK the gate (1.1e-2 at B=256, a router rank flips)
         self.compute = "fp32"
+        self.native_precision = "bf16"
         self.dedup = False   # run the tower on unique token rows only (MUSIC-AVQA test: 33 unique questions)
         self._try_load_local(model_name)
 
@@ -134,7 +139,54 @@ class CLIP_TEncoder(nn.Module):
         for p in self.parameters():
             p.requires_grad = False
 
+    # ---- compute == "native": qat_clip_text_fwd -------------------------------------------------------------
+    def _native_weights(self, prec: int):
+        key = (prec, cabi.params_version(self))
+        cached = self.__dict__.get("_native")
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        blocks = list(self.transformer.resblocks)
+        arr = (cabi.ClipLayerW * len(blocks))()
+        hold = []
+        for i, b in enumerate(blocks):
+            ws = dict(ln_1=cabi.LN(b.ln_1), ln_2=cabi.LN(b.ln_2),
+                      in_proj=cabi.Lin(b.attn.in_proj_weight, b.attn.in_proj_bias, prec),
+                      out_proj=cabi.Lin(b.attn.out_proj.weight, b.attn.out_proj.bias, prec),
+                      c_fc=cabi.Lin(b.mlp.c_fc.weight, b.mlp.c_fc.bias, prec),
+                      c_proj=cabi.Lin(b.mlp.c_proj.weight, b.mlp.c_proj.bias, prec))
+            hold.append(ws)
+            for k, v in ws.items():
+                setattr(arr[i], k, v.c)
+        w = dict(layers=arr, hold=hold, ln_final=cabi.LN(self.ln_final),
+                 text_projection=cabi.Lin(self.text_projection.t(), None, cabi.PREC_FP32),
+                 tok=self.token_embedding.weight.detach().contiguous().float(),
+                 pos=self.positional_embedding.detach().contiguous().float())
+        self.__dict__["_native"] = (key, w)
+        return w
+
+    def _tower_native(self, text: torch.Tensor):
+        if not text.is_cuda:
+            raise RuntimeError("CLIP_TEncoder(compute='native') needs CUDA tensors (qa-tiger_b200 has no CPU path)")
+        prec = cabi.PREC_NAMES[self.native_precision]
+        w = self._native_weights(prec)
+        B, L = text.shape
+        W = self.transformer.width
+        heads = self.transformer.resblocks[0].n_head
+        E = self.text_projection.shape[1]
+        tok = text.to(torch.int32).contiguous()
+        quest = torch.empty(B, E, device=text.device, dtype=torch.float32)
+        words = torch.empty(B, L, W, device=text.device, dtype=torch.float32)
+        a = cabi.ClipTextArgs()
+        a.B, a.L, a.W, a.H, a.E, a.n_layers, a.vocab, a.prec = B, L, W, heads, E, len(w["hold"]), self.vocab_size, prec
+        a.tokens, a.token_embedding, a.positional_embedding = tok.data_ptr(), w["tok"].data_ptr(), w["pos"].data_ptr()
+        a.layers, a.ln_final, a.text_projection = w["layers"], w["ln_final"].c, w["text_projection"].c
+        a.quest, a.words = quest.data_ptr(), words.data_ptr()
+        cabi.run(cabi.OP_CLIP_TEXT, "qat_clip_text_fwd", a, text.device)
+        return quest, words
+
     def _tower(self, text: torch.Tensor):
+        if self.compute == "native":
+            return self._tower_native(text)
         use_tc = self.compute == "bf16x3" and text.is_cuda
         if use_tc and self.__dict__.get("_tc") is None:
             self.__dict__["_tc"] = _TCLinear()

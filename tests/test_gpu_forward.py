@@ -37,6 +37,22 @@ def test_forward_matches_reference_golden(name, prec):
     assert out.argmax(1).cpu().tolist() == g["argmax"].tolist()
 
 
+@pytest.mark.parametrize("name", ["fwd_b8", "fwd_b256"])
+def test_forward_with_native_text_tower(name):
+    """Full forward (token ids in) with the CLIP tower through qat_clip_text_fwd: same gates as above."""
+    g = golden(name)
+    B, T, E, K, wseed, bseed = FWD_CASES[name]
+    sd = synth.make_state_dict(wseed, num_experts=E)
+    model = build_model(sd, E, K, "bf16")
+    model.quest_encoder.compute = "native"
+    batch = synth.make_batch(bseed, B, T)
+    data = {k: v.to(dev()) for k, v in batch.items()}
+    with torch.no_grad():
+        out = model(data)["out"]
+    assert relerr(out, g["out"]) < TOL["bf16"]
+    assert out.argmax(1).cpu().tolist() == g["argmax"].tolist()
+
+
 def test_batch_composition_is_part_of_the_function():
     """logits depend on the local batch; DP sharding must therefore be defined on local batches."""
     sd = synth.make_state_dict(713, num_experts=7)
@@ -63,6 +79,14 @@ def test_text_tower_matches_oracle():
     with torch.no_grad():
         q3, w3 = model.quest_encoder(batch["quest"].to(dev()))
     assert relerr(q3, rq) < 1e-4 and relerr(w3, rw) < 1e-4
+    # the whole tower in one C-ABI call (qat_clip_text_fwd): fp32 FFMA and bf16 hi+lo x3 tensor-core modes
+    for nprec, tol in (("fp32", 2e-5), ("bf16", 1e-4)):
+        model.quest_encoder.compute = "native"
+        model.quest_encoder.native_precision = nprec
+        with torch.no_grad():
+            qn, wn = model.quest_encoder(batch["quest"].to(dev()))
+        assert qn.shape == q.shape and wn.shape == w.shape
+        assert relerr(qn, rq) < tol and relerr(wn, rw) < tol, (nprec, relerr(qn, rq), relerr(wn, rw))
     model.quest_encoder.compute = "fp32"
     model.quest_encoder.dedup = True
     rep = batch["quest"][[0, 1, 0, 2, 1, 0]].to(dev())
