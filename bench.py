@@ -350,29 +350,70 @@ def run_ours(args):
                 rooflines[nm] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
                                  "traffic": None, "ms": t_ms, "bytes": byts}
                 del xs
-            # (2) the two tensor-core GEMM kinds at the largest shapes of the step (nominal 2*M*N*K FLOPs):
-            #     tf32 : PatchSelecter self-attention in-proj [B*T*P,512] x [1536,512]^T  (peak = sustained bf16 / 2)
-            #     bf16x3: AVQ packed in-proj [B*T,512] x [3584,512]^T, 3 MMAs per product (peak = sustained bf16 / 3)
+            # (2) the three tensor-core GEMM kinds at the largest shapes of the step (nominal 2*M*N*K FLOPs):
+            #     bf16x3: AVQ packed in-proj [B*T,512] x [3584,512]^T, 3 MMAs per product  (peak = sustained bf16 / 3)
+            #     f16   : PatchSelecter self-attention in-proj [B*T*P,512] x [1536,512]^T, fp16 planes in and out
+            #     tf32  : patch_proj [B*T*P,1024] x [512,1024]^T straight from the fp32 input  (peak = sustained bf16 / 2)
             ps = model.patch_selecter._prepared(_cabi.PREC_BF16)
             cr = model.crs_attn._prepared(_cabi.PREC_BF16)
-            chunk_rows = min(B * T, 4096) * P          # rows of one PatchSelecter pass (chunk_frames default 4096)
-            for nm, kind, lin, M_, div in (("gemm_tf32_patch_slf_in", _cabi.GEMM_TF32, ps["slf_in"], chunk_rows, 2.0),
-                                           ("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], B * T, 3.0)):
+            pp = model.patch_proj._prepared(_cabi.PREC_BF16)
+            chunk_rows = min(B * T, 8192) * P          # rows of one PatchSelecter pass (chunk_frames default 8192)
+            for nm, kind, lin, M_, div, f16out in (("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], B * T, 3.0, False),
+                                                   ("gemm_f16_patch_slf_in", _cabi.GEMM_F16, ps["slf_in"], chunk_rows, 1.0, True),
+                                                   ("gemm_tf32_patch_proj", _cabi.GEMM_TF32, pp, chunk_rows, 2.0, True)):
                 N_, K_ = lin.w.shape
                 xin = torch.randn(M_, K_, device=dev)
+                if kind == _cabi.GEMM_F16:
+                    xin = xin.half()
                 planes = _cabi.split_planes(xin) if kind == _cabi.GEMM_BF16X3 else None
-                t_ms = time_ms(lambda: _cabi.gemm(kind, xin, lin, a_planes=planes), n=6)
+                t_ms = time_ms(lambda: _cabi.gemm(kind, xin, lin, a_planes=planes, out_f16=f16out), n=6)
                 fl = 2.0 * M_ * N_ * K_
                 ach = fl / (t_ms * 1e-3) / 1e12
                 rooflines[nm] = {"bound": "tensor", "achieved": ach, "peak": tf_sust / div, "unit": "TFLOP/s",
                                  "frac": ach / (tf_sust / div), "traffic": None, "ms": t_ms, "shape": [M_, N_, K_],
                                  "note": f"nominal 2MNK FLOPs; peak = sustained bf16 / {div:g}"}
                 del xin, planes
+            # (3) ToMe 577->14 chain (config 3 shape, 480 frames = 1.1 GB of tokens > L2): frames/s and the stepwise
+            #     merge traffic of SURVEY 8d (56.49 MB per frame) over the WHOLE chain time (match kernels included)
+            try:
+                from qa_tiger_b200.tome import merge as tm
+                nfr = 480
+                xt = torch.randn(nfr, 577, 1024, device=dev)
+                for _ in range(2):
+                    tm.chain(xt)
+                torch.cuda.synchronize()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for _ in range(3):
+                    tm.chain(xt)
+                b_.record()
+                torch.cuda.synchronize()
+                t_ms = a_.elapsed_time(b_) / 3
+                byts = 56.49e6 * nfr
+                ach = byts / (t_ms * 1e-3) / 1e9
+                rooflines["tome_chain_577_to_14"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                                     "traffic": None, "ms": t_ms, "bytes": byts, "frames": nfr, "frames_per_s": nfr / (t_ms * 1e-3),
+                                                     "note": "stepwise merge traffic (SURVEY 8d) over the whole chain time, match + merge + metric"}
+                del xt
+            except Exception as e_:   # noqa: BLE001 -- an auxiliary line must not sink the bench
+                sys.stderr.write(f"[bench] ToMe roofline leg skipped: {e_}\n")
+        # ---- the same step with the CLIP text tower inside (token ids in, everything resident) ------------
+        with torch.no_grad():
+            for _ in range(2):
+                model({"quest": quest, "audio": audio, "video": video, "patch": patch})
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            for _ in range(5):
+                model({"quest": quest, "audio": audio, "video": video, "patch": patch})
+            b_.record()
+            torch.cuda.synchronize()
+            ms_full = a_.elapsed_time(b_) / 5
 
-    tmax = torch.tensor([ms, ms_e2e / e2e_steps * args.steps], device=dev)
+    tmax = torch.tensor([ms, ms_e2e / e2e_steps * args.steps, ms_full], device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms_max, ms_e2e_max = float(tmax[0]), float(tmax[1]) / args.steps
+    ms_max, ms_e2e_max, ms_full_max = float(tmax[0]), float(tmax[1]) / args.steps, float(tmax[2])
     if rank == 0:
         qps = world * B * args.steps / (ms_max * 1e-3)
         qps_e2e = world * B / (ms_e2e_max * 1e-3)
@@ -384,17 +425,23 @@ def run_ours(args):
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": "QA-TIGER eval forward bs=256 T=60 (configs[1]): hot path net.py:120-142, E=K=7, P=14",
                        "per_gpu_batch": B, "precision_mode": args.precision,
-                       "arithmetic": "tcgen05 kind::f16 bf16 hi+lo x3 (serial chain) + kind::tf32 (patch path), fp32 accumulate; "
-                                     "router/Gaussian/rank path fp32" if args.precision == "bf16" else "fp32 FFMA",
-                       "text_tower": "excluded from `value` (frozen CLIP, PyTorch, out of kernel scope: SURVEY 8a/8d; features "
-                                     "precomputed and resident); included in `e2e`",
+                       "arithmetic": "tcgen05 kind::f16 on bf16 hi+lo pairs x3 (serial chain into the router), kind::tf32 (patch_proj) "
+                                     "and single fp16 planes (PatchSelecter), fp32 accumulate; router/Gaussian/rank path fp32"
+                                     if args.precision == "bf16" else "fp32 FFMA",
+                       "text_tower": "excluded from `value` (frozen CLIP: outside the hot path of SURVEY 8a/8d; its outputs are "
+                                     "precomputed and resident); included in `e2e` and in `value_with_text_tower`",
                        "l2": "inputs per step (881 MB patch + 54 MB other) exceed the 126 MB L2; no explicit flush",
                        "cuda_graph": graph is not None, "parallelism": f"dp{world}, contiguous shards, no data-path collective"},
             "clocks": clocks,
             "e2e": {"value": qps_e2e, "unit": "questions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
                     "ms_per_step": ms_e2e_max, "breakdown": parts, "text_tower_vs_fp32_logit_relerr": e2e_parity,
                     "includes": "per step: H2D of the batch from pinned host (copy stream, double-buffered), CLIP text tower "
-                                "(PyTorch; Linear layers via the bf16x3 tcgen05 GEMM), hot path, argmax, D2H of predictions"},
+                                "(qat_clip_text_fwd, SURVEY 8f-N1), hot path, argmax, D2H of predictions; bound by the PCIe copy "
+                                "of 936 MB per 256 questions (breakdown.h2d_only_ms)"},
+            "value_with_text_tower": {"value": world * B / (ms_full_max * 1e-3), "unit": "questions/s", "ms_per_step": ms_full_max,
+                                      "note": "QA_TIGER.forward on resident inputs, token ids in, all 256 questions through the "
+                                              "12-layer CLIP text tower (no dedup: synthetic questions are all distinct; "
+                                              "MUSIC-AVQA test has 33 unique question strings)"},
             "gpu_launches": launches_per_step * args.steps,
             "launches_per_step": launches_per_step,
             "hot_path_tensor_frac_nominal": (flops_q * B / (step_ms * 1e-3)) / (tf_sust * 1e12),
@@ -406,12 +453,13 @@ def run_ours(args):
             for k, v in json.load(open(tpath)).items():
                 if k in rooflines:
                     rooflines[k]["traffic"] = v
-        # headline roofline = the dominant kernel of the step (tcgen05 tf32 GEMM: ~40% of the step in the ncu launch
-        # list, profiles/r1_launches_step_v4.txt), at its largest shape; the HBM-class kernel north_star names and
-        # the bf16x3 kind ride along in rooflines_all
-        key = "gemm_tf32_patch_slf_in"
+        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v8.txt:
+        # the bf16x3 tcgen05 GEMM, 26 % of the step; the f16 kind is next at 23 %), at its largest shape; the other GEMM
+        # kinds, the HBM-class Gaussian-expert kernel north_star names and the ToMe chain ride along in rooflines_all
+        key = "gemm_bf16x3_avq_in_src"
         line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
-        line["roofline"]["kernel"] = "tc::gemm_tc_kernel<KIND_TF32,256,4> PatchSelecter slf in-proj [57344,512]x[1536,512]^T"
+        line["roofline"]["kernel"] = "tc::gemm_tc_kernel<KIND_BF16X3,256,2> AVQCrossAttn packed in-proj [15360,512]x[3584,512]^T"
+        line["roofline"]["note"] = rooflines[key]["note"]
         line["rooflines_all"] = rooflines
         if world == 1 and not args.no_cpu_baseline:
             qps_cpu, cores, sec = cpu_reference_forward(8, 5, 2, with_text=False)

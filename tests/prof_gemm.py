@@ -4,19 +4,23 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from qa_tiger_b200 import _cabi
 dev = torch.device("cuda:0")
-shapes = {"tf32_slf_in": (1, 57344, 1536, 512), "tf32_proj": (1, 57344, 512, 1024), "tf32_slf_out": (1, 57344, 512, 512),
-          "x3_in_src": (2, 15360, 3584, 512), "x3_w1": (2, 15360, 1792, 512)}
+shapes = {"tf32_slf_in": (1, 57344, 1536, 512), "tf32_proj": (1, 114688, 512, 1024), "tf32_slf_out": (1, 57344, 512, 512),
+          "x3_in_src": (2, 15360, 3584, 512), "x3_w1": (2, 15360, 1792, 512),
+          "f16_slf_in": (3, 114688, 1536, 512), "f16_slf_out": (3, 114688, 512, 512), "f16_crs_kv": (3, 114688, 1024, 512)}
+F16_OUT = {"tf32_proj", "f16_slf_in", "f16_slf_out", "f16_crs_kv"}     # outputs that are fp16 planes on the product path
 which = sys.argv[1:] or list(shapes)
 for nm in which:
     kind, M, N, K = shapes[nm]
     a = torch.randn(M, K, device=dev); w = torch.randn(N, K, device=dev) * K ** -0.5
-    lin = _cabi.Lin(w, torch.randn(N, device=dev), _cabi.PREC_BF16)
+    lin = _cabi.Lin(w, torch.randn(N, device=dev), _cabi.PREC_BF16, f16=True)
     planes = _cabi.split_planes(a) if kind == 2 else None
-    for _ in range(2): _cabi.gemm(kind, a, lin, a_planes=planes)
+    if kind == 3: a = a.half()
+    run = lambda: _cabi.gemm(kind, a, lin, a_planes=planes, out_f16=nm in F16_OUT)
+    for _ in range(2): run()
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
-        for _ in range(5): _cabi.gemm(kind, a, lin, a_planes=planes)
+        for _ in range(5): run()
     g.replay(); torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
