@@ -651,7 +651,7 @@ __device__ __forceinline__ void mma3_f16(float (&d)[4], const uint32_t (&ah)[4],
 // registers (the S accumulator fragments of two key tiles are exactly the A fragment of one P*V k-step).
 // One CTA (4 warps) per (sequence, head); warp w owns query rows 16w..16w+15 of each 64-row pass.
 template <int NT16>   // key tiles of 16: Lk <= 16*NT16
-__global__ void __launch_bounds__(128) attn_mma16_kernel(AttnP p) {
+__global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   constexpr int LKP = 16 * NT16, RSB = 144;              // padded key count, row stride in bytes (72 halves)
   const int Lq = p.Lq, Lk = p.Lk;

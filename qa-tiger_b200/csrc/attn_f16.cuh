@@ -6,50 +6,58 @@
 namespace qat {
 
 struct AttnHP {
-  const __half* q;       // [nseq, L, ld] rows; head h at columns h*64
-  const __half* k;
-  const __half* v;
-  long long ld;          // row stride (elements), shared by q, k, v
-  __half* o;             // [nseq, L, ldo]
+  const __half* q;       // [nseq, Lq, ldq] rows; head h at columns h*64
+  const __half* kv;      // [nseq, Lk, ldkv] rows: K at columns [0, D), V at [D, 2D) of the row (K | V packed)
+  long long ldq, ldkv;   // row strides (elements)
+  __half* o;             // [nseq, Lq, ldo]
   long long ldo;
-  int nseq, H, L;
+  int nseq, H, Lq, Lk;
   float scale;
 };
 
-// ---- self-attention over L <= 16 tokens (the 14 patch tokens of a frame, modules.py:688) -------------------
-// One CTA per sequence, one warp per head.  The sequence's [L, 3D] fp16 rows are staged once with cp.async
-// (row stride padded by 16 bytes: conflict-free ldmatrix); S = Q K^T is 4 k-steps x 2 key tiles of
+// ---- attention over <= 16 queries and <= 16 keys (modules.py:688 the 14 patch tokens of a frame attending to each
+// other; :698 the frame's [video; audio] query pair attending to them) -----------------------------------------
+// One CTA per sequence, one warp per head.  The sequence's fp16 rows (Q: [Lq, D], K|V: [Lk, 2D]) are staged once
+// with cp.async (row strides padded by 16 bytes: conflict-free ldmatrix); S = Q K^T is 4 k-steps x 2 key tiles of
 // mma.m16n8k16 (fp32 accumulate), the softmax lives in the C fragments (a row is spread over a quad), P goes
 // back in as the A fragment (fp16) and O = P V is 8 dim tiles x 1 k-step with V through ldmatrix.trans.
-// Rows / keys >= L are clamped to row L-1 when addressing shared memory; padded keys are masked to -inf.
-__global__ void __launch_bounds__(256) attn_small_f16_kernel(AttnHP p) {
+// Rows / keys beyond the sequence are clamped to the last row when addressing shared memory; padded keys are
+// masked to -inf, padded query rows are computed and dropped.
+template <int H>
+__global__ void __launch_bounds__(32 * H) attn_small_f16_kernel(AttnHP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int H = p.H, L = p.L, D = H * HD;
-  const int rs = (3 * D + 8) * 2;                    // smem row stride in bytes
+  constexpr int D = H * HD;
+  constexpr int rsq = (D + 8) * 2, rskv = (2 * D + 8) * 2;      // smem row strides in bytes
+  const int Lq = p.Lq, Lk = p.Lk;
+  unsigned char* sq = smem_raw;
+  unsigned char* skv = smem_raw + Lq * rsq;
   const int tid = threadIdx.x, lane = tid & 31, h = tid >> 5;
   const long long n = blockIdx.x;
   {
-    const int chunks = 3 * D / 8;                    // 16-byte chunks per row
-    const int dch = D / 8;
-    for (int f = tid; f < L * chunks; f += blockDim.x) {
-      const int r = f / chunks, cc = f % chunks;
-      const int part = cc / dch, c = cc % dch;
-      const __half* base = part == 0 ? p.q : (part == 1 ? p.k : p.v);
-      cp_async16(smem_raw + r * rs + cc * 16, base + (n * L + r) * p.ld + c * 8);
+    constexpr int qch = D / 8, kch = 2 * D / 8;       // 16-byte chunks per row
+    const __half* qb = p.q + n * Lq * p.ldq;
+    const __half* kb = p.kv + n * Lk * p.ldkv;
+    for (int f = tid; f < Lq * qch; f += 32 * H) {
+      const int r = f / qch, c = f % qch;
+      cp_async16(sq + r * rsq + c * 16, qb + r * p.ldq + c * 8);
+    }
+    for (int f = tid; f < Lk * kch; f += 32 * H) {
+      const int r = f / kch, c = f % kch;
+      cp_async16(skv + r * rskv + c * 16, kb + r * p.ldkv + c * 8);
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
   __syncthreads();
-  const uint32_t sbase = tc::smem_u32(smem_raw);
+  const uint32_t sqb = tc::smem_u32(sq), skb = tc::smem_u32(skv);
   const int g = lane >> 2, t = lane & 3;
   const int m = lane >> 3, r8 = lane & 7;
   float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   {
-    const int qrow = min(r8 + (m & 1) * 8, L - 1), qcol = (m >> 1) * 8;
-    const int krow = min(r8 + (m >> 1) * 8, L - 1), kcol = (m & 1) * 8;
-    const uint32_t qa = sbase + qrow * rs + (h * HD + qcol) * 2;
-    const uint32_t ka = sbase + krow * rs + (D + h * HD + kcol) * 2;
+    const int qrow = min(r8 + (m & 1) * 8, Lq - 1), qcol = (m >> 1) * 8;
+    const int krow = min(r8 + (m >> 1) * 8, Lk - 1), kcol = (m & 1) * 8;
+    const uint32_t qa = sqb + qrow * rsq + (h * HD + qcol) * 2;
+    const uint32_t ka = skb + krow * rskv + (h * HD + kcol) * 2;
 #pragma unroll
     for (int ks = 0; ks < 4; ++ks) {
       uint32_t a[4], b[4];
@@ -65,7 +73,7 @@ __global__ void __launch_bounds__(256) attn_small_f16_kernel(AttnHP p) {
   for (int nt = 0; nt < 2; ++nt)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      const bool ok = nt * 8 + 2 * t + e < L;
+      const bool ok = nt * 8 + 2 * t + e < Lk;
       s[nt][e] = ok ? s[nt][e] * p.scale : -INFINITY;
       s[nt][2 + e] = ok ? s[nt][2 + e] * p.scale : -INFINITY;
       mx0 = fmaxf(mx0, s[nt][e]);
@@ -101,8 +109,8 @@ __global__ void __launch_bounds__(256) attn_small_f16_kernel(AttnHP p) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
   {
-    const int vrow = min(r8 + (m & 1) * 8, L - 1), vcol = (m >> 1) * 8;
-    const uint32_t va = sbase + vrow * rs + (2 * D + h * HD + vcol) * 2;
+    const int vrow = min(r8 + (m & 1) * 8, Lk - 1), vcol = (m >> 1) * 8;
+    const uint32_t va = skb + vrow * rskv + (D + h * HD + vcol) * 2;
 #pragma unroll
     for (int dp = 0; dp < 4; ++dp) {
       uint32_t b[4];
@@ -117,26 +125,38 @@ __global__ void __launch_bounds__(256) attn_small_f16_kernel(AttnHP p) {
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) {
     const int col = h * HD + dt * 8 + 2 * t;
-    if (g < L) *reinterpret_cast<uint32_t*>(smem_raw + g * rs + col * 2) = pack_half2(o[dt][0], o[dt][1]);
-    if (g + 8 < L) *reinterpret_cast<uint32_t*>(smem_raw + (g + 8) * rs + col * 2) = pack_half2(o[dt][2], o[dt][3]);
+    if (g < Lq) *reinterpret_cast<uint32_t*>(sq + g * rsq + col * 2) = pack_half2(o[dt][0], o[dt][1]);
+    if (g + 8 < Lq) *reinterpret_cast<uint32_t*>(sq + (g + 8) * rsq + col * 2) = pack_half2(o[dt][2], o[dt][3]);
   }
   __syncthreads();
   {
-    const int dch = D / 8;
-    for (int f = tid; f < L * dch; f += blockDim.x) {
+    constexpr int dch = D / 8;
+    for (int f = tid; f < Lq * dch; f += 32 * H) {
       const int r = f / dch, c = f % dch;
-      *reinterpret_cast<uint4*>(p.o + (n * L + r) * p.ldo + c * 8) = *reinterpret_cast<const uint4*>(smem_raw + r * rs + c * 16);
+      *reinterpret_cast<uint4*>(p.o + (n * Lq + r) * p.ldo + c * 8) = *reinterpret_cast<const uint4*>(sq + r * rsq + c * 16);
     }
   }
 }
 
 inline int attention_small_f16(Ctx& c, const AttnHP& p) {
-  QAT_REQUIRE(p.L >= 1 && p.L <= 16 && p.H >= 1 && p.H <= 8, "attention_small_f16: need L<=16 and H<=8 (L=%d H=%d)", p.L, p.H);
-  QAT_REQUIRE(p.ld % 8 == 0 && p.ldo % 8 == 0, "attention_small_f16: row strides must be multiples of 8 elements");
+  QAT_REQUIRE(p.Lq >= 1 && p.Lq <= 16 && p.Lk >= 1 && p.Lk <= 16 && p.H >= 1 && p.H <= 8,
+              "attention_small_f16: need Lq, Lk <= 16 and H <= 8 (Lq=%d Lk=%d H=%d)", p.Lq, p.Lk, p.H);
+  QAT_REQUIRE(p.ldq % 8 == 0 && p.ldkv % 8 == 0 && p.ldo % 8 == 0, "attention_small_f16: row strides must be multiples of 8 elements");
   if (c.dry || p.nseq == 0) return QAT_OK;
-  const size_t smem = (size_t)p.L * (3 * p.H * HD + 8) * 2;
-  if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(attn_small_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attn_small_f16_kernel<<<(unsigned)p.nseq, 32 * p.H, smem, c.stream>>>(p);
+  QAT_REQUIRE(((reinterpret_cast<uintptr_t>(p.q) | reinterpret_cast<uintptr_t>(p.kv) | reinterpret_cast<uintptr_t>(p.o)) & 15) == 0,
+              "attention_small_f16: tensors must be 16-byte aligned");
+  const int D = p.H * HD;
+  const size_t smem = (size_t)p.Lq * (D + 8) * 2 + (size_t)p.Lk * (2 * D + 8) * 2;
+  switch (p.H) {
+#define QAT_SMALL_CASE(HH)                                                                                                    \
+  case HH:                                                                                                                    \
+    if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(attn_small_f16_kernel<HH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attn_small_f16_kernel<HH><<<(unsigned)p.nseq, 32 * HH, smem, c.stream>>>(p);                                              \
+    break;
+    QAT_SMALL_CASE(1) QAT_SMALL_CASE(2) QAT_SMALL_CASE(3) QAT_SMALL_CASE(4) QAT_SMALL_CASE(5) QAT_SMALL_CASE(6) QAT_SMALL_CASE(7) QAT_SMALL_CASE(8)
+#undef QAT_SMALL_CASE
+    default: QAT_FAIL(QAT_EINVAL, "attention_small_f16: H=%d unsupported", p.H);
+  }
   return check_launch("attn_small_f16_kernel");
 }
 
@@ -162,7 +182,7 @@ __global__ void __launch_bounds__(256) attn_fewq_f16_kernel(AttnP p, const __hal
     l[i] = 0.f;
   }
   const int Lk = p.Lk;
-  constexpr int UN = 8;
+  constexpr int UN = 16;            // the 14 patch tokens of a frame go out as ONE batch of 2 x 14 independent loads
   for (int j0 = 0; j0 < Lk; j0 += UN) {
     uint32_t kk[UN], vv[UN];
 #pragma unroll

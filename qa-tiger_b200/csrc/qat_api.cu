@@ -278,10 +278,13 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
                      !(getenv("QAT_PATCH_FP32_PLANES") && getenv("QAT_PATCH_FP32_PLANES")[0] == '1');
   // per-frame query rows [video; audio] -> q2 [BT, 2, D]  (modules.py:692: video first)
   Act Q2, O2, O3, Hm, Mo;
-  QAT_TRY(act_alloc(c, Q2, BT, 2 * D, true, false));
   {
     GemmKind kq = pick_kind(c, BT, D, D, false, Wq);
     if (sel16 && Wq.h16) kq = G_F16;
+    // queries as an fp16 plane when the mma.sync cross-attention core will read them (fp16 path, P <= 16)
+    const bool q16 = kq == G_F16 && sel16 && Wco.h16 && P <= 16 && H <= 8 && Wsi.h16 && Wso.h16 && Wkv.h16;
+    if (q16) QAT_TRY(act_alloc_h(c, Q2, BT, 2 * D));
+    else QAT_TRY(act_alloc(c, Q2, BT, 2 * D, true, false));
     Act Xv, Xa;
     QAT_TRY(operand_of(c, a->video, BT, D, kq, Xv));
     QAT_TRY(operand_of(c, a->audio, BT, D, kq, Xa));
@@ -323,8 +326,8 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
       QAT_TRY(gemm(c, G_F16, Pp, rows, Wsi, Epi(), QKV));
       QAT_TRY(act_alloc_h(c, Oa, rows, D));
       AttnHP hp;
-      hp.q = QKV.h; hp.k = QKV.h + D; hp.v = QKV.h + 2 * D; hp.ld = 3 * D;
-      hp.o = Oa.h; hp.ldo = D; hp.nseq = (int)nf; hp.H = H; hp.L = P; hp.scale = scale;
+      hp.q = QKV.h; hp.kv = QKV.h + D; hp.ldq = 3 * D; hp.ldkv = 3 * D;
+      hp.o = Oa.h; hp.ldo = D; hp.nseq = (int)nf; hp.H = H; hp.Lq = P; hp.Lk = P; hp.scale = scale;
       QAT_TRY(attention_small_f16(c, hp));
       // p' = p + slf_attn(p)   (:688, no LayerNorm)
       QAT_TRY(act_alloc_h(c, P2, rows, D));
@@ -335,7 +338,15 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
       }
       QAT_TRY(act_alloc_h(c, KV, rows, 2 * D));
       QAT_TRY(gemm(c, G_F16, P2, rows, Wkv, Epi(), KV));
-      QAT_TRY(attention_fewq_f16(c, q, KV.h, KV.h + D));
+      if (Q2.h && O2.h && !O2.f && !O2.hi) {
+        // [video; audio] query pair of every frame against the frame's K | V rows, all fp16 planes, same mma.sync core
+        AttnHP cp;
+        cp.q = Q2.h + (size_t)f0 * 2 * D; cp.ldq = D; cp.kv = KV.h; cp.ldkv = 2 * D;
+        cp.o = O2.h + (size_t)f0 * 2 * D; cp.ldo = D; cp.nseq = (int)nf; cp.H = H; cp.Lq = 2; cp.Lk = P; cp.scale = scale;
+        QAT_TRY(attention_small_f16(c, cp));
+      } else {
+        QAT_TRY(attention_fewq_f16(c, q, KV.h, KV.h + D));
+      }
       continue;
     }
     Act Pp, QKV, Oa, P2, KV;
