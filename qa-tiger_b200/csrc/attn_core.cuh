@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(AttnP p) {
     l[i] = 0.f;
   }
   const int Lk = p.Lk;
-  constexpr int UN = 4;
+  constexpr int UN = LQ == 1 ? 16 : 8;   // independent K/V row loads in flight per batch (latency-bound kernel)
   for (int j0 = 0; j0 < Lk; j0 += UN) {
     float2 kk[UN], vv[UN];
 #pragma unroll

@@ -88,6 +88,7 @@ struct GemmP {
   int M, N, K;
   Epi epi;
   Act C;
+  int tma_res;     // 1: the fp16 residual (epi.res_h) arrives through the mR tensor map into the warp's box (fp16-only output)
   int dbg;         // profiling switches (QAT_GEMM_DBG): 1 = epilogue releases the accumulator without reading it,
                    // 2 = MMA issuer skips the MMAs, 4 = epilogue skips its global stores
 };
@@ -109,7 +110,7 @@ struct Cfg {
   static constexpr int W_BYTES = BN * ROW_BYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
   static constexpr int EPI_BYTES = 8 * 4096;                              // 8 epilogue warps x one 4 KB TMA-store box
-  static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
+  static constexpr int BAR_BYTES = (2 * STAGES + 4 + 8) * 8 + 16;        // + one residual-box barrier per epilogue warp
   static constexpr int SMEM = STAGES * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;   // + alignment slack
   static constexpr int TMEM_COLS = 2 * BN;                                // two accumulators: epilogue(i) overlaps mainloop(i+1)
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM allocation must be a power of two");
@@ -124,7 +125,8 @@ __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mW0, const __grid_constant__ CUtensorMap mW1,
                const __grid_constant__ CUtensorMap mCf, const __grid_constant__ CUtensorMap mChi,
-               const __grid_constant__ CUtensorMap mClo, const __grid_constant__ CUtensorMap mCh, GemmP p) {
+               const __grid_constant__ CUtensorMap mClo, const __grid_constant__ CUtensorMap mCh,
+               const __grid_constant__ CUtensorMap mR, GemmP p) {
   typedef Cfg<KIND, BN, STAGES> G;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
@@ -134,7 +136,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   uint64_t* empty = full + STAGES;
   uint64_t* tfull = empty + STAGES;      // [2]
   uint64_t* tempty = tfull + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  uint64_t* rbar = tempty + 2;           // [8] residual boxes (TMA-loaded fp16 residual), one per epilogue warp
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rbar + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + G::BK - 1) / G::BK;
@@ -157,6 +160,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       mbar_init(&tfull[a], 1);
       mbar_init(&tempty[a], 8);          // one arrival per epilogue warp
     }
+    for (int w = 0; w < 8; ++w) mbar_init(&rbar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -239,7 +243,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     unsigned char* box = reinterpret_cast<unsigned char*>(epi_smem) + ew * 4096;
     const uint32_t sbox = smem_u32(box);
     const uint32_t sw128 = uint32_t(lane & 7), sw64 = uint32_t((lane >> 1) & 3);
-    uint32_t lt = 0;
+    uint32_t lt = 0, nres = 0;
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = lt & 1;
@@ -259,6 +263,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         const bool live = col0 < p.N;                       // warp-uniform
         uint32_t v[32];
         if (live) tmem_ld32(tacc + uint32_t(c * 32), v);
+        if (live && p.tma_res) {
+          // fp16 residual box (32 rows x 32 columns, 64B swizzle) into the upper half of the warp's slot; rows / columns
+          // beyond the matrix are zero-filled by the TMA unit
+          // (the previous chunk's lanes finished reading this half before their fence.proxy.async + __syncwarp below;
+          //  the output box is the lower half, so an in-flight store of the previous chunk does not touch it)
+          if (lane == 0) {
+            mbar_arrive_expect_tx(&rbar[ew], 2048);
+            tma_load_2d(box + 2048, &mR, &rbar[ew], col0, m0 + lg * 32);
+          }
+        }
         // operands of the epilogue are fetched while the TMEM load is in flight
         float4 bb[8];
 #pragma unroll
@@ -273,7 +287,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live && row_ok && col0 + 4 * q < p.N) rr[q] = __ldg(reinterpret_cast<const float4*>(p.epi.res + row * p.epi.ldr + col0 + 4 * q));
           }
-        } else if (p.epi.res_h) {
+        } else if (p.epi.res_h && !p.tma_res) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -306,7 +320,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 32; ++e) x[e] = epi_act(x[e], 2);
         }
-        if (p.epi.res || p.epi.res_h) {
+        if (p.tma_res) {
+          mbar_wait(&rbar[ew], nres & 1);
+          ++nres;
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) {
+            const uint4 u = *reinterpret_cast<const uint4*>(box + 2048 + lane * 64 + ((q ^ sw64) << 4));
+            const float2 r0 = unpack_half2(u.x), r1 = unpack_half2(u.y), r2 = unpack_half2(u.z), r3 = unpack_half2(u.w);
+            x[8 * q] += r0.x; x[8 * q + 1] += r0.y; x[8 * q + 2] += r1.x; x[8 * q + 3] += r1.y;
+            x[8 * q + 4] += r2.x; x[8 * q + 5] += r2.y; x[8 * q + 6] += r3.x; x[8 * q + 7] += r3.y;
+          }
+        } else if (p.epi.res || p.epi.res_h) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             x[4 * q] += rr[q].x; x[4 * q + 1] += rr[q].y; x[4 * q + 2] += rr[q].z; x[4 * q + 3] += rr[q].w;
@@ -355,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         }
         if (p.C.h) {
           // an fp16 box is 2 KB: when it is the only plane the two halves of the warp's 4 KB slot alternate
-          const bool solo = !p.C.f && !p.C.hi;
+          const bool solo = !p.C.f && !p.C.hi && !p.tma_res;
           const uint32_t hb = solo ? uint32_t(c & 1) * 2048u : 0u;
           if (lane == 0) {
             if (solo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -442,7 +466,7 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   typedef Cfg<KIND, BN, STAGES> G;
   const CUtensorMapDataType dt = KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : (KIND == KIND_BF16X3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
-  CUtensorMap mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh;
+  CUtensorMap mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR;
   QAT_TRY(make_map(&mA0, A0, dt, M, K, lda, G::BM));
   QAT_TRY(make_map(&mW0, W0, dt, N, K, K, BN));
   if (G::PLANES == 2) {
@@ -461,6 +485,14 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   if (C.h) QAT_TRY(make_store_map(&mCh, C.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
   GemmP p;
   p.M = (int)M; p.N = N; p.K = K; p.epi = epi; p.C = C;
+  // fp16 residual next to an fp16-only output: through the TMA unit as well (lane-per-row LSU loads of a row-strided
+  // residual cost 32 L1 wavefronts per instruction and made the PatchSelecter out-proj epilogue-bound)
+  mR = mA0;
+  p.tma_res = 0;
+  if (epi.res_h && !epi.res && C.h && !C.f && !C.hi && (reinterpret_cast<uintptr_t>(epi.res_h) & 15) == 0 && epi.ldr % 8 == 0) {
+    QAT_TRY(make_store_map(&mR, epi.res_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, epi.ldr));
+    p.tma_res = 1;
+  }
   const char* dbg = getenv("QAT_GEMM_DBG");
   p.dbg = dbg ? atoi(dbg) : 0;
   auto kern = gemm_tc_kernel<KIND, BN, STAGES>;
@@ -470,7 +502,7 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, 320, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, p);
+  kern<<<grid, 320, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR, p);
   return check_launch("gemm_tc_kernel");
 }
 
