@@ -136,3 +136,80 @@ def format_report(result: Dict[str, object]) -> List[str]:
     key = "Total avg"
     lines.append(f"Test {key:>24} accuracy: {result['acc']:.2f}({result['correct']}/{result['total']})")
     return lines
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# `python -m qa_tiger_b200.evalloop` (or under torchrun, one rank per GPU): BASELINE.json configs[3], the data-parallel
+# eval over a synthetic MUSIC-AVQA-test-sized set.  The shard is generated on the device up front (resident inputs:
+# 9 129 questions x 3.65 MB = 33 GB fit one B200), then the eval loop is timed: text tower + hot path + argmax +
+# on-device counters per local batch, one all_gather + one all_reduce at the end.
+def _main():
+    import argparse
+    import json
+    import os
+    import time
+    import warnings
+
+    from .models.net import QA_TIGER
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n", type=int, default=9129)
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--unique-questions", type=int, default=33, help="question pool size (MUSIC-AVQA test: 33 unique strings); 0 = all distinct")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--text", default="native", choices=["native", "fp32", "bf16x3"])
+    ap.add_argument("--no-dedup", action="store_true")
+    args = ap.parse_args()
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("qa_tiger_b200.evalloop needs a GPU (there is no CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(713)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = QA_TIGER(d_model=512, video_dim=768, patch_dim=1024, audio_dim=128, topK=7, num_experts=7)
+    model = model.to(dev).eval().set_precision(args.precision)
+    model.quest_encoder.compute = args.text
+    model.quest_encoder.dedup = not args.no_dedup
+    ds = SyntheticAVQA(args.n, n_unique_questions=args.unique_questions)
+    t0 = time.perf_counter()
+    cache = {(s, e): ds.batch(s, e, dev) for (s, e) in local_batches(args.n, rank, world, args.batch)}
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t0
+
+    class Resident:
+        n = args.n
+
+        @staticmethod
+        def batch(s, e, device):
+            return cache[(s, e)]
+
+    fwd = lambda b: model(b)["out"]
+    evaluate(fwd, Resident, dev, args.batch, rank, world)          # warm-up pass (weight preparation, workspaces)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    res = evaluate(fwd, Resident, dev, args.batch, rank, world)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dt = time.perf_counter() - t0
+    if rank == 0:
+        print(json.dumps({"workload": f"DP eval over {args.n} synthetic questions (configs[3]), per-GPU batch {args.batch}, "
+                                      f"question pool {args.unique_questions or 'all distinct'}, text tower {args.text}"
+                                      f"{'' if args.no_dedup else ' + dedup'}",
+                          "n_gpus": world, "questions": args.n, "wall_s": dt, "questions_per_s": args.n / dt,
+                          "local_batches_rank0": len(cache), "generate_s_rank0": t_gen, "acc_vs_random_labels": res["acc"],
+                          "total": res["total"], "collectives": "1 all_gather_into_tensor + 1 all_reduce(int64[20])" if world > 1 else "none"}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    _main()

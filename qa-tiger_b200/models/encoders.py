@@ -209,9 +209,31 @@ class CLIP_TEncoder(nn.Module):
                 torch.backends.cuda.matmul.allow_tf32 = prev
         return self._forward(text)
 
+    def _unique_rows(self, text: torch.Tensor):
+        """(unique rows, inverse) of the token matrix.  On CUDA torch.unique(dim=0) costs ~13 ms at B=256 (measured,
+        tests/prof_cpu_overhead.py); a 64-bit multiplicative row hash + 1-D unique + an exact check of the
+        reconstruction does the same in a fraction of a millisecond."""
+        if not text.is_cuda:
+            return torch.unique(text, dim=0, return_inverse=True)
+        B, L = text.shape
+        key = (text.device, L)
+        mult = self.__dict__.setdefault("_hash_mult", {}).get(key)
+        if mult is None:
+            g = torch.Generator().manual_seed(0x5EED)
+            mult = (torch.randint(-(1 << 62), 1 << 62, (L,), generator=g, dtype=torch.int64) * 2 + 1).to(text.device)
+            self.__dict__["_hash_mult"][key] = mult
+        h = (text.to(torch.int64) * mult).sum(dim=1)                       # wraps mod 2^64
+        hu, inv = torch.unique(h, return_inverse=True)
+        first = torch.full((hu.numel(),), B, dtype=torch.int64, device=text.device)
+        first.scatter_reduce_(0, inv, torch.arange(B, device=text.device), reduce="amin")
+        uniq = text[first]
+        if not torch.equal(uniq[inv], text):                                # a hash collision: take the exact path
+            return torch.unique(text, dim=0, return_inverse=True)
+        return uniq, inv
+
     def _forward(self, text):
         if self.dedup:
-            uniq, inv = torch.unique(text, dim=0, return_inverse=True)
+            uniq, inv = self._unique_rows(text)
             q, w = self._tower(uniq)
             return q[inv], w[inv]
         return self._tower(text)
