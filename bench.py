@@ -375,6 +375,26 @@ def run_ours(args):
                                  "frac": ach / (tf_sust / div), "traffic": None, "ms": t_ms, "shape": [M_, N_, K_],
                                  "note": f"nominal 2MNK FLOPs; peak = sustained bf16 / {div:g}"}
                 del xin, planes
+            # (2b) attention cores (HBM class: the (sequence, head) problems are far below a tensor tile):
+            #     patch self-attention, 8192 frames x 14 tokens, fp16 planes in and out (one PatchSelecter pass);
+            #     AVQ self-attention, 2*B sequences x 60 tokens, fp32 in / out, fp16 hi/lo mma.sync inside
+            nf = min(B * T, 8192)
+            q16 = torch.randn(nf, P, 8, 64, device=dev).half()
+            kv16 = torch.randn(nf, P, 2, 8, 64, device=dev).half()
+            t_ms = time_ms(lambda: _cabi.attention(q16, kv16, None), n=6)
+            byts = (q16.numel() + kv16.numel() + q16.numel()) * 2
+            ach = byts / (t_ms * 1e-3) / 1e9
+            rooflines["attn_small_f16_patch_slf"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                                     "traffic": None, "ms": t_ms, "bytes": byts, "shape": [nf, 8, P, P]}
+            del q16, kv16
+            qa = [torch.randn(2 * B, T, 8, 64, device=dev) for _ in range(3)]
+            t_ms = time_ms(lambda: _cabi.attention(qa[0], qa[1], qa[2]), n=6)
+            byts = 4 * qa[0].numel() * 4
+            ach = byts / (t_ms * 1e-3) / 1e9
+            rooflines["attn_mma16_avq_slf"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
+                                               "traffic": None, "ms": t_ms, "bytes": byts, "shape": [2 * B, 8, T, T],
+                                               "note": "252 MB working set: partly L2-resident between replays"}
+            del qa
             # (3) ToMe 577->14 chain (config 3 shape, 480 frames = 1.1 GB of tokens > L2): frames/s and the stepwise
             #     merge traffic of SURVEY 8d (56.49 MB per frame) over the WHOLE chain time (match kernels included)
             try:

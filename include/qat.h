@@ -110,6 +110,29 @@ typedef struct {
 } QatGemmArgs;
 int qat_gemm(const QatGemmArgs* a);
 
+/* ---- softmax(q k^T * scale) v on head-dim-64 heads: the attention cores every block above is built from (torch MHA
+ *      slow path semantics, SURVEY 8a-A3: no masks except `causal`); exported for parity tests and roofline timing ---- */
+enum { QAT_ATTN_F32 = 0,       /* fp32 q/k/v, generic strided views; the library picks the core from (Lq, Lk) */
+       QAT_ATTN_F16_SMALL = 1  /* fp16 planes, Lq, Lk <= 16, H <= 8: one CTA per sequence on mma.sync (PatchSelecter) */ };
+typedef struct {
+  int32_t kind;
+  int32_t nseq, H, Lq, Lk;
+  float scale;
+  int32_t causal;          /* F32 only, Lk > 32 or Lq >= 32 */
+  void* stream;
+  const void* q;           /* F32: element (n, i, h, d) at n*q_sn + i*q_si + h*64 + d;  F16_SMALL: rows [nseq*Lq, q_si] */
+  const void* k;           /* F32: kv sequence of query sequence n is (n + k_shift) % k_mod; F16_SMALL: rows [nseq*Lk, k_si] = K | V packed */
+  const void* v;           /* F32 only */
+  int64_t q_sn, q_si, k_sn, k_si;
+  int32_t k_shift, k_mod;
+  float* o;                /* F32: row n*o_rn + i*o_ri of a [rows, ldo] matrix, col h*64 + d */
+  void* o_f16;             /* F16_SMALL: rows [nseq*Lq, ldo] */
+  int64_t o_rn, o_ri;
+  int32_t ldo;
+  float* attw;             /* F32 only: optional [nseq, Lq, Lk] head-averaged weights, zero-initialised by the caller */
+} QatAttnArgs;
+int qat_attention_fwd(const QatAttnArgs* a);
+
 /* ---- A1-A3: AVQCrossAttn.forward, modules.py:239-265 (sub_forward :194-237) ----------------- */
 typedef struct {
   int32_t B, T, L, D, H; /* T frames, L words; D = H*64 */

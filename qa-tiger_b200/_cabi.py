@@ -112,6 +112,15 @@ class TomeChainArgs(C.Structure):
                 ("idx_trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class AttnArgs(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nseq", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
+                ("scale", C.c_float), ("causal", C.c_int32), ("stream", C.c_void_p),
+                ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
+                ("q_sn", C.c_int64), ("q_si", C.c_int64), ("k_sn", C.c_int64), ("k_si", C.c_int64),
+                ("k_shift", C.c_int32), ("k_mod", C.c_int32), ("o", C.c_void_p), ("o_f16", C.c_void_p),
+                ("o_rn", C.c_int64), ("o_ri", C.c_int64), ("ldo", C.c_int32), ("attw", C.c_void_p)]
+
+
 class ClipLayerW(C.Structure):
     _fields_ = [("ln_1", LayerNormW), ("ln_2", LayerNormW), ("in_proj", LinearW), ("out_proj", LinearW),
                 ("c_fc", LinearW), ("c_proj", LinearW)]
@@ -127,6 +136,7 @@ class ClipTextArgs(C.Structure):
 
 EXPORTS = {
     "qat_gemm": (C.c_int, [C.POINTER(GemmArgs)]),
+    "qat_attention_fwd": (C.c_int, [C.POINTER(AttnArgs)]),
     "qat_linear_fwd": (C.c_int, [C.POINTER(LinearArgs)]),
     "qat_avq_cross_attn_fwd": (C.c_int, [C.POINTER(AvqArgs)]),
     "qat_patch_select_fwd": (C.c_int, [C.POINTER(PatchArgs)]),
@@ -271,6 +281,32 @@ def gemm(kind: int, a: torch.Tensor, lin: "Lin", relu: bool = False, res: Option
     with torch.cuda.device(dev):
         check(lib().qat_gemm(C.byref(g)), "qat_gemm")
     return (c, planes) if out_planes else c
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False, need_weights: bool = False):
+    """softmax(q k^T / 8) v on the library's attention cores (parity tests / roofline timing).
+    fp32: q [N,Lq,H,64], k, v [N,Lk,H,64] (contiguous) -> o [N,Lq,H*64] (+ head-averaged weights [N,Lq,Lk]).
+    fp16: q [N,Lq,H,64], k and v are the halves of ONE packed tensor kv [N,Lk,2,H,64] (pass kv as `k`, v=None) -> fp16 o."""
+    N, Lq, H, hd = q.shape
+    assert hd == 64
+    a = AttnArgs()
+    a.nseq, a.H, a.Lq, a.scale, a.causal, a.stream = N, H, Lq, 0.125, int(causal), stream_ptr(q.device)
+    if q.dtype == torch.float16:
+        Lk = k.shape[1]
+        o = torch.empty(N, Lq, H * 64, device=q.device, dtype=torch.float16)
+        a.kind, a.Lk, a.q, a.k, a.q_si, a.k_si, a.o_f16, a.ldo = 1, Lk, q.data_ptr(), k.data_ptr(), H * 64, 2 * H * 64, o.data_ptr(), H * 64
+        with torch.cuda.device(q.device):
+            check(lib().qat_attention_fwd(C.byref(a)), "qat_attention_fwd")
+        return o
+    Lk = k.shape[1]
+    o = torch.empty(N, Lq, H * 64, device=q.device, dtype=torch.float32)
+    w = torch.zeros(N, Lq, Lk, device=q.device, dtype=torch.float32) if need_weights else None
+    a.kind, a.Lk, a.q, a.k, a.v = 0, Lk, q.data_ptr(), k.data_ptr(), v.data_ptr()
+    a.q_sn, a.q_si, a.k_sn, a.k_si, a.k_shift, a.k_mod = Lq * H * 64, H * 64, Lk * H * 64, H * 64, 0, N
+    a.o, a.o_rn, a.o_ri, a.ldo, a.attw = o.data_ptr(), Lq, 1, H * 64, ptr(w)
+    with torch.cuda.device(q.device):
+        check(lib().qat_attention_fwd(C.byref(a)), "qat_attention_fwd")
+    return (o, w) if need_weights else o
 
 
 # ---- workspace ----------------------------------------------------------------------------------

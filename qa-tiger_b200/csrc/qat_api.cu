@@ -163,6 +163,27 @@ static int run_gemm(const QatGemmArgs* a, Ctx& c) {
   return gemm(c, (GemmKind)a->kind, A, a->M, wview(a->w), e, C);
 }
 
+static int run_attention(const QatAttnArgs* a, Ctx& c) {
+  QAT_REQUIRE(a->nseq >= 0 && a->H >= 1 && a->Lq >= 1 && a->Lk >= 1, "attention: bad shape");
+  if (a->kind == QAT_ATTN_F16_SMALL) {
+    QAT_REQUIRE(a->q && a->k && a->o_f16, "attention: NULL tensor");
+    AttnHP p;
+    p.q = reinterpret_cast<const __half*>(a->q); p.kv = reinterpret_cast<const __half*>(a->k);
+    p.ldq = a->q_si; p.ldkv = a->k_si; p.o = reinterpret_cast<__half*>(a->o_f16); p.ldo = a->ldo;
+    p.nseq = a->nseq; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk; p.scale = a->scale;
+    return attention_small_f16(c, p);
+  }
+  QAT_REQUIRE(a->kind == QAT_ATTN_F32, "attention: unknown kind %d", a->kind);
+  QAT_REQUIRE(a->q && a->k && a->v && a->o && a->k_mod >= 1, "attention: NULL tensor or k_mod < 1");
+  QAT_REQUIRE(!a->causal || a->Lk > 32 || a->Lq >= 32, "attention: the causal core serves Lk > 32 or Lq >= 32");
+  AttnP p;
+  p.q = reinterpret_cast<const float*>(a->q); p.k = reinterpret_cast<const float*>(a->k); p.v = reinterpret_cast<const float*>(a->v);
+  p.q_sn = a->q_sn; p.q_si = a->q_si; p.k_sn = a->k_sn; p.k_si = a->k_si; p.k_shift = a->k_shift; p.k_mod = a->k_mod;
+  p.o = act_of(a->o, a->ldo); p.o_rn = a->o_rn; p.o_ri = a->o_ri; p.attw = a->attw;
+  p.nseq = a->nseq; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk; p.scale = a->scale; p.causal = a->causal;
+  return attention(c, p);
+}
+
 // =================================================================================================
 // A1-A3  AVQCrossAttn
 // =================================================================================================
@@ -748,6 +769,7 @@ using namespace qat;
 extern "C" {
 
 int qat_gemm(const QatGemmArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, run_gemm); }
+int qat_attention_fwd(const QatAttnArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, run_attention); }
 int qat_linear_fwd(const QatLinearArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_linear); }
 int qat_avq_cross_attn_fwd(const QatAvqArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_avq); }
 int qat_patch_select_fwd(const QatPatchArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_patch); }
