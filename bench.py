@@ -475,8 +475,8 @@ def run_ours(args):
             for k, v in json.load(open(tpath)).items():
                 if k in rooflines:
                     rooflines[k]["traffic"] = v
-        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v8.txt:
-        # the bf16x3 tcgen05 GEMM, 26 % of the step; the f16 kind is next at 23 %), at its largest shape; the other GEMM
+        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v10.txt:
+        # the bf16x3 tcgen05 GEMM, 29 % of the step; the f16 kind is next at 23 %), at its largest shape; the other GEMM
         # kinds, the HBM-class Gaussian-expert kernel north_star names and the ToMe chain ride along in rooflines_all
         key = "gemm_bf16x3_avq_in_src"
         line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
