@@ -665,22 +665,39 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
   const int g = lane >> 2, t = lane & 3;
   const float* kb = p.k + kn * p.k_sn + h * HD;
   const float* vb = p.v + kn * p.k_sn + h * HD;
-  for (int f = tid; f < LKP * 16; f += 128) {
-    const int j = f >> 4, c4 = f & 15;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-    if (j < Lk) {
-      kv = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
-      vv = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+  // staging in batches of 4 iterations: all 8 loads of a batch are issued before the first is consumed (the kernel is
+  // latency-bound: every exposed global-load round trip costs as much as the whole MMA work of the CTA; prefetching the
+  // Q fragments as well was measured slower -- it costs the fourth resident CTA)
+  constexpr int ITERS = LKP * 16 / 128;
+#pragma unroll
+  for (int it0 = 0; it0 < ITERS; it0 += 4) {
+    float4 kv[4], vv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int f = tid + (it0 + u) * 128;
+      const int j = f >> 4, c4 = f & 15;
+      kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vv[u] = kv[u];
+      if (it0 + u < ITERS && j < Lk) {
+        kv[u] = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
+        vv[u] = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+      }
     }
-    uint2 hi, lo;
-    split_half2(kv.x, kv.y, hi.x, lo.x);
-    split_half2(kv.z, kv.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(Kh + j * RSB + c4 * 8) = hi;
-    *reinterpret_cast<uint2*>(Kl + j * RSB + c4 * 8) = lo;
-    split_half2(vv.x, vv.y, hi.x, lo.x);
-    split_half2(vv.z, vv.w, hi.y, lo.y);
-    *reinterpret_cast<uint2*>(Vh + j * RSB + c4 * 8) = hi;
-    *reinterpret_cast<uint2*>(Vl + j * RSB + c4 * 8) = lo;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (it0 + u >= ITERS) break;
+      const int f = tid + (it0 + u) * 128;
+      const int j = f >> 4, c4 = f & 15;
+      uint2 hi, lo;
+      split_half2(kv[u].x, kv[u].y, hi.x, lo.x);
+      split_half2(kv[u].z, kv[u].w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(Kh + j * RSB + c4 * 8) = hi;
+      *reinterpret_cast<uint2*>(Kl + j * RSB + c4 * 8) = lo;
+      split_half2(vv[u].x, vv[u].y, hi.x, lo.x);
+      split_half2(vv[u].z, vv[u].w, hi.y, lo.y);
+      *reinterpret_cast<uint2*>(Vh + j * RSB + c4 * 8) = hi;
+      *reinterpret_cast<uint2*>(Vl + j * RSB + c4 * 8) = lo;
+    }
   }
   __syncthreads();
   const uint32_t sKh = tc::smem_u32(Kh), sKl = tc::smem_u32(Kl), sVh = tc::smem_u32(Vh), sVl = tc::smem_u32(Vl);
