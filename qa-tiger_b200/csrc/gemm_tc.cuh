@@ -120,7 +120,10 @@ struct Cfg {
 // the A rows through L2).  Three decoupled loops meet only through mbarriers:
 //   full/empty[STAGES]   TMA <-> MMA    (smem ring, continuous across tiles)
 //   tfull/tempty[2]      MMA <-> epilogue (the two TMEM accumulators)
-template <int KIND, int BN, int STAGES>
+// EPI specialises the epilogue on the set of output planes (a smaller chunk body schedules measurably better):
+//   1 = one fp16 plane, residual (if any) through the TMA unit (the PatchSelecter GEMMs); 2 = one fp32 plane;
+//   3 = bf16 (hi, lo) planes; 0 = any combination behind run-time flags.
+template <int KIND, int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mW0, const __grid_constant__ CUtensorMap mW1,
@@ -235,6 +238,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     // Per 32-column chunk: tcgen05.ld (lane = row) -> bias / ReLU / residual in registers -> the warp's 32 x 32 box in
     // shared memory in the TMA swizzle layout -> one lane issues cp.async.bulk.tensor stores (one per output plane);
     // the TMA unit clips row / column tails, so the LSU never sees the (row-strided) output.
+    const bool out_f = EPI == 0 ? p.C.f != nullptr : EPI == 2, out_hi = EPI == 0 ? p.C.hi != nullptr : EPI == 3;
+    const bool out_lo = EPI == 0 ? p.C.lo != nullptr : EPI == 3, out_h = EPI == 0 ? p.C.h != nullptr : EPI == 1;
+    const float* const res_f = EPI == 1 ? nullptr : p.epi.res;
+    const __half* const res_h = (EPI == 1 && !p.tma_res) ? nullptr : p.epi.res_h;
     const int ew = warp - 2;
     const int lg = warp & 3;
     const int half = ew >> 2;
@@ -281,18 +288,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           if (live && p.epi.bias && col0 + 4 * q < p.N) bb[q] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col0 + 4 * q));
         }
         float4 rr[8];
-        if (p.epi.res) {
+        if (res_f) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (live && row_ok && col0 + 4 * q < p.N) rr[q] = __ldg(reinterpret_cast<const float4*>(p.epi.res + row * p.epi.ldr + col0 + 4 * q));
+            if (live && row_ok && col0 + 4 * q < p.N) rr[q] = __ldg(reinterpret_cast<const float4*>(res_f + row * p.epi.ldr + col0 + 4 * q));
           }
-        } else if (p.epi.res_h && !p.tma_res) {
+        } else if (EPI != 1 && res_h && !p.tma_res) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             rr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (live && row_ok && col0 + 4 * q < p.N) {
-              const uint2 u = __ldg(reinterpret_cast<const uint2*>(p.epi.res_h + row * p.epi.ldr + col0 + 4 * q));
+              const uint2 u = __ldg(reinterpret_cast<const uint2*>(res_h + row * p.epi.ldr + col0 + 4 * q));
               const float2 r0 = unpack_half2(u.x), r1 = unpack_half2(u.y);
               rr[q] = make_float4(r0.x, r0.y, r1.x, r1.y);
             }
@@ -330,14 +337,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             x[8 * q] += r0.x; x[8 * q + 1] += r0.y; x[8 * q + 2] += r1.x; x[8 * q + 3] += r1.y;
             x[8 * q + 4] += r2.x; x[8 * q + 5] += r2.y; x[8 * q + 6] += r3.x; x[8 * q + 7] += r3.y;
           }
-        } else if (p.epi.res || p.epi.res_h) {
+        } else if (EPI != 1 && (res_f || res_h)) {
 #pragma unroll
           for (int q = 0; q < 8; ++q) {
             x[4 * q] += rr[q].x; x[4 * q + 1] += rr[q].y; x[4 * q + 2] += rr[q].z; x[4 * q + 3] += rr[q].w;
           }
         }
         const int crow = m0 + lg * 32;
-        if (p.C.f) {
+        if (out_f) {
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the box is free again
           __syncwarp();
 #pragma unroll
@@ -351,7 +358,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        if (p.C.hi) {
+        if (out_hi) {
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
@@ -373,13 +380,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           __syncwarp();
           if (lane == 0 && !(p.dbg & 4)) {
             tma_store_2d(&mChi, box, col0, crow);
-            if (p.C.lo) tma_store_2d(&mClo, box + 2048, col0, crow);
+            if (out_lo) tma_store_2d(&mClo, box + 2048, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
-        if (p.C.h) {
+        if (out_h) {
           // an fp16 box is 2 KB: when it is the only plane the two halves of the warp's 4 KB slot alternate
-          const bool solo = !p.C.f && !p.C.hi && !p.tma_res;
+          const bool solo = !out_f && !out_hi && !p.tma_res;
           const uint32_t hb = solo ? uint32_t(c & 1) * 2048u : 0u;
           if (lane == 0) {
             if (solo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
@@ -495,14 +502,26 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   }
   const char* dbg = getenv("QAT_GEMM_DBG");
   p.dbg = dbg ? atoi(dbg) : 0;
-  auto kern = gemm_tc_kernel<KIND, BN, STAGES>;
-  QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
   const long long ntiles = (long long)((N + BN - 1) / BN) * ((M + G::BM - 1) / G::BM);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  kern<<<grid, 320, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR, p);
+  int mode = 0;
+  if (KIND != KIND_BF16X3 && C.h && !C.f && !C.hi && !epi.res && (!epi.res_h || p.tma_res)) mode = 1;
+  else if (C.f && !C.hi && !C.lo && !C.h) mode = 2;
+  else if (KIND == KIND_BF16X3 && C.hi && C.lo && !C.f && !C.h) mode = 3;
+#define QAT_GEMM_LAUNCH(EPI_)                                                                                 \
+  do {                                                                                                        \
+    auto kern = gemm_tc_kernel<KIND, BN, STAGES, EPI_>;                                                       \
+    QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));               \
+    kern<<<grid, 320, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR, p);                  \
+  } while (0)
+  if (mode == 1) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 ? 0 : 1));
+  else if (mode == 2) QAT_GEMM_LAUNCH(2);
+  else if (mode == 3) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 ? 3 : 0));
+  else QAT_GEMM_LAUNCH(0);
+#undef QAT_GEMM_LAUNCH
   return check_launch("gemm_tc_kernel");
 }
 
