@@ -304,6 +304,31 @@ int qat_tome_chain(const QatTomeChainArgs* a);
 int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token);
 size_t qat_tome_chain_trace_len(int N, int t0, int n_steps, const int32_t* r_list, int class_token);
 
+/* ---- the whole hot path in one call: QA_TIGER.forward net.py:120-142 on the text tower's outputs -----------------
+ * The embedded per-block structs carry WEIGHTS and hyper-parameters only (D, H, E, K, sigma, Cin, has_proj, chunk_frames,
+ * head); their tensor pointers, B/T/L/P, prec, stream and workspace fields are ignored.  at.topk_inds / topk_probs /
+ * gauss_weight (and vt.*) are honoured as optional outputs.  Intermediates live in the workspace and move between the
+ * blocks with the storage planes their consumers read, so no conversion pass runs at a module boundary. */
+typedef struct {
+  int32_t B, T, L, P;
+  int32_t prec;
+  void* stream;
+  const float* quest;     /* [B, quest_proj.k]   CLIP question feature */
+  const float* words;     /* [B, L, words_proj.k] */
+  const float* audio;     /* [B, T, audio_proj.k] */
+  const float* video;     /* [B, T, video_proj.k] */
+  const float* patch;     /* [B, T, P, patch_sel.Cin] */
+  QatLinearW audio_proj, video_proj, words_proj, quest_proj;   /* net.py:120-123; patch_proj is patch_sel.proj */
+  QatAvqArgs avq;
+  QatPatchArgs patch_sel;
+  QatMoeArgs at, vt;
+  QatGroundArgs ground;   /* both QstGrounding passes share these weights; `head` is applied after the second */
+  float* logits;          /* [B, ground.head.n] */
+  void* workspace;
+  size_t workspace_bytes;
+} QatForwardArgs;
+int qat_forward_fwd(const QatForwardArgs* a);
+
 /* ---- N1: frozen CLIP text tower, encoders.py:30-37 + base/clip_base.py:186-254 (ResidualAttentionBlock
  *      x + attn(ln_1 x), x + c_proj(QuickGELU(c_fc(ln_2 x))), causal mask), ln_final, EOT-row @ text_projection ---- */
 typedef struct {
@@ -333,7 +358,7 @@ int qat_clip_text_fwd(const QatClipTextArgs* a);
 
 /* ---- bookkeeping ---------------------------------------------------------------------------- */
 enum { QAT_OP_LINEAR = 0, QAT_OP_AVQ = 1, QAT_OP_PATCH = 2, QAT_OP_MOE = 3, QAT_OP_GROUND = 4,
-       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7, QAT_OP_CLIP_TEXT = 8 };
+       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7, QAT_OP_CLIP_TEXT = 8, QAT_OP_FORWARD = 9 };
 /* Pass the same args struct the op will be called with (pointers may be NULL). */
 size_t qat_workspace_bytes(int op, const void* args);
 const char* qat_last_error(void);

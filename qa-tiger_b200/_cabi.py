@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libqat_b200.so")
 
 PREC_FP32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
-OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT = range(9)
+OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT, OP_FORWARD = range(10)
 PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 
 c_f32p = C.c_void_p  # all device pointers travel as void*
@@ -92,6 +92,14 @@ class GroundArgs(C.Structure):
                 ("logits", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class ForwardArgs(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32), ("P", C.c_int32), ("prec", C.c_int32), ("stream", C.c_void_p),
+                ("quest", C.c_void_p), ("words", C.c_void_p), ("audio", C.c_void_p), ("video", C.c_void_p), ("patch", C.c_void_p),
+                ("audio_proj", LinearW), ("video_proj", LinearW), ("words_proj", LinearW), ("quest_proj", LinearW),
+                ("avq", AvqArgs), ("patch_sel", PatchArgs), ("at", MoeArgs), ("vt", MoeArgs), ("ground", GroundArgs),
+                ("logits", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 class TomeMatchArgs(C.Structure):
     _fields_ = [("N", C.c_int32), ("t", C.c_int32), ("C", C.c_int32), ("r", C.c_int32), ("class_token", C.c_int32),
                 ("stream", C.c_void_p), ("metric", C.c_void_p), ("unm_idx", C.c_void_p), ("src_idx", C.c_void_p),
@@ -144,6 +152,7 @@ EXPORTS = {
     "qat_temp_moe_fwd": (C.c_int, [C.POINTER(MoeArgs)]),
     "qat_qst_grounding_head_fwd": (C.c_int, [C.POINTER(GroundArgs)]),
     "qat_clip_text_fwd": (C.c_int, [C.POINTER(ClipTextArgs)]),
+    "qat_forward_fwd": (C.c_int, [C.POINTER(ForwardArgs)]),
     "qat_tome_match": (C.c_int, [C.POINTER(TomeMatchArgs)]),
     "qat_tome_clamp_r": (C.c_int, [C.c_int, C.c_int, C.c_int]),
     "qat_tome_merge": (C.c_int, [C.POINTER(TomeMergeArgs)]),

@@ -77,6 +77,21 @@ static int operand_of(Ctx& c, const float* x, long long rows, int cols, GemmKind
   return QAT_OK;
 }
 
+// make sure `x` (which always carries its fp32 view) also has the storage planes engine `k` reads; a conversion pass runs
+// only when the producer did not already emit them (inside qat_forward_fwd the producers do)
+static int ensure_operand(Ctx& c, Act& x, long long rows, int cols, GemmKind k) {
+  const bool need_hl = k == G_BF16X3 && !(x.hi && x.lo), need_h = k == G_F16 && !x.h;
+  if (!need_hl && !need_h) return QAT_OK;
+  QAT_REQUIRE(c.dry || x.f, "operand: fp32 view missing");
+  QAT_REQUIRE(x.ld == cols, "operand: planes need a dense fp32 view (ld=%d cols=%d)", x.ld, cols);
+  Act pl;
+  QAT_TRY(act_alloc_for(c, pl, rows, cols, k));
+  QAT_TRY(add_rows(c, x.f, x.ld, nullptr, 0, pl, rows, cols));
+  if (need_hl) { x.hi = pl.hi; x.lo = pl.lo; }
+  if (need_h) x.h = pl.h;
+  return QAT_OK;
+}
+
 static int gemm(Ctx& c, GemmKind kind, const Act& A, long long M, const WView& W, Epi epi, Act C) {
   if (!epi.bias) epi.bias = W.bias;
   switch (kind) {
@@ -128,16 +143,19 @@ static int ln(Ctx& c, const float* x0, long long ld0, const float* x1, long long
 // =================================================================================================
 // P1  Projection
 // =================================================================================================
-static int run_linear(const QatLinearArgs* a, Ctx& c) {
-  QAT_REQUIRE(a->rows >= 0 && a->w.n > 0 && a->w.k > 0, "linear: bad shape");
-  QAT_TRY(check_w(a->w, a->w.n, a->w.k, "linear.w", c.prec));
-  WView W = wview(a->w);
-  GemmKind kind = pick_kind(c, a->rows, W.n, W.k, false, W);
-  Act X;
-  QAT_TRY(planes_of(c, a->x, a->rows, W.k, reads_planes(kind), X));
+static int linear_core(Ctx& c, const QatLinearW& w, Act X, long long rows, int relu, Act Y) {
+  QAT_REQUIRE(rows >= 0 && w.n > 0 && w.k > 0, "linear: bad shape");
+  QAT_TRY(check_w(w, w.n, w.k, "linear.w", c.prec));
+  WView W = wview(w);
+  GemmKind kind = pick_kind(c, rows, W.n, W.k, false, W);
+  QAT_TRY(ensure_operand(c, X, rows, W.k, kind));
   Epi e;
-  e.relu = a->relu;
-  return gemm(c, kind, X, a->rows, W, e, act_of(a->y, W.n));
+  e.relu = relu;
+  return gemm(c, kind, X, rows, W, e, Y);
+}
+
+static int run_linear(const QatLinearArgs* a, Ctx& c) {
+  return linear_core(c, a->w, act_of(a->x, a->w.k), a->rows, a->relu, act_of(a->y, a->w.n));
 }
 
 static int run_gemm(const QatGemmArgs* a, Ctx& c) {
@@ -187,8 +205,11 @@ static int run_attention(const QatAttnArgs* a, Ctx& c) {
 // =================================================================================================
 // A1-A3  AVQCrossAttn
 // =================================================================================================
-static int run_avq(const QatAvqArgs* a, Ctx& c) {
-  const int B = a->B, T = a->T, L = a->L, D = a->D, H = a->H;
+// Xa / Xv / Xw carry the fp32 views (residuals) and whichever planes their producer emitted; out_a / out_v receive every
+// plane they point at (fp32 always; inside qat_forward_fwd also the planes the next blocks read)
+static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Act Xv, Act Xw, Act out_a, Act out_v, float* attw_audio,
+                    float* attw_video) {
+  const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && H >= 1 && D == H * 64, "avq: need D == H*64 (D=%d H=%d)", D, H);
   QAT_REQUIRE(T <= 128 && L <= 128, "avq: sequence lengths T=%d L=%d must be <= 128", T, L);
   QAT_TRY(check_w(a->in_src, 7 * D, D, "avq.in_src", c.prec));
@@ -201,10 +222,9 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
   const GemmKind k_src = pick_kind(c, BT, 7 * D, D, false, Wsrc), k_words = pick_kind(c, BL, 2 * D, D, false, Wwords);
   const GemmKind k_out = pick_kind(c, BT, D, 3 * D, false, Wout), k_f1 = pick_kind(c, BT, D, D, false, W1), k_f2 = pick_kind(c, BT, D, D, false, W2);
 
-  Act Xa, Xv, Xw;
-  QAT_TRY(planes_of(c, a->audio, BT, D, reads_planes(k_src), Xa));
-  QAT_TRY(planes_of(c, a->video, BT, D, reads_planes(k_src), Xv));
-  QAT_TRY(planes_of(c, a->words, BL, D, reads_planes(k_words), Xw));
+  QAT_TRY(ensure_operand(c, Xa, BT, D, k_src));
+  QAT_TRY(ensure_operand(c, Xv, BT, D, k_src));
+  QAT_TRY(ensure_operand(c, Xw, BL, D, k_words));
   // S = in-projections of both modalities, rows [0,BT) audio, [BT,2BT) video; cols as in_src
   Act S, KVw, O, X1, Hh, Y;
   QAT_TRY(act_alloc(c, S, 2 * BT, 7 * D, true, false));
@@ -222,14 +242,14 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
   // qst: keys/values = words of sample n % B
   p.q = S.f; p.k = KVw.f; p.v = KVw.f + D; p.k_sn = (long long)L * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B; p.Lk = L;
   p.o = O.cols(0); p.attw = nullptr;
-  if (a->attw_audio || a->attw_video) {
-    QAT_REQUIRE(a->attw_audio && a->attw_video, "avq: pass both attention-weight outputs or neither");
+  if (attw_audio || attw_video) {
+    QAT_REQUIRE(attw_audio && attw_video, "avq: pass both attention-weight outputs or neither");
     // the two outputs are separate tensors: run the two directions as separate launches
     AttnP pa = p;
-    pa.nseq = B; pa.attw = a->attw_audio;
+    pa.nseq = B; pa.attw = attw_audio;
     QAT_TRY(attention(c, pa));
     AttnP pv = p;
-    pv.nseq = B; pv.attw = a->attw_video; pv.q = S.f + BT * 7 * D; pv.o = O.rows(BT).cols(0);
+    pv.nseq = B; pv.attw = attw_video; pv.q = S.f + BT * 7 * D; pv.o = O.rows(BT).cols(0);
     QAT_TRY(attention(c, pv));
   } else {
     QAT_TRY(attention(c, p));
@@ -247,9 +267,9 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
   QAT_TRY(act_alloc(c, Y, 2 * BT, D, true, false));
   {
     Epi e;
-    e.res = a->audio; e.ldr = D;
+    e.res = Xa.f; e.ldr = Xa.ld;
     QAT_TRY(gemm(c, k_out, O, BT, Wout, e, Y));
-    e.res = a->video;
+    e.res = Xv.f; e.ldr = Xv.ld;
     QAT_TRY(gemm(c, k_out, O.rows(BT), BT, Wout, e, Y.rows(BT)));
   }
   QAT_TRY(act_alloc(c, X1, 2 * BT, D, true, reads_planes(k_f1)));
@@ -264,16 +284,22 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
     e2.res = X1.f; e2.ldr = D;
     QAT_TRY(gemm(c, k_f2, Hh, 2 * BT, W2, e2, Y));
   }
-  QAT_TRY(ln(c, Y.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm2, act_of(a->out_audio, D), BT, D));
-  QAT_TRY(ln(c, Y.f + BT * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm2, act_of(a->out_video, D), BT, D));
+  QAT_TRY(ln(c, Y.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm2, out_a, BT, D));
+  QAT_TRY(ln(c, Y.f + BT * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm2, out_v, BT, D));
   return QAT_OK;
+}
+
+static int run_avq(const QatAvqArgs* a, Ctx& c) {
+  const int D = a->D;
+  return avq_core(a, a->B, a->T, a->L, c, act_of(a->audio, D), act_of(a->video, D), act_of(a->words, D), act_of(a->out_audio, D),
+                  act_of(a->out_video, D), a->attw_audio, a->attw_video);
 }
 
 // =================================================================================================
 // P1(patch) + S1  PatchSelecter
 // =================================================================================================
-static int run_patch(const QatPatchArgs* a, Ctx& c) {
-  const int B = a->B, T = a->T, P = a->P, D = a->D, H = a->H;
+static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const float* patch, Act Xaud, Act Xvid, Act out_a, Act out_v) {
+  const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && T >= 1 && P >= 1 && P <= 32 && D == H * 64, "patch_select: need P<=32 and D==H*64 (P=%d D=%d H=%d)", P, D, H);
   if (a->has_proj) QAT_TRY(check_w(a->proj, D, a->Cin, "patch.proj", c.prec));
   QAT_TRY(check_w(a->slf_in, 3 * D, D, "patch.slf_in", c.prec));
@@ -306,11 +332,10 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
     const bool q16 = kq == G_F16 && sel16 && Wco.h16 && P <= 16 && H <= 8 && Wsi.h16 && Wso.h16 && Wkv.h16;
     if (q16) QAT_TRY(act_alloc_h(c, Q2, BT, 2 * D));
     else QAT_TRY(act_alloc(c, Q2, BT, 2 * D, true, false));
-    Act Xv, Xa;
-    QAT_TRY(operand_of(c, a->video, BT, D, kq, Xv));
-    QAT_TRY(operand_of(c, a->audio, BT, D, kq, Xa));
-    QAT_TRY(gemm(c, kq, Xv, BT, Wq, Epi(), Q2.cols(0)));
-    QAT_TRY(gemm(c, kq, Xa, BT, Wq, Epi(), Q2.cols(D)));
+    QAT_TRY(ensure_operand(c, Xvid, BT, D, kq));
+    QAT_TRY(ensure_operand(c, Xaud, BT, D, kq));
+    QAT_TRY(gemm(c, kq, Xvid, BT, Wq, Epi(), Q2.cols(0)));
+    QAT_TRY(gemm(c, kq, Xaud, BT, Wq, Epi(), Q2.cols(D)));
   }
   GemmKind k_co = pick_kind(c, 2 * BT, D, D, false, Wco), k_m0 = pick_kind(c, 2 * BT, D / 2, D, false, Wm0);
   GemmKind k_m2 = pick_kind(c, 2 * BT, D, D / 2, false, Wm2);
@@ -328,7 +353,7 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
     const long long nf = (BT - f0 < chunk) ? BT - f0 : chunk;
     const long long rows = nf * P;
     c.release(mark);
-    const float* pin = a->patch + (size_t)f0 * P * Cin;
+    const float* pin = patch + (size_t)f0 * P * Cin;
     AttnP q;
     q.nseq = (int)nf; q.H = H; q.Lq = 2; q.Lk = P; q.scale = scale;
     q.q = Q2.f + (size_t)f0 * 2 * D; q.q_sn = 2 * D; q.q_si = D;
@@ -410,9 +435,15 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
   QAT_TRY(act_alloc(c, Mo, 2 * BT, D, true, false));
   QAT_TRY(gemm(c, k_m2, Hm, 2 * BT, Wm2, Epi(), Mo));
   // rows (bt,0) = video-related, (bt,1) = audio-related (:706); returned as [anorm(a), vnorm(v)] (:713-716)
-  QAT_TRY(ln(c, Mo.f + D, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->anorm, act_of(a->out_a, D), BT, D));
-  QAT_TRY(ln(c, Mo.f, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->vnorm, act_of(a->out_v, D), BT, D));
+  QAT_TRY(ln(c, Mo.f + D, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->anorm, out_a, BT, D));
+  QAT_TRY(ln(c, Mo.f, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->vnorm, out_v, BT, D));
   return QAT_OK;
+}
+
+static int run_patch(const QatPatchArgs* a, Ctx& c) {
+  QAT_REQUIRE(c.dry || (a->patch && a->audio && a->video && a->out_a && a->out_v), "patch_select: NULL tensor");
+  return patch_core(a, a->B, a->T, a->P, c, a->patch, act_of(a->audio, a->D), act_of(a->video, a->D), act_of(a->out_a, a->D),
+                    act_of(a->out_v, a->D));
 }
 
 // =================================================================================================
@@ -436,11 +467,12 @@ static int run_gauss(const QatGaussArgs* a, Ctx& c) {
 // =================================================================================================
 // M1-M4 (+LN)  TempMoE
 // =================================================================================================
-static int run_moe(const QatMoeArgs* a, Ctx& c) {
-  const int B = a->B, T = a->T, D = a->D, H = a->H, E = a->E, K = a->K;
+static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst, Act Xd, const float* sub_a, const float* sub_v, float* out_a,
+                    float* out_v) {
+  const int D = a->D, H = a->H, E = a->E, K = a->K;
   QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
   QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
-  QAT_REQUIRE((a->sub_a == nullptr) == (a->sub_v == nullptr), "temp_moe: sub_data needs both tensors or none");
+  QAT_REQUIRE((sub_a == nullptr) == (sub_v == nullptr), "temp_moe: sub_data needs both tensors or none");
   const int Ch = D / 2, KE = E * Ch + 64;
   QAT_TRY(check_w(a->attn_q, D, D, "moe.attn_q", c.prec));
   QAT_TRY(check_w(a->attn_kv, 2 * D, D, "moe.attn_kv", c.prec));
@@ -449,19 +481,20 @@ static int run_moe(const QatMoeArgs* a, Ctx& c) {
   QAT_TRY(check_w(a->w1_cat, E * Ch, D, "moe.w1_cat", c.prec));
   QAT_TRY(check_w(a->w2_ext, D, KE, "moe.w2_ext", c.prec));
   const long long BT = (long long)B * T;
-  const bool two = a->sub_a != nullptr;
-  QAT_REQUIRE(a->out_a && (!two || a->out_v), "temp_moe: output pointer missing");
+  const bool two = sub_a != nullptr;
+  QAT_REQUIRE(c.dry || (out_a && (!two || out_v)), "temp_moe: output pointer missing");
   const WView Wq = wview(a->attn_q), Wkv = wview(a->attn_kv), Wo = wview(a->attn_out), Wrg = wview(a->router_gauss);
   const WView W1 = wview(a->w1_cat), W2 = wview(a->w2_ext);
   const GemmKind k_kv = pick_kind(c, BT, 2 * D, D, false, Wkv), k_w1 = pick_kind(c, BT, E * Ch, D, false, W1);
 
   // temp_w = qst_attn(q = qst, kv = data)   (:562) -- the rank-critical chain: K/V at bf16x3 or fp32, rest fp32
-  Act Xd, KV, Q, Oq, TW, RG;
-  QAT_TRY(planes_of(c, a->data, BT, D, reads_planes(k_kv) || (!two && reads_planes(k_w1)), Xd));
+  Act KV, Q, Oq, TW, RG;
+  QAT_TRY(ensure_operand(c, Xd, BT, D, k_kv));
+  if (!two) QAT_TRY(ensure_operand(c, Xd, BT, D, k_w1));
   QAT_TRY(act_alloc(c, KV, BT, 2 * D, true, false));
   QAT_TRY(gemm(c, k_kv, Xd, BT, Wkv, Epi(), KV));
   QAT_TRY(act_alloc(c, Q, B, D, true, false));
-  QAT_TRY(gemm(c, G_SIMT, act_of(a->qst, D), B, Wq, Epi(), Q));
+  QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, Wq, Epi(), Q));
   QAT_TRY(act_alloc(c, Oq, B, D, true, false));
   AttnP p;
   p.nseq = B; p.H = H; p.Lq = 1; p.Lk = T; p.scale = 0.125f;
@@ -490,7 +523,7 @@ static int run_moe(const QatMoeArgs* a, Ctx& c) {
     Act Xe = Xd;
     if (two) {
       QAT_TRY(act_alloc(c, Xe, BT, D, !reads_planes(k_w1), reads_planes(k_w1)));
-      QAT_TRY(add_rows(c, a->data, D, br == 0 ? a->sub_a : a->sub_v, D, Xe, BT, D));     // :587,597
+      QAT_TRY(add_rows(c, Xd.f, Xd.ld, br == 0 ? sub_a : sub_v, D, Xe, BT, D));     // :587,597
     }
     // hidden = relu(W1_e x + b1_e) for every expert: [BT, E*Ch]
     Act Hd, Hb, Ob;
@@ -519,17 +552,23 @@ static int run_moe(const QatMoeArgs* a, Ctx& c) {
       QAT_TRY(gemm(c, G_SIMT, Hb, B, w2, e, Ob));
     }
     const QatLayerNormW& nw = (br == 0) ? a->norm_a : a->norm_v;
-    QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, nw, act_of(br == 0 ? a->out_a : a->out_v, D), B, D));
+    QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, nw, act_of(br == 0 ? out_a : out_v, D), B, D));
     c.release(mark);
   }
   return QAT_OK;
 }
 
+static int run_moe(const QatMoeArgs* a, Ctx& c) {
+  QAT_REQUIRE(c.dry || (a->qst && a->data), "temp_moe: NULL tensor");
+  return moe_core(a, a->B, a->T, c, a->qst, act_of(a->data, a->D), a->sub_a, a->sub_v, a->out_a, a->out_v);
+}
+
 // =================================================================================================
 // G1 (+H1)  QstGrounding on a length-2 sequence, optional head
 // =================================================================================================
-static int run_ground(const QatGroundArgs* a, Ctx& c) {
-  const int B = a->B, D = a->D, H = a->H;
+static int ground_core(const QatGroundArgs* a, int B, Ctx& c, const float* qst, const float* d0, const float* d1, float* out, bool with_head,
+                       float* logits) {
+  const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && D == H * 64, "qst_grounding: need D==H*64");
   QAT_TRY(check_w(a->attn_q, D, D, "ground.attn_q", c.prec));
   QAT_TRY(check_w(a->attn_kv, 2 * D, D, "ground.attn_kv", c.prec));
@@ -543,11 +582,11 @@ static int run_ground(const QatGroundArgs* a, Ctx& c) {
     kv0.ld = 4 * D;
     kv1.ld = 4 * D;
     kv1.f += 2 * D;
-    QAT_TRY(gemm(c, G_SIMT, act_of(a->d0, D), B, wview(a->attn_kv), Epi(), kv0));
-    QAT_TRY(gemm(c, G_SIMT, act_of(a->d1, D), B, wview(a->attn_kv), Epi(), kv1));
+    QAT_TRY(gemm(c, G_SIMT, act_of(d0, D), B, wview(a->attn_kv), Epi(), kv0));
+    QAT_TRY(gemm(c, G_SIMT, act_of(d1, D), B, wview(a->attn_kv), Epi(), kv1));
   }
   QAT_TRY(act_alloc(c, Q, B, D, true, false));
-  QAT_TRY(gemm(c, G_SIMT, act_of(a->qst, D), B, wview(a->attn_q), Epi(), Q));
+  QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, wview(a->attn_q), Epi(), Q));
   QAT_TRY(act_alloc(c, O, B, D, true, false));
   AttnP p;
   p.nseq = B; p.H = H; p.Lq = 1; p.Lk = 2; p.scale = 0.125f;
@@ -566,19 +605,80 @@ static int run_ground(const QatGroundArgs* a, Ctx& c) {
   QAT_TRY(act_alloc(c, Mo, B, D, true, false));
   QAT_TRY(gemm(c, G_SIMT, Hm, B, wview(a->mlp2), Epi(), Mo));
   // feat = mean_seq(data) + mlp(attn)  -> LN   (:344-346)
-  QAT_TRY(ln(c, a->d0, D, a->d1, D, Mo.f, D, 0.5f, a->norm, act_of(a->out, D), B, D));
-  if (a->has_head) {
-    QAT_REQUIRE(a->logits && a->head.w && a->head.k == D, "qst_grounding: head weights/logits missing");
+  QAT_TRY(ln(c, d0, D, d1, D, Mo.f, D, 0.5f, a->norm, act_of(out, D), B, D));
+  if (with_head) {
+    QAT_REQUIRE((c.dry || logits) && a->head.w && a->head.k == D, "qst_grounding: head weights/logits missing");
     // head(relu(fusion)) net.py:141-142: relu folded into a tiny elementwise pass on the LN output
     Act R;
     QAT_TRY(act_alloc(c, R, B, D, true, false));
     if (!c.dry) {
-      QAT_TRY(relu_rows(c, a->out, R.f, (long long)B * D));
+      QAT_TRY(relu_rows(c, out, R.f, (long long)B * D));
     }
-    QAT_TRY(gemm(c, G_SIMT, R, B, wview(a->head), Epi(), act_of(a->logits, a->head.n)));
+    QAT_TRY(gemm(c, G_SIMT, R, B, wview(a->head), Epi(), act_of(logits, a->head.n)));
   }
   return QAT_OK;
 }
+
+static int run_ground(const QatGroundArgs* a, Ctx& c) {
+  QAT_REQUIRE(c.dry || (a->qst && a->d0 && a->d1 && a->out), "qst_grounding: NULL tensor");
+  return ground_core(a, a->B, c, a->qst, a->d0, a->d1, a->out, a->has_head != 0, a->logits);
+}
+
+// =================================================================================================
+// The whole hot path in ONE call: net.py:120-142.  Intermediates live in the workspace and travel between the blocks
+// with the storage planes their consumers read (no conversion passes at module boundaries, one launch sequence).
+// =================================================================================================
+static int run_forward(const QatForwardArgs* a, Ctx& c) {
+  const int B = a->B, T = a->T, L = a->L, P = a->P, D = a->avq.D;
+  QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && P >= 1, "forward: bad shape");
+  QAT_REQUIRE(c.dry || (a->quest && a->words && a->audio && a->video && a->patch && a->logits), "forward: NULL tensor");
+  QAT_REQUIRE(a->patch_sel.D == D && a->at.D == D && a->vt.D == D && a->ground.D == D && a->audio_proj.n == D && a->video_proj.n == D &&
+                  a->words_proj.n == D && a->quest_proj.n == D, "forward: every block must share d_model=%d", D);
+  QAT_REQUIRE(a->patch_sel.has_proj, "forward: patch_proj weights missing (patch_sel.has_proj)");
+  const long long BT = (long long)B * T, BL = (long long)B * L;
+  const bool tc = c.prec == QAT_PREC_BF16;
+  // projected inputs: fp32 (residuals) + bf16 hi/lo planes (the AVQ in-projections read those in bf16 mode)
+  Act A0, V0, W0, Q0, Ax, Vx, Ap, Vp;
+  QAT_TRY(act_alloc(c, A0, BT, D, true, tc));
+  QAT_TRY(act_alloc(c, V0, BT, D, true, tc));
+  QAT_TRY(act_alloc(c, W0, BL, D, true, tc));
+  QAT_TRY(act_alloc(c, Q0, B, D, true, false));
+  QAT_TRY(linear_core(c, a->audio_proj, act_of(a->audio, a->audio_proj.k), BT, 0, A0));
+  QAT_TRY(linear_core(c, a->video_proj, act_of(a->video, a->video_proj.k), BT, 0, V0));
+  QAT_TRY(linear_core(c, a->words_proj, act_of(a->words, a->words_proj.k), BL, 0, W0));
+  QAT_TRY(linear_core(c, a->quest_proj, act_of(a->quest, a->quest_proj.k), B, 0, Q0));
+  // AVQ outputs: fp32 + bf16 planes (TempMoE K/V and expert GEMMs) + fp16 plane (PatchSelecter query projection)
+  QAT_TRY(act_alloc(c, Ax, BT, D, true, tc));
+  QAT_TRY(act_alloc(c, Vx, BT, D, true, tc));
+  if (tc) {
+    Act h;
+    QAT_TRY(act_alloc_h(c, h, BT, D)); Ax.h = h.h;
+    QAT_TRY(act_alloc_h(c, h, BT, D)); Vx.h = h.h;
+  }
+  QAT_TRY(act_alloc(c, Ap, BT, D, true, false));
+  QAT_TRY(act_alloc(c, Vp, BT, D, true, false));
+  float* glob = reinterpret_cast<float*>(c.alloc((size_t)5 * B * D * 4));     // a_global | ap_global | vp_global | fusion1 | fusion2
+  if (!c.dry && !glob) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+  float* a_global = glob;
+  float* ap_global = glob + (size_t)B * D;
+  float* vp_global = glob + (size_t)2 * B * D;
+  float* fusion1 = glob + (size_t)3 * B * D;
+  float* fusion2 = glob + (size_t)4 * B * D;
+  const size_t mark = c.mark();
+  QAT_TRY(avq_core(&a->avq, B, T, L, c, A0, V0, W0, Ax, Vx, nullptr, nullptr));
+  c.release(mark);
+  QAT_TRY(patch_core(&a->patch_sel, B, T, P, c, a->patch, Ax, Vx, Ap, Vp));
+  c.release(mark);
+  QAT_TRY(moe_core(&a->at, B, T, c, Q0.f, Ax, nullptr, nullptr, a_global, nullptr));
+  c.release(mark);
+  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Ap.f, Vp.f, ap_global, vp_global));
+  c.release(mark);
+  QAT_TRY(ground_core(&a->ground, B, c, Q0.f, ap_global, vp_global, fusion1, false, nullptr));
+  c.release(mark);
+  QAT_TRY(ground_core(&a->ground, B, c, Q0.f, fusion1, a_global, fusion2, true, a->logits));
+  return QAT_OK;
+}
+
 
 // =================================================================================================
 // N1  CLIP text tower (frozen), encoders.py:30-37 / clip_base.py:186-254
@@ -782,6 +882,8 @@ int qat_tome_chain(const QatTomeChainArgs* a) { return dispatch(a, a ? a->stream
 
 int qat_clip_text_fwd(const QatClipTextArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_clip_text); }
 
+int qat_forward_fwd(const QatForwardArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_forward); }
+
 int qat_tome_clamp_r(int t, int r, int class_token) { return tome_clamp_r(t, r, class_token); }
 
 int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token) {
@@ -811,6 +913,7 @@ size_t qat_workspace_bytes(int op, const void* args) {
     case QAT_OP_MOE: return dry_bytes(reinterpret_cast<const QatMoeArgs*>(args), reinterpret_cast<const QatMoeArgs*>(args)->prec, run_moe);
     case QAT_OP_GROUND: return dry_bytes(reinterpret_cast<const QatGroundArgs*>(args), reinterpret_cast<const QatGroundArgs*>(args)->prec, run_ground);
     case QAT_OP_CLIP_TEXT: return dry_bytes(reinterpret_cast<const QatClipTextArgs*>(args), reinterpret_cast<const QatClipTextArgs*>(args)->prec, run_clip_text);
+    case QAT_OP_FORWARD: return dry_bytes(reinterpret_cast<const QatForwardArgs*>(args), reinterpret_cast<const QatForwardArgs*>(args)->prec, run_forward);
     case QAT_OP_TOME_MATCH: return 256;
     case QAT_OP_TOME_MERGE: return 256;
     case QAT_OP_TOME_CHAIN: return dry_bytes(reinterpret_cast<const QatTomeChainArgs*>(args), QAT_PREC_FP32, run_tome_chain);

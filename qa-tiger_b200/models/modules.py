@@ -126,6 +126,13 @@ class AVQCrossAttn(_QatModule):
             ffn2=cabi.Lin(self.linear2.weight, self.linear2.bias, prec),
             norm1=cabi.LN(self.norm1), norm2=cabi.LN(self.norm2))
 
+    def fill_weights(self, a, prec: int):
+        """weights + hyper-parameters of this block into a QatAvqArgs (its own call, or the one embedded in QatForwardArgs)"""
+        w = self._prepared(prec)
+        a.D, a.H = self.d_model, self.nhead
+        a.in_src, a.in_words, a.out_cat, a.ffn1, a.ffn2 = (w[k].c for k in ("in_src", "in_words", "out_cat", "ffn1", "ffn2"))
+        a.norm1, a.norm2 = w["norm1"].c, w["norm2"].c
+
     def forward(self, src_q: Tensor, src_v: Tensor, query: Tensor, visualize: bool = False):
         self._guard()
         prec = self._prec()
@@ -141,10 +148,9 @@ class AVQCrossAttn(_QatModule):
             aw = torch.zeros(B, T, L, device=src_q.device, dtype=torch.float32)
             vw = torch.zeros(B, T, L, device=src_q.device, dtype=torch.float32)
         a = cabi.AvqArgs()
-        a.B, a.T, a.L, a.D, a.H, a.prec = B, T, L, D, self.nhead, prec
+        a.B, a.T, a.L, a.prec = B, T, L, prec
+        self.fill_weights(a, prec)
         a.audio, a.video, a.words = src_q.data_ptr(), src_v.data_ptr(), query.data_ptr()
-        a.in_src, a.in_words, a.out_cat, a.ffn1, a.ffn2 = (w[k].c for k in ("in_src", "in_words", "out_cat", "ffn1", "ffn2"))
-        a.norm1, a.norm2 = w["norm1"].c, w["norm2"].c
         a.out_audio, a.out_video = out_a.data_ptr(), out_v.data_ptr()
         a.attw_audio, a.attw_video = cabi.ptr(aw), cabi.ptr(vw)
         cabi.run(cabi.OP_AVQ, "qat_avq_cross_attn_fwd", a, src_q.device)
@@ -178,6 +184,22 @@ class QstGrounding(_QatModule):
             mlp2=cabi.Lin(self.mlp[2].weight, self.mlp[2].bias, prec),
             norm=cabi.LN(self.norm))
 
+    def fill_weights(self, a, prec: int, head: Optional[nn.Linear] = None):
+        """weights into a QatGroundArgs; returns the object that keeps the head's prepared weights alive (or None)"""
+        w = self._prepared(prec)
+        a.D, a.H = self.d_model, self.nhead
+        a.attn_q, a.attn_kv, a.attn_out, a.mlp0, a.mlp2 = (w[k].c for k in ("attn_q", "attn_kv", "attn_out", "mlp0", "mlp2"))
+        a.norm = w["norm"].c
+        if head is None:
+            return None
+        key = (head.weight.data_ptr(), head.weight._version, head.bias.data_ptr(), head.bias._version)
+        cached = self.__dict__.get("_head_cache")
+        if cached is None or cached[0] != key:
+            cached = (key, cabi.Lin(head.weight, head.bias, cabi.PREC_FP32))
+            self.__dict__["_head_cache"] = cached
+        a.has_head, a.head = 1, cached[1].c
+        return cached[1]
+
     def forward(self, qst: Tensor, data: Union[Tensor, List[Tensor]], head: Optional[nn.Linear] = None):
         """`head` (not in the reference signature) fuses net.py:141-142 `head(relu(.))` into the same call
         and returns (feat, logits)."""
@@ -196,16 +218,14 @@ class QstGrounding(_QatModule):
         cabi.require_cuda_f32(d0, "data[0]", (B, D))
         out = torch.empty(B, D, device=qst.device, dtype=torch.float32)
         a = cabi.GroundArgs()
-        a.B, a.D, a.H, a.prec = B, D, self.nhead, prec
+        a.B, a.prec = B, prec
+        hold = self.fill_weights(a, prec, head)
         a.qst, a.d0, a.d1 = qst.data_ptr(), d0.data_ptr(), d1.data_ptr()
-        a.attn_q, a.attn_kv, a.attn_out, a.mlp0, a.mlp2 = (w[k].c for k in ("attn_q", "attn_kv", "attn_out", "mlp0", "mlp2"))
-        a.norm, a.out = w["norm"].c, out.data_ptr()
+        a.out = out.data_ptr()
         logits = None
-        hold = None
         if head is not None:
-            hold = cabi.Lin(head.weight, head.bias, cabi.PREC_FP32)
             logits = torch.empty(B, head.weight.shape[0], device=qst.device, dtype=torch.float32)
-            a.has_head, a.head, a.logits = 1, hold.c, logits.data_ptr()
+            a.logits = logits.data_ptr()
         cabi.run(cabi.OP_GROUND, "qat_qst_grounding_head_fwd", a, qst.device)
         return (out, logits) if head is not None else out
 
@@ -265,10 +285,26 @@ class TempMoE(_QatModule):
             d["norm_a"] = d["norm_v"] = cabi.LN(self.norm)
         return d
 
+    def fill_weights(self, a, prec: int):
+        w = self._prepared(prec)
+        a.D, a.H, a.E, a.K, a.sigma = self.d_model, self.nhead, self.n_experts, self.topK, float(self.sigma)
+        a.attn_q, a.attn_kv, a.attn_out, a.router_gauss, a.w1_cat, a.w2_ext = (
+            w[k].c for k in ("attn_q", "attn_kv", "attn_out", "router_gauss", "w1_cat", "w2_ext"))
+        a.norm_a, a.norm_v = w["norm_a"].c, w["norm_v"].c
+
+    def attach_aux(self, a, B: int, T: int, dev):
+        """optional rank / gate / mask outputs (`keep_aux`): allocate them and point the args at them"""
+        if not self.keep_aux:
+            return None
+        aux = (torch.empty(B, self.topK, device=dev, dtype=torch.int64),
+               torch.empty(B, self.topK, device=dev, dtype=torch.float32),
+               torch.empty(B, self.topK, T, device=dev, dtype=torch.float32))
+        a.topk_inds, a.topk_probs, a.gauss_weight = (t.data_ptr() for t in aux)
+        return aux
+
     def forward(self, qst: Tensor, data: Tensor, sub_data: Optional[List[Tensor]] = None):
         self._guard()
         prec = self._prec()
-        w = self._prepared(prec)
         B, T, D = data.shape
         qst = qst.reshape(B, D)
         cabi.require_cuda_f32(qst, "qst", (B, D))
@@ -277,23 +313,16 @@ class TempMoE(_QatModule):
         out_a = torch.empty(B, 1, D, device=dev, dtype=torch.float32)
         out_v = None
         a = cabi.MoeArgs()
-        a.B, a.T, a.D, a.H, a.E, a.K, a.prec, a.sigma = B, T, D, self.nhead, self.n_experts, self.topK, prec, float(self.sigma)
+        a.B, a.T, a.prec = B, T, prec
+        self.fill_weights(a, prec)
         a.qst, a.data = qst.data_ptr(), data.data_ptr()
         if sub_data is not None:
             cabi.require_cuda_f32(sub_data[0], "sub_data[0]", (B, T, D))
             cabi.require_cuda_f32(sub_data[1], "sub_data[1]", (B, T, D))
             out_v = torch.empty(B, 1, D, device=dev, dtype=torch.float32)
             a.sub_a, a.sub_v = sub_data[0].data_ptr(), sub_data[1].data_ptr()
-        a.attn_q, a.attn_kv, a.attn_out, a.router_gauss, a.w1_cat, a.w2_ext = (
-            w[k].c for k in ("attn_q", "attn_kv", "attn_out", "router_gauss", "w1_cat", "w2_ext"))
-        a.norm_a, a.norm_v = w["norm_a"].c, w["norm_v"].c
         a.out_a, a.out_v = out_a.data_ptr(), cabi.ptr(out_v)
-        aux = None
-        if self.keep_aux:
-            aux = (torch.empty(B, self.topK, device=dev, dtype=torch.int64),
-                   torch.empty(B, self.topK, device=dev, dtype=torch.float32),
-                   torch.empty(B, self.topK, T, device=dev, dtype=torch.float32))
-            a.topk_inds, a.topk_probs, a.gauss_weight = (t.data_ptr() for t in aux)
+        aux = self.attach_aux(a, B, T, dev)
         cabi.run(cabi.OP_MOE, "qat_temp_moe_fwd", a, dev)
         self.last_aux = aux
         if sub_data is not None:
@@ -362,10 +391,18 @@ class PatchSelecter(_QatModule):
             mlp2=cabi.Lin(self.mlp[2].weight, self.mlp[2].bias, prec, f16=True),
             anorm=cabi.LN(self.anorm), vnorm=cabi.LN(self.vnorm))
 
+    def fill_weights(self, a, prec: int, proj: Optional[Projection], Cin: int):
+        w = self._prepared(prec)
+        a.D, a.H, a.Cin, a.chunk_frames = self.d_model, self.nhead, Cin, int(self.chunk_frames)
+        if proj is not None:
+            a.has_proj, a.proj = 1, proj._prepared(prec).c
+        for k in ("slf_in", "slf_out", "crs_q", "crs_kv", "crs_out", "mlp0", "mlp2"):
+            setattr(a, k, w[k].c)
+        a.anorm, a.vnorm = w["anorm"].c, w["vnorm"].c
+
     def forward(self, patch: Tensor, audio: Tensor, video: Tensor, proj: Optional[Projection] = None) -> List[Tensor]:
         self._guard()
         prec = self._prec()
-        w = self._prepared(prec)
         B, T, P, Cin = patch.shape
         D = self.d_model
         cabi.require_cuda_f32(patch, "patch")
@@ -376,15 +413,9 @@ class PatchSelecter(_QatModule):
         out_a = torch.empty(B, T, D, device=patch.device, dtype=torch.float32)
         out_v = torch.empty(B, T, D, device=patch.device, dtype=torch.float32)
         a = cabi.PatchArgs()
-        a.B, a.T, a.P, a.D, a.H, a.Cin, a.prec = B, T, P, D, self.nhead, Cin, prec
+        a.B, a.T, a.P, a.prec = B, T, P, prec
+        self.fill_weights(a, prec, proj, Cin)
         a.patch, a.audio, a.video = patch.data_ptr(), audio.data_ptr(), video.data_ptr()
-        pw = None
-        if proj is not None:
-            pw = proj._prepared(prec)
-            a.has_proj, a.proj = 1, pw.c
-        for k in ("slf_in", "slf_out", "crs_q", "crs_kv", "crs_out", "mlp0", "mlp2"):
-            setattr(a, k, w[k].c)
-        a.anorm, a.vnorm = w["anorm"].c, w["vnorm"].c
-        a.out_a, a.out_v, a.chunk_frames = out_a.data_ptr(), out_v.data_ptr(), int(self.chunk_frames)
+        a.out_a, a.out_v = out_a.data_ptr(), out_v.data_ptr()
         cabi.run(cabi.OP_PATCH, "qat_patch_select_fwd", a, patch.device)
         return [out_a, out_v]

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 from torch import Tensor
 
+from .. import _cabi as cabi
 from .encoders import CLIP_TEncoder
 from .modules import AVQCrossAttn, PatchSelecter, Projection, QstGrounding, TempMoE
 
@@ -72,8 +73,48 @@ class QA_TIGER(nn.Module):
             quest = quest.squeeze(1)
         return quest, words, audio, video, patch
 
+    # `fused = True`: the whole hot path is ONE C-ABI call (qat_forward_fwd): no per-module marshalling, intermediates in
+    # the workspace, activations handed between blocks in the storage planes the next block reads.  `fused = False` goes
+    # block by block through the drop-in modules (identical arithmetic; what a partially switched reference would do).
+    fused = True
+
+    def _forward_fused(self, quest: Tensor, words: Tensor, audio: Tensor, video: Tensor, patch: Tensor) -> Tensor:
+        blocks = (self.audio_proj, self.video_proj, self.words_proj, self.quest_proj, self.patch_proj, self.crs_attn,
+                  self.patch_selecter, self.at_aggregator, self.vt_aggregator, self.quest_grounding)
+        for m in blocks:
+            m._guard()
+        prec = self.crs_attn._prec()
+        if any(m._prec() != prec for m in blocks):
+            raise RuntimeError("QA_TIGER(fused=True): every block must run in the same precision mode (use set_precision)")
+        B, T, P = patch.shape[0], patch.shape[1], patch.shape[2]
+        L = words.shape[1]
+        cabi.require_cuda_f32(quest, "quest", (B, self.quest_proj.proj.in_features))
+        cabi.require_cuda_f32(words, "words", (B, L, self.words_proj.proj.in_features))
+        cabi.require_cuda_f32(audio, "audio", (B, T, self.audio_proj.proj.in_features))
+        cabi.require_cuda_f32(video, "video", (B, T, self.video_proj.proj.in_features))
+        cabi.require_cuda_f32(patch, "patch", (B, T, P, self.patch_proj.proj.in_features))
+        dev = patch.device
+        a = cabi.ForwardArgs()
+        a.B, a.T, a.L, a.P, a.prec = B, T, L, P, prec
+        a.quest, a.words, a.audio, a.video, a.patch = (t.data_ptr() for t in (quest, words, audio, video, patch))
+        a.audio_proj, a.video_proj, a.words_proj, a.quest_proj = (m._prepared(prec).c for m in blocks[:4])
+        self.crs_attn.fill_weights(a.avq, prec)
+        self.patch_selecter.fill_weights(a.patch_sel, prec, self.patch_proj, patch.shape[3])
+        self.at_aggregator.fill_weights(a.at, prec)
+        self.vt_aggregator.fill_weights(a.vt, prec)
+        hold = self.quest_grounding.fill_weights(a.ground, prec, self.head)   # noqa: F841 -- keeps the head weights alive
+        aux_at = self.at_aggregator.attach_aux(a.at, B, T, dev)
+        aux_vt = self.vt_aggregator.attach_aux(a.vt, B, T, dev)
+        logits = torch.empty(B, self.head.out_features, device=dev, dtype=torch.float32)
+        a.logits = logits.data_ptr()
+        cabi.run(cabi.OP_FORWARD, "qat_forward_fwd", a, dev)
+        self.at_aggregator.last_aux, self.vt_aggregator.last_aux = aux_at, aux_vt
+        return logits
+
     def forward_features(self, quest: Tensor, words: Tensor, audio: Tensor, video: Tensor, patch: Tensor) -> Tensor:
         """The hot path proper (net.py:120-142) on text-tower outputs quest [B,768], words [B,77,768]."""
+        if self.fused and patch.is_cuda:
+            return self._forward_fused(quest.contiguous(), words.contiguous(), audio, video, patch)
         audio = self.audio_proj(audio)
         video = self.video_proj(video)
         words = self.words_proj(words.contiguous())

@@ -37,7 +37,8 @@ def test_struct_layout_matches_c(tmp_path):
              "QatPatchArgs": _cabi.PatchArgs, "QatGaussArgs": _cabi.GaussArgs, "QatMoeArgs": _cabi.MoeArgs,
              "QatGroundArgs": _cabi.GroundArgs, "QatTomeMatchArgs": _cabi.TomeMatchArgs,
              "QatTomeMergeArgs": _cabi.TomeMergeArgs, "QatTomeChainArgs": _cabi.TomeChainArgs,
-             "QatClipLayerW": _cabi.ClipLayerW, "QatClipTextArgs": _cabi.ClipTextArgs, "QatAttnArgs": _cabi.AttnArgs}
+             "QatClipLayerW": _cabi.ClipLayerW, "QatClipTextArgs": _cabi.ClipTextArgs, "QatAttnArgs": _cabi.AttnArgs,
+             "QatForwardArgs": _cabi.ForwardArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "qat.h"', 'int main(void){']
     for cname, ct in pairs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

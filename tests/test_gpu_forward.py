@@ -53,6 +53,22 @@ def test_forward_with_native_text_tower(name):
     assert out.argmax(1).cpu().tolist() == g["argmax"].tolist()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_fused_call_matches_block_by_block(prec):
+    """qat_forward_fwd (one C-ABI call) and the drop-in modules called one by one run the same arithmetic; in bf16 mode
+    the fused path hands planes across block boundaries instead of re-deriving them from fp32 (identical values)."""
+    sd = synth.make_state_dict(713, num_experts=7)
+    model = build_model(sd, 7, 7, prec)
+    batch = synth.make_batch(5, 6, 60)
+    data = {k: v.to(dev()) for k, v in batch.items()}
+    with torch.no_grad():
+        model.fused = True
+        fused = model(data)["out"]
+        model.fused = False
+        blocks = model(data)["out"]
+    assert torch.equal(fused, blocks) or relerr(fused, blocks) < 1e-6
+
+
 def test_batch_composition_is_part_of_the_function():
     """logits depend on the local batch; DP sharding must therefore be defined on local batches."""
     sd = synth.make_state_dict(713, num_experts=7)
