@@ -109,6 +109,15 @@ def test_text_tower_matches_oracle():
     with torch.no_grad():
         q2, w2 = model.quest_encoder(rep)
     assert relerr(q2[2], q[0]) < 1e-5 and relerr(w2[4], w[1]) < 1e-5
+    # cross-call memo: second call sees only cached rows (and one new question), results identical to the direct path
+    model.quest_encoder.memo = True
+    with torch.no_grad():
+        q3a, w3a = model.quest_encoder(rep)
+        q3b, w3b = model.quest_encoder(torch.cat([rep[:3], batch["quest"][3:4].to(dev())]))
+    assert relerr(q3a, q2) < 1e-6 and relerr(w3a, w2) < 1e-6
+    assert relerr(q3b[:3], q2[:3]) < 1e-6 and relerr(q3b[3], q[3]) < 1e-5 and relerr(w3b[3], w[3]) < 1e-5
+    assert len(model.quest_encoder._memo_state["slots"]) == 4
+    model.quest_encoder.memo = False
 
 
 def test_state_dict_is_reference_compatible():
