@@ -6,6 +6,7 @@
 #include "gauss.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_attn.cuh"
 #include "qat_common.cuh"
 #include "rowops.cuh"
 #include "tome.cuh"
@@ -368,13 +369,19 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
       } else {
         QAT_TRY(add_rows(c, pin, D, nullptr, 0, Pp, rows, D));
       }
-      QAT_TRY(act_alloc_h(c, QKV, rows, 3 * D));
-      QAT_TRY(gemm(c, G_F16, Pp, rows, Wsi, Epi(), QKV));
       QAT_TRY(act_alloc_h(c, Oa, rows, D));
-      AttnHP hp;
-      hp.q = QKV.h; hp.kv = QKV.h + D; hp.ldq = 3 * D; hp.ldkv = 3 * D;
-      hp.o = Oa.h; hp.ldo = D; hp.nseq = (int)nf; hp.H = H; hp.Lq = P; hp.Lk = P; hp.scale = scale;
-      QAT_TRY(attention_small_f16(c, hp));
+      const char* nofuse = getenv("QAT_PATCH_NO_FUSED_ATTN");      // A/B switch: in-proj GEMM + separate attention kernel
+      if (Wsi.bias && (128 / P) * P <= tc::GA_QKV_ROWS && !(nofuse && nofuse[0] == '1')) {
+        // in-projection and the 14-token self-attention in one kernel: [q | k | v] never reaches HBM
+        QAT_TRY(gemm_attn_f16(c, Pp.h, Pp.ld, (int)nf, P, H, D, Wsi.h16, Wsi.bias, scale, Oa.h, D));
+      } else {
+        QAT_TRY(act_alloc_h(c, QKV, rows, 3 * D));
+        QAT_TRY(gemm(c, G_F16, Pp, rows, Wsi, Epi(), QKV));
+        AttnHP hp;
+        hp.q = QKV.h; hp.kv = QKV.h + D; hp.ldq = 3 * D; hp.ldkv = 3 * D;
+        hp.o = Oa.h; hp.ldo = D; hp.nseq = (int)nf; hp.H = H; hp.Lq = P; hp.Lk = P; hp.scale = scale;
+        QAT_TRY(attention_small_f16(c, hp));
+      }
       // p' = p + slf_attn(p)   (:688, no LayerNorm)
       QAT_TRY(act_alloc_h(c, P2, rows, D));
       {
