@@ -55,6 +55,7 @@ class ClockSampler:
     def __init__(self, index: int):
         self.index, self.samples, self.reasons, self.stop_flag, self.th, self.err = index, [], set(), False, None, None
         self.max_mhz = None
+        self.armed = False        # NVML is initialised ahead of time (it takes tens of ms); samples count only while armed
 
     def _run(self):
         try:
@@ -67,12 +68,13 @@ class ClockSampler:
             names = {nv.nvmlClocksEventReasonHwSlowdown: "hw_slowdown", nv.nvmlClocksEventReasonHwThermalSlowdown: "hw_thermal_slowdown",
                      nv.nvmlClocksEventReasonSwThermalSlowdown: "sw_thermal_slowdown", nv.nvmlClocksEventReasonSwPowerCap: "sw_power_cap"}
             while not self.stop_flag:
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for bit, nm in names.items():
-                    if r & bit:
-                        self.reasons.add(nm)
-                time.sleep(0.01)
+                if self.armed:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for bit, nm in names.items():
+                        if r & bit:
+                            self.reasons.add(nm)
+                time.sleep(0.002)
         except Exception as e:   # noqa: BLE001
             self.err = repr(e)
 
@@ -226,21 +228,23 @@ def run_ours(args):
             else:
                 hot()
 
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
         for _ in range(args.warmup):
             step()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sampler.armed = True
         e0.record()
         for _ in range(args.steps):
             step()
         e1.record()
         torch.cuda.synchronize()
+        sampler.armed = False
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
@@ -475,8 +479,8 @@ def run_ours(args):
             for k, v in json.load(open(tpath)).items():
                 if k in rooflines:
                     rooflines[k]["traffic"] = v
-        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v10.txt:
-        # the bf16x3 tcgen05 GEMM, 29 % of the step; the f16 kind is next at 23 %), at its largest shape; the other GEMM
+        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v13.txt:
+        # the bf16x3 tcgen05 GEMM, 30 % of the step; the f16 kind and the fused in-proj + attention kernel follow at 13 % each), at its largest shape; the other GEMM
         # kinds, the HBM-class Gaussian-expert kernel north_star names and the ToMe chain ride along in rooflines_all
         key = "gemm_bf16x3_avq_in_src"
         line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "traffic")}
