@@ -44,7 +44,15 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--hot-only", action="store_true", help="profiling aid: time only the hot path (no e2e / rooflines / cpu legs)")
-    return ap.parse_args()
+    ap.add_argument("--stress", action="store_true",
+                    help="BASELINE configs[4] shape instead of configs[1]: T=120, E=K=14, 128 questions per GPU (combine with --hot-only)")
+    a = ap.parse_args()
+    if a.stress:
+        global T, E, K_TOP
+        T, E, K_TOP = 120, 14, 14
+        if a.batch == 256:
+            a.batch = 128
+    return a
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -254,7 +262,8 @@ def run_ours(args):
         if args.hot_only:
             if rank == 0:
                 print(json.dumps({"metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "ms_per_step": ms / args.steps,
-                                  "launches_per_step": launches_per_step, "hot_only": True, "cuda_graph": graph is not None}))
+                                  "launches_per_step": launches_per_step, "hot_only": True, "cuda_graph": graph is not None,
+                                  "shape": {"per_gpu_batch": B, "T": T, "E": E, "K": K_TOP, "P": P}, "n_gpus": world}))
             return
         # ---- e2e: public API from pinned host memory, text tower included ---------------------------
         # Every step: H2D of THAT step's batch (pinned -> device, on a copy stream, double-buffered so the copy of
