@@ -1,6 +1,6 @@
 """Frozen CLIP text tower (mirror of /root/reference/src/models/encoders.py:7-37 and the text half of
 src/models/base/clip_base.py:186-254,300-460).  BASELINE.json's north_star keeps it PyTorch (the default
-`compute = "fp32"`); SURVEY 8f-N1 ranks it first among the "next" rows because it is 70 % of the forward's FLOPs,
+`compute = "fp32"`; the default `"auto"` picks the native path below for CUDA inputs); SURVEY 8f-N1 ranks it first among the "next" rows because it is 70 % of the forward's FLOPs,
 so `compute = "native"` runs it through libqat_b200 (`qat_clip_text_fwd`: one C-ABI call, bf16 hi+lo x3 tcgen05
 GEMMs, fp16 hi/lo mma.sync causal attention -- fp32-faithful, it feeds the router).  Parameter names match the reference (`transformer.resblocks.N.{attn,ln_1,mlp.c_fc,
 mlp.c_proj,ln_2}`, `token_embedding`, `positional_embedding`, `ln_final`, `text_projection`,
@@ -117,8 +117,9 @@ class CLIP_TEncoder(nn.Module):
         # 'native' the whole tower in ONE C-ABI call (qat_clip_text_fwd; `native_precision` = 'bf16' -> bf16x3 tensor-core
         #          GEMMs, 'fp32' -> fp32 FFMA), no per-op CPU launch cost
         # 'tf32' / 'bf16' torch reduced precision: measured to BREAK the gate (1.1e-2 at B=256, a router rank flips)
-        self.compute = "fp32"
-        self.native_precision = "bf16"
+        # 'auto'   (default) 'native' for CUDA inputs, 'fp32' (torch) for CPU inputs
+        self.compute = "auto"
+        self.native_precision = "bf16"   # follows QA_TIGER.set_precision
         self.dedup = False   # run the tower on unique token rows only (MUSIC-AVQA test: 33 unique questions)
         self.memo = False    # additionally remember encoded questions ACROSS calls (SURVEY 8f-N1 "memoise by token row"):
                              # keyed by a 128-bit row hash kept on the host, outputs cached on the device; one small D2H
@@ -188,7 +189,7 @@ class CLIP_TEncoder(nn.Module):
         return quest, words
 
     def _tower(self, text: torch.Tensor):
-        if self.compute == "native":
+        if self.compute == "native" or (self.compute == "auto" and text.is_cuda):
             return self._tower_native(text)
         use_tc = self.compute == "bf16x3" and text.is_cuda
         if use_tc and self.__dict__.get("_tc") is None:

@@ -51,10 +51,12 @@ class QA_TIGER(nn.Module):
                 nn.init.constant_(m.bias, 0)
 
     def set_precision(self, name: str):
-        """'fp32' | 'bf16' for every block of the hot path (the text tower has its own `.compute`)."""
+        """'fp32' | 'bf16' for every block of the hot path and for the native text tower (`quest_encoder.compute`
+        selects torch / native for the tower itself)."""
         for m in self.modules():
             if hasattr(m, "_prec"):
                 m.precision = name
+        self.quest_encoder.native_precision = name
         return self
 
     def sub_forward(self, reshaped_data: Dict[str, Tensor], prefix: str = ""):

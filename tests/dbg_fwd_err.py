@@ -12,7 +12,7 @@ for name in ("fwd_b8", "fwd_stress", "fwd_b256"):
     ref = torch.as_tensor(g["out"])
     for prec in ("fp32", "bf16"):
         m = build_model(sd, E, K, prec)
-        for tt in ("fp32", "tf32"):
+        for tt in ("fp32", "native", "tf32"):
             m.quest_encoder.compute = tt
             with torch.no_grad(): out = m(data)["out"].cpu()
             e = float((out - ref).norm() / ref.norm()); w = float(((out - ref).norm(dim=1) / ref.norm(dim=1)).max())

@@ -87,6 +87,7 @@ def test_text_tower_matches_oracle():
     sd = synth.make_state_dict(713, num_experts=7)
     model = build_model(sd, 7, 7, "fp32")
     batch = synth.make_batch(9, 6, 60)
+    model.quest_encoder.compute = "fp32"          # torch fp32 matmuls (the reference's arithmetic)
     with torch.no_grad():
         q, w = model.quest_encoder(batch["quest"].to(dev()))
         rq, rw = O.clip_text_encoder(sd, "quest_encoder", batch["quest"])
