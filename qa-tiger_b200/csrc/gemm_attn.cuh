@@ -7,9 +7,10 @@
 // 128 x 192 fp32 in TMEM (two of them, so the epilogue of tile i overlaps the main loop of tile i+1).
 //   warp 0      TMA producer (A: fp16 activations, W: fp16 weights; 128B swizzle, 4-stage ring)
 //   warp 1      TMEM allocator + tcgen05.mma issuer (kind::f16, M = 128, N = 192)
-//   warps 2..9  epilogue: TMEM -> +bias -> fp16 [128][192] tile in shared memory -> (named barrier) -> one warp per
+//   warps 2..9  epilogue: TMEM -> +bias -> fp16 [126][192] tile in shared memory -> (named barrier) -> one warp per
 //               frame: mma.sync m16n8k16 attention out of that tile (ldmatrix, softmax in the accumulator fragments,
 //               P re-used as the A fragment) -> O rows in a 128B-swizzled box -> (named barrier) -> one TMA store.
+//   warps 10,11 attention only: with 9 frames per tile, ten attention warps finish in one round instead of two
 #pragma once
 #include "attn_core.cuh"
 #include "gemm_tc.cuh"
@@ -38,7 +39,7 @@ constexpr int GA_BAR_BYTES = (2 * GA_STAGES + 4) * 8 + 16;
 constexpr int GA_SMEM = GA_STAGES * GA_STAGE_BYTES + GA_O_BYTES + GA_QKV_BYTES + GA_BAR_BYTES + 1024;
 static_assert(GA_SMEM <= 232448, "gemm_attn: shared-memory budget");
 
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO,
                  GemmAttnP p) {
   extern __shared__ unsigned char smem_dyn[];
@@ -124,7 +125,7 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
       }
     }
   } else {
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp - 2;                 // 0..9; warps 8, 9 of the epilogue group only run attention
     const int lg = warp & 3, half = ew >> 2;
     const uint32_t sqkv = smem_u32(sQKV), so = smem_u32(sO);
     const int g = lane >> 2, tq = lane & 3, m8 = lane >> 3, r8 = lane & 7;
@@ -132,11 +133,12 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
       const int mt = t / H, h = t % H, m0 = mt * RPT;
       const uint32_t as = lt & 1;
+      const int row = lg * 32 + lane;
+      if (ew < 8) {
       mbar_wait(&tfull[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tacc = tmem_base + as * 256 + half * 96 + (uint32_t(lg * 32) << 16);
-      const int row = lg * 32 + lane;
-      // ---- 1. accumulator -> (+bias) -> fp16 [128][192] tile ----
+      // ---- 1. accumulator -> (+bias) -> fp16 [126][192] tile ----
 #pragma unroll 1
       for (int c = 0; c < 3; ++c) {
         const int col0 = half * 96 + c * 32;                          // q: [0,64), k: [64,128), v: [128,192)
@@ -162,11 +164,12 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
                  pack_half2(__uint_as_float(v[8 * q + 6]) + b1.z, __uint_as_float(v[8 * q + 7]) + b1.w));
         }
       }
+      }
       // the previous tile's O box must have left shared memory before anyone overwrites it
       if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 320;" ::: "memory");
       // ---- 2. one warp per frame: softmax(q k^T * scale) v on mma.sync ----
-      for (int f = ew; f < FPT; f += 8) {
+      for (int f = ew; f < FPT; f += 10) {
         if (mt * FPT + f >= p.nframes) break;
         const uint32_t fb = sqkv + (f * P) * GA_QKV_STRIDE;
         float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
@@ -244,7 +247,7 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 256;" ::: "memory");
+      asm volatile("bar.sync 1, 320;" ::: "memory");
       // ---- 3. the head's O columns of the tile's rows leave through one TMA store (row tail clipped by the TMA unit) ----
       if (ew == 0 && lane == 0) {
         tma_store_2d(&mO, sO, h * 64, m0);
@@ -297,7 +300,7 @@ inline int gemm_attn_f16(Ctx& c, const __half* X, int ldx, int nframes, int P, i
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  tc::gemm_attn_kernel<<<grid, 320, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
+  tc::gemm_attn_kernel<<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
   return check_launch("gemm_attn_kernel");
 }
 
