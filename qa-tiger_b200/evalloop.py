@@ -168,6 +168,8 @@ def _main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # the version banner goes to stdout regardless of the file
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     torch.manual_seed(713)
     with warnings.catch_warnings():
