@@ -162,6 +162,8 @@ typedef struct {
   int32_t prec;
   void* stream;
   const float* patch;    /* [B,T,P,Cin] if has_proj else [B,T,P,D] */
+  const void* patch_f16; /* the same tensor as fp16 (half-size feature store / H2D); when set, `patch` is ignored.
+                            bf16 mode feeds it straight to the tensor cores (patch_proj then needs proj.w_f16), fp32 mode widens it */
   const float* audio;    /* [B,T,D] */
   const float* video;    /* [B,T,D] */
   int32_t has_proj;
@@ -317,7 +319,8 @@ typedef struct {
   const float* words;     /* [B, L, words_proj.k] */
   const float* audio;     /* [B, T, audio_proj.k] */
   const float* video;     /* [B, T, video_proj.k] */
-  const float* patch;     /* [B, T, P, patch_sel.Cin] */
+  const float* patch;     /* [B, T, P, patch_sel.Cin]; or NULL with patch_sel.patch_f16 set (the one tensor pointer of the
+                             embedded structs that IS honoured) */
   QatLinearW audio_proj, video_proj, words_proj, quest_proj;   /* net.py:120-123; patch_proj is patch_sel.proj */
   QatAvqArgs avq;
   QatPatchArgs patch_sel;

@@ -55,7 +55,7 @@ class AvqArgs(C.Structure):
 class PatchArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("P", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("Cin", C.c_int32),
                 ("prec", C.c_int32), ("stream", C.c_void_p),
-                ("patch", C.c_void_p), ("audio", C.c_void_p), ("video", C.c_void_p),
+                ("patch", C.c_void_p), ("patch_f16", C.c_void_p), ("audio", C.c_void_p), ("video", C.c_void_p),
                 ("has_proj", C.c_int32),
                 ("proj", LinearW), ("slf_in", LinearW), ("slf_out", LinearW), ("crs_q", LinearW), ("crs_kv", LinearW),
                 ("crs_out", LinearW), ("mlp0", LinearW), ("mlp2", LinearW),
@@ -198,11 +198,11 @@ def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
-def require_cuda_f32(t: torch.Tensor, name: str, shape: Optional[Tuple[int, ...]] = None):
+def require_cuda_f32(t: torch.Tensor, name: str, shape: Optional[Tuple[int, ...]] = None, allow_f16: bool = False):
     if not t.is_cuda:
         raise RuntimeError(f"{name}: expected a CUDA tensor (qa-tiger_b200 has no CPU path), got {t.device}")
-    if t.dtype != torch.float32:
-        raise RuntimeError(f"{name}: expected float32, got {t.dtype}")
+    if t.dtype != torch.float32 and not (allow_f16 and t.dtype == torch.float16):
+        raise RuntimeError(f"{name}: expected float32{' or float16' if allow_f16 else ''}, got {t.dtype}")
     if not t.is_contiguous():
         raise RuntimeError(f"{name}: expected a contiguous tensor (SURVEY 8b: the shim asserts, it does not copy)")
     if shape is not None and tuple(t.shape) != tuple(shape):

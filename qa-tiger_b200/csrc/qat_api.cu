@@ -301,6 +301,8 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
 // =================================================================================================
 static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const float* patch, Act Xaud, Act Xvid, Act out_a, Act out_v) {
   const int D = a->D, H = a->H;
+  const __half* patch_h = reinterpret_cast<const __half*>(a->patch_f16);
+  QAT_REQUIRE(c.dry || patch || patch_h, "patch_select: patch tensor missing");
   QAT_REQUIRE(B >= 1 && T >= 1 && P >= 1 && P <= 32 && D == H * 64, "patch_select: need P<=32 and D==H*64 (P=%d D=%d H=%d)", P, D, H);
   if (a->has_proj) QAT_TRY(check_w(a->proj, D, a->Cin, "patch.proj", c.prec));
   QAT_TRY(check_w(a->slf_in, 3 * D, D, "patch.slf_in", c.prec));
@@ -354,7 +356,8 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
     const long long nf = (BT - f0 < chunk) ? BT - f0 : chunk;
     const long long rows = nf * P;
     c.release(mark);
-    const float* pin = patch + (size_t)f0 * P * Cin;
+    const float* pin = patch ? patch + (size_t)f0 * P * Cin : nullptr;
+    const __half* pin_h = patch_h ? patch_h + (size_t)f0 * P * Cin : nullptr;
     AttnP q;
     q.nseq = (int)nf; q.H = H; q.Lq = 2; q.Lk = P; q.scale = scale;
     q.q = Q2.f + (size_t)f0 * 2 * D; q.q_sn = 2 * D; q.q_si = D;
@@ -362,12 +365,26 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
     q.o = O2.rows(2 * f0); q.o_rn = 2; q.o_ri = 1; q.attw = nullptr;
     if (f16_path) {
       Act Pp, QKV, Oa, P2, KV;
-      QAT_TRY(act_alloc_h(c, Pp, rows, D));
-      if (a->has_proj) {
-        const GemmKind kp = (Cin % 32 == 0) ? G_TF32 : G_SIMT;
-        QAT_TRY(gemm(c, kp, act_of(pin, Cin), rows, Wp, Epi(), Pp));
+      if (pin_h && !a->has_proj) {
+        Pp = Act();                                    // fp16 patches that are already projected: the plane is the input itself
+        Pp.h = const_cast<__half*>(pin_h);
+        Pp.ld = D;
       } else {
-        QAT_TRY(add_rows(c, pin, D, nullptr, 0, Pp, rows, D));
+        QAT_TRY(act_alloc_h(c, Pp, rows, D));
+        if (pin_h) {
+          // fp16 feature store: patch_proj as a single kind::f16 pass straight on the stored patches
+          QAT_REQUIRE(c.dry || Wp.h16, "patch_select: fp16 patches need patch_proj's fp16 weights (proj.w_f16)");
+          QAT_REQUIRE(Cin % 64 == 0, "patch_select: fp16 patches need Cin %% 64 == 0 (Cin=%d)", Cin);
+          Act Xh;
+          Xh.h = const_cast<__half*>(pin_h);
+          Xh.ld = Cin;
+          QAT_TRY(gemm(c, G_F16, Xh, rows, Wp, Epi(), Pp));
+        } else if (a->has_proj) {
+          const GemmKind kp = (Cin % 32 == 0) ? G_TF32 : G_SIMT;
+          QAT_TRY(gemm(c, kp, act_of(pin, Cin), rows, Wp, Epi(), Pp));
+        } else {
+          QAT_TRY(add_rows(c, pin, D, nullptr, 0, Pp, rows, D));
+        }
       }
       QAT_TRY(act_alloc_h(c, Oa, rows, D));
       const char* nofuse = getenv("QAT_PATCH_NO_FUSED_ATTN");      // A/B switch: in-proj GEMM + separate attention kernel
@@ -403,6 +420,12 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
       continue;
     }
     Act Pp, QKV, Oa, P2, KV;
+    if (pin_h) {                                       // fp32 mode (or P > 16): widen the fp16 patches of this pass first
+      float* wide = reinterpret_cast<float*>(c.alloc((size_t)rows * Cin * 4));
+      if (!c.dry && !wide) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+      QAT_TRY(widen_f16(c, pin_h, wide, rows * (long long)Cin));
+      pin = wide;
+    }
     if (a->has_proj) {
       QAT_TRY(act_alloc(c, Pp, rows, D, true, false));
       QAT_TRY(gemm(c, pick_kind(c, rows, D, Cin, true, Wp), act_of(pin, Cin), rows, Wp, Epi(), Pp));
@@ -448,7 +471,7 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
 }
 
 static int run_patch(const QatPatchArgs* a, Ctx& c) {
-  QAT_REQUIRE(c.dry || (a->patch && a->audio && a->video && a->out_a && a->out_v), "patch_select: NULL tensor");
+  QAT_REQUIRE(c.dry || ((a->patch || a->patch_f16) && a->audio && a->video && a->out_a && a->out_v), "patch_select: NULL tensor");
   return patch_core(a, a->B, a->T, a->P, c, a->patch, act_of(a->audio, a->D), act_of(a->video, a->D), act_of(a->out_a, a->D),
                     act_of(a->out_v, a->D));
 }
@@ -638,7 +661,7 @@ static int run_ground(const QatGroundArgs* a, Ctx& c) {
 static int run_forward(const QatForwardArgs* a, Ctx& c) {
   const int B = a->B, T = a->T, L = a->L, P = a->P, D = a->avq.D;
   QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && P >= 1, "forward: bad shape");
-  QAT_REQUIRE(c.dry || (a->quest && a->words && a->audio && a->video && a->patch && a->logits), "forward: NULL tensor");
+  QAT_REQUIRE(c.dry || (a->quest && a->words && a->audio && a->video && (a->patch || a->patch_sel.patch_f16) && a->logits), "forward: NULL tensor");
   QAT_REQUIRE(a->patch_sel.D == D && a->at.D == D && a->vt.D == D && a->ground.D == D && a->audio_proj.n == D && a->video_proj.n == D &&
                   a->words_proj.n == D && a->quest_proj.n == D, "forward: every block must share d_model=%d", D);
   QAT_REQUIRE(a->patch_sel.has_proj, "forward: patch_proj weights missing (patch_sel.has_proj)");

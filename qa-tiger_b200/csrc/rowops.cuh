@@ -111,6 +111,25 @@ inline int add_rows(Ctx& c, const float* a, long long lda, const float* b, long 
   return check_launch("add_rows_kernel");
 }
 
+// fp16 -> fp32 widening of a dense array (n8 groups of 8 elements)
+__global__ void __launch_bounds__(256) widen_f16_kernel(const __half* __restrict__ x, float* __restrict__ y, long long n8) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(x) + i);
+    const float2 a = unpack_half2(u.x), b = unpack_half2(u.y), c = unpack_half2(u.z), d = unpack_half2(u.w);
+    reinterpret_cast<float4*>(y)[2 * i] = make_float4(a.x, a.y, b.x, b.y);
+    reinterpret_cast<float4*>(y)[2 * i + 1] = make_float4(c.x, c.y, d.x, d.y);
+  }
+}
+inline int widen_f16(Ctx& c, const __half* x, float* y, long long n) {
+  QAT_REQUIRE(n % 8 == 0, "widen_f16: element count must be a multiple of 8");
+  if (c.dry || n == 0) return QAT_OK;
+  const long long n8 = n / 8;
+  unsigned grid = (unsigned)((n8 + 255) / 256 > 148 * 16 ? 148 * 16 : (n8 + 255) / 256);
+  widen_f16_kernel<<<grid, 256, 0, c.stream>>>(x, y, n8);
+  return check_launch("widen_f16_kernel");
+}
+
 __global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaxf(x[i], 0.f);

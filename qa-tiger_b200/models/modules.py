@@ -76,7 +76,7 @@ class Projection(_QatModule):
         self.proj = nn.Linear(inp_dim, d_model)
 
     def _prepare(self, prec):
-        return cabi.Lin(self.proj.weight, self.proj.bias, prec)
+        return cabi.Lin(self.proj.weight, self.proj.bias, prec, f16=True)   # fp16 copy: patch_proj on an fp16 feature store
 
     def forward(self, inp: Tensor) -> Tensor:
         self._guard()
@@ -405,7 +405,7 @@ class PatchSelecter(_QatModule):
         prec = self._prec()
         B, T, P, Cin = patch.shape
         D = self.d_model
-        cabi.require_cuda_f32(patch, "patch")
+        cabi.require_cuda_f32(patch, "patch", allow_f16=True)      # fp16 = half-size feature store
         cabi.require_cuda_f32(audio, "audio", (B, T, D))
         cabi.require_cuda_f32(video, "video", (B, T, D))
         if proj is None and Cin != D:
@@ -415,7 +415,11 @@ class PatchSelecter(_QatModule):
         a = cabi.PatchArgs()
         a.B, a.T, a.P, a.prec = B, T, P, prec
         self.fill_weights(a, prec, proj, Cin)
-        a.patch, a.audio, a.video = patch.data_ptr(), audio.data_ptr(), video.data_ptr()
+        if patch.dtype == torch.float16:
+            a.patch_f16 = patch.data_ptr()
+        else:
+            a.patch = patch.data_ptr()
+        a.audio, a.video = audio.data_ptr(), video.data_ptr()
         a.out_a, a.out_v = out_a.data_ptr(), out_v.data_ptr()
         cabi.run(cabi.OP_PATCH, "qat_patch_select_fwd", a, patch.device)
         return [out_a, out_v]

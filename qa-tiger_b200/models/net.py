@@ -94,11 +94,15 @@ class QA_TIGER(nn.Module):
         cabi.require_cuda_f32(words, "words", (B, L, self.words_proj.proj.in_features))
         cabi.require_cuda_f32(audio, "audio", (B, T, self.audio_proj.proj.in_features))
         cabi.require_cuda_f32(video, "video", (B, T, self.video_proj.proj.in_features))
-        cabi.require_cuda_f32(patch, "patch", (B, T, P, self.patch_proj.proj.in_features))
+        cabi.require_cuda_f32(patch, "patch", (B, T, P, self.patch_proj.proj.in_features), allow_f16=True)
         dev = patch.device
         a = cabi.ForwardArgs()
         a.B, a.T, a.L, a.P, a.prec = B, T, L, P, prec
-        a.quest, a.words, a.audio, a.video, a.patch = (t.data_ptr() for t in (quest, words, audio, video, patch))
+        a.quest, a.words, a.audio, a.video = (t.data_ptr() for t in (quest, words, audio, video))
+        if patch.dtype == torch.float16:       # half-size feature store: fed to the tensor cores as it is
+            a.patch_sel.patch_f16 = patch.data_ptr()
+        else:
+            a.patch = patch.data_ptr()
         a.audio_proj, a.video_proj, a.words_proj, a.quest_proj = (m._prepared(prec).c for m in blocks[:4])
         self.crs_attn.fill_weights(a.avq, prec)
         self.patch_selecter.fill_weights(a.patch_sel, prec, self.patch_proj, patch.shape[3])

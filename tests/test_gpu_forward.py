@@ -69,6 +69,24 @@ def test_fused_call_matches_block_by_block(prec):
     assert torch.equal(fused, blocks) or relerr(fused, blocks) < 1e-6
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("fused", [True, False])
+def test_fp16_patch_feature_store(prec, fused):
+    """`patch` may arrive as fp16 (half-size feature store / H2D).  The result must equal the reference
+    forward on the same (fp16-representable) values: fp32 mode widens them, bf16 mode feeds them to the tensor cores."""
+    sd = synth.make_state_dict(713, num_experts=7)
+    model = build_model(sd, 7, 7, prec)
+    model.fused = fused
+    batch = synth.make_batch(21, 5, 60)
+    batch["patch"] = batch["patch"].half()
+    ref = O.qa_tiger_forward(sd, {**batch, "patch": batch["patch"].float()})
+    data = {k: v.to(dev()) for k, v in batch.items()}
+    with torch.no_grad():
+        out = model(data)["out"]
+    assert relerr(out, ref) < TOL[prec]
+    assert out.argmax(1).cpu().tolist() == ref.argmax(1).tolist()
+
+
 def test_batch_composition_is_part_of_the_function():
     """logits depend on the local batch; DP sharding must therefore be defined on local batches."""
     sd = synth.make_state_dict(713, num_experts=7)
