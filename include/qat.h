@@ -326,6 +326,8 @@ typedef struct {
   QatPatchArgs patch_sel;
   QatMoeArgs at, vt;
   QatGroundArgs ground;   /* both QstGrounding passes share these weights; `head` is applied after the second */
+  QatLinearW q_cat;       /* optional [3D, D] = cat(at.attn_q, vt.attn_q, ground.attn_q) (+ biases): the query projections of
+                             the blocks that attend from the question as one contraction; w = NULL -> each block does its own */
   float* logits;          /* [B, ground.head.n] */
   void* workspace;
   size_t workspace_bytes;

@@ -97,7 +97,7 @@ class ForwardArgs(C.Structure):
                 ("quest", C.c_void_p), ("words", C.c_void_p), ("audio", C.c_void_p), ("video", C.c_void_p), ("patch", C.c_void_p),
                 ("audio_proj", LinearW), ("video_proj", LinearW), ("words_proj", LinearW), ("quest_proj", LinearW),
                 ("avq", AvqArgs), ("patch_sel", PatchArgs), ("at", MoeArgs), ("vt", MoeArgs), ("ground", GroundArgs),
-                ("logits", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("q_cat", LinearW), ("logits", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class TomeMatchArgs(C.Structure):

@@ -23,8 +23,9 @@ namespace cg = cooperative_groups;
 struct GaussP {
   const void* x;
   long long st, sb;   // element strides of X over t and b; (e, c) are contiguous: e*C + c
-  const float* rl;    // [B,E]
-  const float* gr;    // [B,2E]
+  const float* rl;    // router logits, row b at rl + b * rl_ld (dense [B,E]: rl_ld = E)
+  const float* gr;    // gauss_pred output, row b at gr + b * gr_ld (dense [B,2E]: gr_ld = 2E)
+  int rl_ld = 0, gr_ld = 0;   // 0 = dense
   int B, T, E, K, C;
   float sigma;
   int per_expert;     // 0: out[b, c] summed over experts (reference get_output)
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
     float pr[GAUSS_MAX_E];
     float mx = -INFINITY;
     for (int e = 0; e < E; ++e) {
-      pr[e] = __ldg(p.rl + (long long)o * E + e);
+      pr[e] = __ldg(p.rl + (long long)o * (p.rl_ld ? p.rl_ld : E) + e);
       mx = fmaxf(mx, pr[e]);
     }
     float sum = 0.f;
@@ -144,8 +145,9 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
       for (int i = 0; i < K; ++i) {
         const int e = s_idx[i];
         s_p[i] = s_p[i] / psum;
-        float g0 = __ldg(p.gr + (long long)b * 2 * E + 2 * e);
-        float g1 = __ldg(p.gr + (long long)b * 2 * E + 2 * e + 1);
+        const long long gro = (long long)b * (p.gr_ld ? p.gr_ld : 2 * E);
+        float g0 = __ldg(p.gr + gro + 2 * e);
+        float g1 = __ldg(p.gr + gro + 2 * e + 1);
         float centre = linspace_at(margin, 1.f - margin, E, e) + tanhf(g0) * margin;
         float width = 1.f / (1.f + expf(-g1));
         s_c[i] = fminf(fmaxf(centre, 0.f), 1.f);

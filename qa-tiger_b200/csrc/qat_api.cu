@@ -498,7 +498,7 @@ static int run_gauss(const QatGaussArgs* a, Ctx& c) {
 // M1-M4 (+LN)  TempMoE
 // =================================================================================================
 static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst, Act Xd, const float* sub_a, const float* sub_v, float* out_a,
-                    float* out_v) {
+                    float* out_v, const float* qpre = nullptr, int ldq = 0) {
   const int D = a->D, H = a->H, E = a->E, K = a->K;
   QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
   QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
@@ -523,12 +523,16 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
   if (!two) QAT_TRY(ensure_operand(c, Xd, BT, D, k_w1));
   QAT_TRY(act_alloc(c, KV, BT, 2 * D, true, false));
   QAT_TRY(gemm(c, k_kv, Xd, BT, Wkv, Epi(), KV));
-  QAT_TRY(act_alloc(c, Q, B, D, true, false));
-  QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, Wq, Epi(), Q));
+  if (qpre) {
+    Q = act_of(qpre, ldq);
+  } else {
+    QAT_TRY(act_alloc(c, Q, B, D, true, false));
+    QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, Wq, Epi(), Q));
+  }
   QAT_TRY(act_alloc(c, Oq, B, D, true, false));
   AttnP p;
   p.nseq = B; p.H = H; p.Lq = 1; p.Lk = T; p.scale = 0.125f;
-  p.q = Q.f; p.q_sn = D; p.q_si = D;
+  p.q = Q.f; p.q_sn = Q.ld; p.q_si = Q.ld;
   p.k = KV.f; p.v = KV.f + D; p.k_sn = (long long)T * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B;
   p.o = Oq; p.o_rn = 1; p.o_ri = 1; p.attw = nullptr;
   QAT_TRY(attention(c, p));
@@ -537,15 +541,7 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
   // router logits [B,E] | gauss_pred [B,2E] in one fp32 contraction (:565,573)
   QAT_TRY(act_alloc(c, RG, B, 3 * E, true, false));
   QAT_TRY(gemm(c, G_SIMT, TW, B, Wrg, Epi(), RG));
-  // RG rows are [router(E) | gauss(2E)] with ld 3E: the reduce kernel wants dense [B,E] and [B,2E]
-  Act RL, GR;
-  QAT_TRY(act_alloc(c, RL, B, E, true, false));
-  QAT_TRY(act_alloc(c, GR, B, 2 * E, true, false));
-  if (!c.dry) {
-    QAT_CUDA(cudaMemcpy2DAsync(RL.f, (size_t)E * 4, RG.f, (size_t)3 * E * 4, (size_t)E * 4, B, cudaMemcpyDeviceToDevice, c.stream));
-    QAT_CUDA(cudaMemcpy2DAsync(GR.f, (size_t)2 * E * 4, RG.f + E, (size_t)3 * E * 4, (size_t)2 * E * 4, B, cudaMemcpyDeviceToDevice, c.stream));
-    g_launches += 2;
-  }
+  // RG rows are [router(E) | gauss(2E)] with ld 3E: the reduce kernel reads both through a row pitch
 
   const int nbranch = two ? 2 : 1;
   for (int br = 0; br < nbranch; ++br) {
@@ -567,7 +563,7 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
     QAT_TRY(act_alloc(c, Hb, B, KE, true, false));
     GaussP g;
     g.x = Hd.f; g.st = (long long)E * Ch; g.sb = (long long)T * E * Ch;
-    g.rl = RL.f; g.gr = GR.f; g.B = B; g.T = T; g.E = E; g.K = K; g.C = Ch; g.sigma = a->sigma;
+    g.rl = RG.f; g.gr = RG.f + E; g.rl_ld = 3 * E; g.gr_ld = 3 * E; g.B = B; g.T = T; g.E = E; g.K = K; g.C = Ch; g.sigma = a->sigma;
     g.per_expert = 1; g.out = Hb;
     g.topk_inds = br == 0 ? reinterpret_cast<long long*>(a->topk_inds) : nullptr;
     g.topk_probs = br == 0 ? a->topk_probs : nullptr;
@@ -596,8 +592,10 @@ static int run_moe(const QatMoeArgs* a, Ctx& c) {
 // =================================================================================================
 // G1 (+H1)  QstGrounding on a length-2 sequence, optional head
 // =================================================================================================
+// qpre (optional): the query projection attn_q(qst) computed by the caller, row pitch ldq (qat_forward_fwd batches the
+// query projections of every block that attends from the question into one contraction)
 static int ground_core(const QatGroundArgs* a, int B, Ctx& c, const float* qst, const float* d0, const float* d1, float* out, bool with_head,
-                       float* logits) {
+                       float* logits, const float* qpre = nullptr, int ldq = 0) {
   const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && D == H * 64, "qst_grounding: need D==H*64");
   QAT_TRY(check_w(a->attn_q, D, D, "ground.attn_q", c.prec));
@@ -606,22 +604,31 @@ static int ground_core(const QatGroundArgs* a, int B, Ctx& c, const float* qst, 
   QAT_TRY(check_w(a->mlp0, D / 2, D, "ground.mlp0", c.prec));
   QAT_TRY(check_w(a->mlp2, D, D / 2, "ground.mlp2", c.prec));
   Act KV, Q, O, A1, Hm, Mo;
-  QAT_TRY(act_alloc(c, KV, 2ll * B, 2 * D, true, false));      // [B, 2, 2D]
-  {
-    Act kv0 = KV, kv1 = KV;
+  QAT_TRY(act_alloc(c, KV, 2ll * B, 2 * D, true, false));
+  AttnP p;
+  if (d1 == d0 + (size_t)B * D) {
+    // the two length-1 inputs sit back to back: one contraction over [2B, D]; key i of sample b is row i*B + b
+    QAT_TRY(gemm(c, G_SIMT, act_of(d0, D), 2ll * B, wview(a->attn_kv), Epi(), KV));
+    p.k_sn = 2 * D; p.k_si = (long long)B * 2 * D;
+  } else {
+    Act kv0 = KV, kv1 = KV;                                      // [B, 2, 2D]
     kv0.ld = 4 * D;
     kv1.ld = 4 * D;
     kv1.f += 2 * D;
     QAT_TRY(gemm(c, G_SIMT, act_of(d0, D), B, wview(a->attn_kv), Epi(), kv0));
     QAT_TRY(gemm(c, G_SIMT, act_of(d1, D), B, wview(a->attn_kv), Epi(), kv1));
+    p.k_sn = 4 * D; p.k_si = 2 * D;
   }
-  QAT_TRY(act_alloc(c, Q, B, D, true, false));
-  QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, wview(a->attn_q), Epi(), Q));
+  if (qpre) {
+    Q = act_of(qpre, ldq);
+  } else {
+    QAT_TRY(act_alloc(c, Q, B, D, true, false));
+    QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, wview(a->attn_q), Epi(), Q));
+  }
   QAT_TRY(act_alloc(c, O, B, D, true, false));
-  AttnP p;
   p.nseq = B; p.H = H; p.Lq = 1; p.Lk = 2; p.scale = 0.125f;
-  p.q = Q.f; p.q_sn = D; p.q_si = D;
-  p.k = KV.f; p.v = KV.f + D; p.k_sn = 4 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B;
+  p.q = Q.f; p.q_sn = Q.ld; p.q_si = Q.ld;
+  p.k = KV.f; p.v = KV.f + D; p.k_shift = 0; p.k_mod = B;
   p.o = O; p.o_rn = 1; p.o_ri = 1; p.attw = nullptr;
   QAT_TRY(attention(c, p));
   QAT_TRY(act_alloc(c, A1, B, D, true, false));
@@ -687,25 +694,39 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
   }
   QAT_TRY(act_alloc(c, Ap, BT, D, true, false));
   QAT_TRY(act_alloc(c, Vp, BT, D, true, false));
-  float* glob = reinterpret_cast<float*>(c.alloc((size_t)5 * B * D * 4));     // a_global | ap_global | vp_global | fusion1 | fusion2
+  // ap_global | vp_global | fusion1 | a_global | fusion2: both QstGrounding passes find their two inputs back to back
+  float* glob = reinterpret_cast<float*>(c.alloc((size_t)5 * B * D * 4));
   if (!c.dry && !glob) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
-  float* a_global = glob;
-  float* ap_global = glob + (size_t)B * D;
-  float* vp_global = glob + (size_t)2 * B * D;
-  float* fusion1 = glob + (size_t)3 * B * D;
+  float* ap_global = glob;
+  float* vp_global = glob + (size_t)B * D;
+  float* fusion1 = glob + (size_t)2 * B * D;
+  float* a_global = glob + (size_t)3 * B * D;
   float* fusion2 = glob + (size_t)4 * B * D;
+  // the three blocks that attend FROM the question project it with different weights: one [B, D] x [3D, D]^T contraction
+  // (q_cat = at.attn_q | vt.attn_q | ground.attn_q) instead of four launches (ground runs twice on the same query)
+  const float* q_at = nullptr;
+  const float* q_vt = nullptr;
+  const float* q_gr = nullptr;
+  int ldq = 0;
+  if (a->q_cat.w) {
+    QAT_TRY(check_w(a->q_cat, 3 * D, D, "forward.q_cat", c.prec));
+    Act Qc;
+    QAT_TRY(act_alloc(c, Qc, B, 3 * D, true, false));
+    QAT_TRY(gemm(c, G_SIMT, Q0, B, wview(a->q_cat), Epi(), Qc));
+    q_at = Qc.f; q_vt = Qc.f + D; q_gr = Qc.f + 2 * D; ldq = 3 * D;
+  }
   const size_t mark = c.mark();
   QAT_TRY(avq_core(&a->avq, B, T, L, c, A0, V0, W0, Ax, Vx, nullptr, nullptr));
   c.release(mark);
   QAT_TRY(patch_core(&a->patch_sel, B, T, P, c, a->patch, Ax, Vx, Ap, Vp));
   c.release(mark);
-  QAT_TRY(moe_core(&a->at, B, T, c, Q0.f, Ax, nullptr, nullptr, a_global, nullptr));
+  QAT_TRY(moe_core(&a->at, B, T, c, Q0.f, Ax, nullptr, nullptr, a_global, nullptr, q_at, ldq));
   c.release(mark);
-  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Ap.f, Vp.f, ap_global, vp_global));
+  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Ap.f, Vp.f, ap_global, vp_global, q_vt, ldq));
   c.release(mark);
-  QAT_TRY(ground_core(&a->ground, B, c, Q0.f, ap_global, vp_global, fusion1, false, nullptr));
+  QAT_TRY(ground_core(&a->ground, B, c, Q0.f, ap_global, vp_global, fusion1, false, nullptr, q_gr, ldq));
   c.release(mark);
-  QAT_TRY(ground_core(&a->ground, B, c, Q0.f, fusion1, a_global, fusion2, true, a->logits));
+  QAT_TRY(ground_core(&a->ground, B, c, Q0.f, fusion1, a_global, fusion2, true, a->logits, q_gr, ldq));
   return QAT_OK;
 }
 

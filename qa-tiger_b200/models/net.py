@@ -80,6 +80,21 @@ class QA_TIGER(nn.Module):
     # block by block through the drop-in modules (identical arithmetic; what a partially switched reference would do).
     fused = True
 
+    def _q_cat(self):
+        """[3D, D] = the query in-projections of at_aggregator, vt_aggregator and quest_grounding stacked (always fp32 FFMA:
+        they are on the router path), cached on the parameter versions."""
+        mods = (self.at_aggregator.qst_attn, self.vt_aggregator.qst_attn, self.quest_grounding.attn)
+        key = tuple((m.in_proj_weight.data_ptr(), m.in_proj_weight._version, m.in_proj_bias.data_ptr(), m.in_proj_bias._version) for m in mods)
+        cached = self.__dict__.get("_q_cat_cache")
+        if cached is None or cached[0] != key:
+            D = self.head.in_features
+            with torch.no_grad():
+                w = torch.cat([m.in_proj_weight[:D] for m in mods], 0)
+                b = torch.cat([m.in_proj_bias[:D] for m in mods], 0)
+            cached = (key, cabi.Lin(w, b, cabi.PREC_FP32))
+            self.__dict__["_q_cat_cache"] = cached
+        return cached[1]
+
     def _forward_fused(self, quest: Tensor, words: Tensor, audio: Tensor, video: Tensor, patch: Tensor) -> Tensor:
         blocks = (self.audio_proj, self.video_proj, self.words_proj, self.quest_proj, self.patch_proj, self.crs_attn,
                   self.patch_selecter, self.at_aggregator, self.vt_aggregator, self.quest_grounding)
@@ -109,6 +124,7 @@ class QA_TIGER(nn.Module):
         self.at_aggregator.fill_weights(a.at, prec)
         self.vt_aggregator.fill_weights(a.vt, prec)
         hold = self.quest_grounding.fill_weights(a.ground, prec, self.head)   # noqa: F841 -- keeps the head weights alive
+        a.q_cat = self._q_cat().c
         aux_at = self.at_aggregator.attach_aux(a.at, B, T, dev)
         aux_vt = self.vt_aggregator.attach_aux(a.vt, B, T, dev)
         logits = torch.empty(B, self.head.out_features, device=dev, dtype=torch.float32)
