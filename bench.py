@@ -549,7 +549,7 @@ def run_ours(args):
             for k, v in json.load(open(tpath)).items():
                 if k in rooflines:
                     rooflines[k]["traffic"] = v
-        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v13.txt:
+        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v16.txt:
         # the bf16x3 tcgen05 GEMM, 30 % of the step; the f16 kind and the fused in-proj + attention kernel follow at 13 % each), at its largest shape; the other GEMM
         # kinds, the HBM-class Gaussian-expert kernel north_star names and the ToMe chain ride along in rooflines_all
         key = "gemm_bf16x3_avq_in_src"
