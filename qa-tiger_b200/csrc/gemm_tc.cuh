@@ -48,8 +48,68 @@ __host__ __device__ constexpr uint32_t umma_idesc(int fmt, int M, int N) {
   return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
 }
 
-template <int KIND>
+// ---- CTA-pair (cta_group::2) helpers: the two CTAs of a cluster sit on the two SMs of one TPC; the leader (cluster rank 0)
+// issues one M = 256 MMA over both CTAs' shared memory (own 128 A rows + own half of the W rows each) and both TMEMs ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `saddr` (a shared::cta address of the executing CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// the load lands in the executing CTA's shared memory; its bytes are counted on `bar_cluster` (a shared::cluster address,
+// the LEADER's full barrier)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, uint32_t bar_cluster, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster) : "memory");
+}
+// bounded wait with cluster-scope acquire (the arrivals come from the peer CTA)
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+
+template <int KIND, int CG = 1>
 __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  if (CG == 2) {
+    if (KIND == KIND_TF32) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+          : "memory");
+    } else {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+          "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+          ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+          : "memory");
+    }
+    return;
+  }
   if (KIND == KIND_TF32) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -66,6 +126,13 @@ __device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t da, uint64_t db, 
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// pair form: one arrival on the barrier at this offset in BOTH CTAs of the pair once the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile(
@@ -99,15 +166,16 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
                : "memory");
 }
 
-template <int KIND, int BN, int STAGES>
+template <int KIND, int BN, int STAGES, int CG = 1>
 struct Cfg {
-  static constexpr int BM = 128;
+  static constexpr int BM = 128;                                          // rows per CTA (the pair tile is CG * BM rows)
   static constexpr int ROW_BYTES = 128;                                   // one swizzle row
   static constexpr int BK = KIND == KIND_TF32 ? 32 : 64;                  // elements per k-block
   static constexpr int UK = KIND == KIND_TF32 ? 8 : 16;                   // elements per MMA
   static constexpr int PLANES = KIND == KIND_BF16X3 ? 2 : 1;
   static constexpr int A_BYTES = BM * ROW_BYTES;                          // per plane
-  static constexpr int W_BYTES = BN * ROW_BYTES;
+  static constexpr int BN_CTA = BN / CG;                                  // W rows this CTA stages (the pair splits them)
+  static constexpr int W_BYTES = BN_CTA * ROW_BYTES;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + W_BYTES);
   static constexpr int EPI_BYTES = 8 * 4096;                              // 8 epilogue warps x one 4 KB TMA-store box
   static constexpr int BAR_BYTES = (2 * STAGES + 4 + 8) * 8 + 16;        // + one residual-box barrier per epilogue warp
@@ -123,14 +191,20 @@ struct Cfg {
 // EPI specialises the epilogue on the set of output planes (a smaller chunk body schedules measurably better):
 //   1 = one fp16 plane, residual (if any) through the TMA unit (the PatchSelecter GEMMs); 2 = one fp32 plane;
 //   3 = bf16 (hi, lo) planes; 0 = any combination behind run-time flags.
-template <int KIND, int BN, int STAGES, int EPI>
+// CG = 2: CTA pairs (cluster of 2 on one TPC, launched with a cluster dimension of 2).  The pair owns a 256 x BN tile: each
+// CTA stages its own 128 A rows and HALF of the W rows, the leader issues tcgen05.mma.cta_group::2 (M = 256) over both
+// shared memories and both TMEMs, so every SM's operand traffic through shared memory drops by a third (the single-CTA
+// f16 kind at K = 512 is bound by it: TMA writes + MMA reads + epilogue boxes exceed the 128 B/clk port).  Barriers: `full`
+// lives in the leader and counts both CTAs' bytes; `empty` / `tfull` are signalled in both CTAs by a multicast commit;
+// `tempty` lives in the leader and collects the epilogue warps of both CTAs.
+template <int KIND, int BN, int STAGES, int EPI, int CG = 1>
 __global__ void __launch_bounds__(320, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mW0, const __grid_constant__ CUtensorMap mW1,
                const __grid_constant__ CUtensorMap mCf, const __grid_constant__ CUtensorMap mChi,
                const __grid_constant__ CUtensorMap mClo, const __grid_constant__ CUtensorMap mCh,
                const __grid_constant__ CUtensorMap mR, GemmP p) {
-  typedef Cfg<KIND, BN, STAGES> G;
+  typedef Cfg<KIND, BN, STAGES, CG> G;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* tiles = smem;                                               // STAGES x [A planes | W planes]
@@ -145,8 +219,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + G::BK - 1) / G::BK;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int tiles_m = (p.M + G::BM - 1) / G::BM;
+  const int tiles_m = ((p.M + G::BM - 1) / G::BM + CG - 1) / CG;             // pair tiles when CG == 2 (a tail pair may be half empty)
   const int ntiles = tiles_n * tiles_m;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / CG, nunits = gridDim.x / CG;                 // persistent walk, one unit = one CTA (pair)
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA0)) : "memory");
@@ -161,18 +237,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);          // one arrival per epilogue warp
+      mbar_init(&tempty[a], 8 * CG);     // one arrival per epilogue warp (of both CTAs of a pair)
     }
     for (int w = 0; w < 8; ++w) mbar_init(&rbar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(G::TMEM_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(G::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(G::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
@@ -180,30 +262,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t it = 0;                                   // running k-block counter across tiles
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
+      for (int t = unit0; t < ntiles; t += nunits) {
+        const int m0 = ((t / tiles_n) * CG + (int)crank) * G::BM, n0 = (t % tiles_n) * BN + (int)crank * G::BN_CTA;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
           mbar_wait(&empty[s], ph ^ 1);
           unsigned char* st = tiles + s * G::STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
           const int k0 = kb * G::BK;
-          tma_load_2d(st, &mA0, &full[s], k0, m0);
-          if (G::PLANES == 2) tma_load_2d(st + G::A_BYTES, &mA1, &full[s], k0, m0);
-          tma_load_2d(st + G::PLANES * G::A_BYTES, &mW0, &full[s], k0, n0);
-          if (G::PLANES == 2) tma_load_2d(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, &full[s], k0, n0);
+          if (CG == 2) {
+            // both CTAs' bytes are counted on the leader's barrier (armed by the leader alone, for the pair)
+            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * G::STAGE_BYTES);
+            const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
+            tma_load_2d_pair(st, &mA0, fb, k0, m0);
+            if (G::PLANES == 2) tma_load_2d_pair(st + G::A_BYTES, &mA1, fb, k0, m0);
+            tma_load_2d_pair(st + G::PLANES * G::A_BYTES, &mW0, fb, k0, n0);
+            if (G::PLANES == 2) tma_load_2d_pair(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, fb, k0, n0);
+          } else {
+            mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
+            tma_load_2d(st, &mA0, &full[s], k0, m0);
+            if (G::PLANES == 2) tma_load_2d(st + G::A_BYTES, &mA1, &full[s], k0, m0);
+            tma_load_2d(st + G::PLANES * G::A_BYTES, &mW0, &full[s], k0, n0);
+            if (G::PLANES == 2) tma_load_2d(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, &full[s], k0, n0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc(KIND == KIND_TF32 ? 2 : (KIND == KIND_BF16X3 ? 1 : 0), G::BM, BN);
+    if (lane == 0 && crank == 0) {
+      constexpr uint32_t idesc = umma_idesc(KIND == KIND_TF32 ? 2 : (KIND == KIND_BF16X3 ? 1 : 0), G::BM * CG, BN);
       uint32_t it = 0, lt = 0;                           // lt = local tile counter
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      for (int t = unit0; t < ntiles; t += nunits, ++lt) {
         const uint32_t as = lt & 1;
-        mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);     // epilogue has drained this accumulator
+        // the epilogue (of both CTAs) has drained this accumulator
+        if (CG == 2) mbar_wait_cluster(&tempty[as], ((lt >> 1) & 1) ^ 1);
+        else mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tacc = tmem_base + as * BN;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
@@ -220,16 +314,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             if (p.dbg & 2) break;
             const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
             if (G::PLANES == 1) {
-              umma<KIND>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
+              umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
             } else {
-              umma<KIND>(tacc, dA1 + adv, dW0 + adv, idesc, (kb | k) != 0);    // lo * hi
-              umma<KIND>(tacc, dA0 + adv, dW1 + adv, idesc, 1);                // hi * lo
-              umma<KIND>(tacc, dA0 + adv, dW0 + adv, idesc, 1);                // hi * hi
+              umma<KIND, CG>(tacc, dA1 + adv, dW0 + adv, idesc, (kb | k) != 0);    // lo * hi
+              umma<KIND, CG>(tacc, dA0 + adv, dW1 + adv, idesc, 1);                // hi * lo
+              umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, 1);                // hi * hi
             }
           }
-          umma_commit(&empty[s]);            // smem slot reusable once these MMAs have read it
+          // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
+          if (CG == 2) umma_commit_pair(&empty[s]);
+          else umma_commit(&empty[s]);
         }
-        umma_commit(&tfull[as]);             // accumulator complete
+        // accumulator complete
+        if (CG == 2) umma_commit_pair(&tfull[as]);
+        else umma_commit(&tfull[as]);
       }
     }
   } else {
@@ -251,8 +349,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     const uint32_t sbox = smem_u32(box);
     const uint32_t sw128 = uint32_t(lane & 7), sw64 = uint32_t((lane >> 1) & 3);
     uint32_t lt = 0, nres = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-      const int m0 = (t / tiles_n) * G::BM, n0 = (t % tiles_n) * BN;
+    // accumulator hand-back: the leader's barrier (a remote arrival from the peer CTA)
+    const uint32_t tempty_a0 = CG == 2 ? mapa_rank(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]);
+    const uint32_t tempty_a1 = CG == 2 ? mapa_rank(smem_u32(&tempty[1]), 0) : smem_u32(&tempty[1]);
+    for (int t = unit0; t < ntiles; t += nunits, ++lt) {
+      const int m0 = ((t / tiles_n) * CG + (int)crank) * G::BM, n0 = (t % tiles_n) * BN;
       const uint32_t as = lt & 1;
       mbar_wait(&tfull[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -261,7 +362,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       const bool row_ok = row < p.M;
       if (p.dbg & 1) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster((as ? tempty_a1 : tempty_a0));
+          else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((as ? tempty_a1 : tempty_a0)) : "memory");
+        }
         continue;
       }
 #pragma unroll 1
@@ -309,7 +413,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         if (c == NCH - 1) {
           // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster((as ? tempty_a1 : tempty_a0));
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((as ? tempty_a1 : tempty_a0)) : "memory");
+          }
         }
         if (!live) continue;
         float x[32];
@@ -411,9 +518,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // no CTA of the pair leaves (or frees TMEM) while the other may still signal / be read
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(G::TMEM_COLS) : "memory");
   }
 }
 
@@ -467,18 +576,19 @@ inline int make_store_map(CUtensorMap* m, const void* base, CUtensorMapDataType 
   return QAT_OK;
 }
 
-template <int KIND, int BN, int STAGES>
+template <int KIND, int BN, int STAGES, int CG = 1>
 inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long long M, const void* W0, const void* W1, int N, int K,
                   const Epi& epi, const Act& C) {
-  typedef Cfg<KIND, BN, STAGES> G;
+  typedef Cfg<KIND, BN, STAGES, CG> G;
+  static_assert(G::SMEM <= 227 * 1024, "gemm_tc: shared-memory budget exceeded");
   const CUtensorMapDataType dt = KIND == KIND_TF32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                  : (KIND == KIND_BF16X3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
   CUtensorMap mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR;
   QAT_TRY(make_map(&mA0, A0, dt, M, K, lda, G::BM));
-  QAT_TRY(make_map(&mW0, W0, dt, N, K, K, BN));
+  QAT_TRY(make_map(&mW0, W0, dt, N, K, K, G::BN_CTA));
   if (G::PLANES == 2) {
     QAT_TRY(make_map(&mA1, A1, dt, M, K, lda, G::BM));
-    QAT_TRY(make_map(&mW1, W1, dt, N, K, K, BN));
+    QAT_TRY(make_map(&mW1, W1, dt, N, K, K, G::BN_CTA));
   } else {
     mA1 = mA0;
     mW1 = mW0;
@@ -502,20 +612,34 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   }
   const char* dbg = getenv("QAT_GEMM_DBG");
   p.dbg = dbg ? atoi(dbg) : 0;
-  const long long ntiles = (long long)((N + BN - 1) / BN) * ((M + G::BM - 1) / G::BM);
+  // persistent units: CTAs, or CTA pairs walking 256-row pair tiles
+  const long long ntiles = (long long)((N + BN - 1) / BN) * (((M + G::BM - 1) / G::BM + CG - 1) / CG);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  const long long units = sms / CG;
+  const unsigned grid = (unsigned)(ntiles < units ? ntiles : units) * CG;
   int mode = 0;
   if (KIND != KIND_BF16X3 && C.h && !C.f && !C.hi && !epi.res && (!epi.res_h || p.tma_res)) mode = 1;
   else if (C.f && !C.hi && !C.lo && !C.h) mode = 2;
   else if (KIND == KIND_BF16X3 && C.hi && C.lo && !C.f && !C.h) mode = 3;
 #define QAT_GEMM_LAUNCH(EPI_)                                                                                 \
   do {                                                                                                        \
-    auto kern = gemm_tc_kernel<KIND, BN, STAGES, EPI_>;                                                       \
+    auto kern = gemm_tc_kernel<KIND, BN, STAGES, EPI_, CG>;                                                   \
     QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));               \
-    kern<<<grid, 320, G::SMEM, c.stream>>>(mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR, p);                  \
+    cudaLaunchConfig_t cfg = {};                                                                              \
+    cfg.gridDim = dim3(grid);                                                                                 \
+    cfg.blockDim = dim3(320);                                                                                 \
+    cfg.dynamicSmemBytes = G::SMEM;                                                                           \
+    cfg.stream = c.stream;                                                                                    \
+    cudaLaunchAttribute at[1];                                                                                \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                           \
+    at[0].val.clusterDim.x = CG;                                                                              \
+    at[0].val.clusterDim.y = 1;                                                                               \
+    at[0].val.clusterDim.z = 1;                                                                               \
+    cfg.attrs = at;                                                                                           \
+    cfg.numAttrs = CG == 2 ? 1 : 0;                                                                           \
+    QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR, p));                \
   } while (0)
   if (mode == 1) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 ? 0 : 1));
   else if (mode == 2) QAT_GEMM_LAUNCH(2);
@@ -539,6 +663,14 @@ inline bool wide_tile(int N) {
   if (e) return atoi(e) == 256;
   return N % 256 == 0;
 }
+// CTA pairs (cta_group::2) for the wide tile; QAT_GEMM_CG=1 / 2 is the A/B switch.  Measured on B200 (tests/prof_gemm.py):
+// bf16x3 +12 % (475 vs 425 nominal TFLOP/s at [15360,512]x[3584,512]^T), tf32 +4..10 %, f16 -3..7 % (its MMA time per tile is
+// close to its epilogue time, and a pair couples the two CTAs' epilogues to one accumulator hand-back), hence the defaults.
+inline bool pair_tile(long long M, bool dflt) {
+  const char* e = getenv("QAT_GEMM_CG");
+  if (e) return atoi(e) == 2;
+  return dflt && M > 128;
+}
 
 }  // namespace tc
 
@@ -547,6 +679,7 @@ inline int gemm_tc_tf32(Ctx& c, const float* A, int lda, long long M, const floa
   QAT_TRY(tc::check_common(M, N, K, lda, epi, C, 4));
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
   if (c.dry) return QAT_OK;
+  if (tc::wide_tile(N) && tc::pair_tile(M, true)) return tc::launch<tc::KIND_TF32, 256, 6, 2>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
   if (tc::wide_tile(N)) return tc::launch<tc::KIND_TF32, 256, 4>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
   return tc::launch<tc::KIND_TF32, 128, 6>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
 }
@@ -558,6 +691,7 @@ inline int gemm_tc_bf16x3(Ctx& c, const bf16* Ahi, const bf16* Alo, int lda, lon
   if (c.dry) return QAT_OK;
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(Ahi) | reinterpret_cast<uintptr_t>(Alo) | reinterpret_cast<uintptr_t>(Whi) |
                reinterpret_cast<uintptr_t>(Wlo)) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
+  if (tc::wide_tile(N) && tc::pair_tile(M, true)) return tc::launch<tc::KIND_BF16X3, 256, 3, 2>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
   if (tc::wide_tile(N)) return tc::launch<tc::KIND_BF16X3, 256, 2>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
   return tc::launch<tc::KIND_BF16X3, 128, 3>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
 }
@@ -567,6 +701,7 @@ inline int gemm_tc_f16(Ctx& c, const __half* A, int lda, long long M, const __ha
   QAT_TRY(tc::check_common(M, N, K, lda, epi, C, 2));
   if (c.dry) return QAT_OK;
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
+  if (tc::wide_tile(N) && tc::pair_tile(M, false)) return tc::launch<tc::KIND_F16, 256, 6, 2>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
   if (tc::wide_tile(N)) return tc::launch<tc::KIND_F16, 256, 4>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
   return tc::launch<tc::KIND_F16, 128, 6>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
 }

@@ -86,3 +86,34 @@ def test_gemm_tf32_to_f16_plane(M, N, K):
     full = _cabi.gemm(_cabi.GEMM_TF32, a, lin)
     got = _cabi.gemm(_cabi.GEMM_TF32, a, lin, out_f16=True)
     assert torch.equal(got, full.half())
+
+
+@pytest.mark.parametrize("cg", ["1", "2"])
+@pytest.mark.parametrize("M", [129, 777, 1024, 40 * 128 + 5])
+def test_gemm_cta_pairs(cg, M, monkeypatch):
+    """cta_group::2 (256-row pair tiles, W rows split across the pair) against single-CTA tiles: every kind, odd and even
+    numbers of 128-row tiles (a tail pair is half empty), bias / ReLU / residual epilogues, plane outputs."""
+    from qa_tiger_b200 import _cabi
+    monkeypatch.setenv("QAT_GEMM_CG", cg)
+    N, K = 768, 320
+    g = torch.Generator(device="cuda").manual_seed(M)
+    a = torch.randn(M, K, device=dev(), generator=g)
+    w = torch.randn(N, K, device=dev(), generator=g) * K ** -0.5
+    b = torch.randn(N, device=dev(), generator=g)
+    res = torch.randn(M, N, device=dev(), generator=g)
+    lin = _cabi.Lin(w, b, _cabi.PREC_BF16, f16=True)
+    ref = a.double() @ w.double().t() + b.double()
+    ref2 = torch.relu(ref) + res.double()
+    for kind, tol in ((_cabi.GEMM_TF32, 1.5e-3), (2, 2e-5)):
+        assert relerr(_cabi.gemm(kind, a, lin), ref) < tol
+        got2, (hi, lo) = _cabi.gemm(kind, a, lin, relu=True, res=res, out_planes=True)
+        assert relerr(got2, ref2) < tol
+        assert torch.equal(hi, got2.to(torch.bfloat16))
+    ah = a.half()
+    refh = ah.double() @ lin.h.double().t() + b.double()
+    got = _cabi.gemm(_cabi.GEMM_F16, ah, lin)
+    assert relerr(got, refh) < 2e-6
+    assert torch.equal(_cabi.gemm(_cabi.GEMM_F16, ah, lin, out_f16=True), got.half())
+    rh = res.half()
+    got3 = _cabi.gemm(_cabi.GEMM_F16, ah, lin, relu=True, res=rh)
+    assert torch.equal(_cabi.gemm(_cabi.GEMM_F16, ah, lin, relu=True, res=rh, out_f16=True), got3.half())
