@@ -84,8 +84,9 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
+  // producer and MMA loops run warp-uniform, one elected lane issues (operands stay in uniform registers; gemm_tc.cuh)
   if (warp == 0) {
-    if (lane == 0) {
+    {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int m0 = (t / H) * RPT, h = t % H;
@@ -93,17 +94,20 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
           const int s = it % GA_STAGES;
           mbar_wait(&empty[s], ((it / GA_STAGES) & 1) ^ 1);
           unsigned char* st = tiles + s * GA_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], GA_STAGE_BYTES);
           const int k0 = kb * 64;
-          tma_load_2d(st, &mA, &full[s], k0, m0);
-          tma_load_2d(st + GA_A_BYTES, &mW, &full[s], k0, h * 64);
-          tma_load_2d(st + GA_A_BYTES + 8192, &mW, &full[s], k0, D + h * 64);
-          tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&full[s], GA_STAGE_BYTES);
+            tma_load_2d(st, &mA, &full[s], k0, m0);
+            tma_load_2d(st + GA_A_BYTES, &mW, &full[s], k0, h * 64);
+            tma_load_2d(st + GA_A_BYTES + 8192, &mW, &full[s], k0, D + h * 64);
+            tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc = umma_idesc(0, 128, GA_BN);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
@@ -117,11 +121,15 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a0 = smem_u32(tiles + s * GA_STAGE_BYTES);
           const uint64_t dA = umma_desc(a0), dW = umma_desc(a0 + GA_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma<KIND_F16>(tacc, dA + uint64_t(k * 2), dW + uint64_t(k * 2), idesc, (kb | k) != 0);
-          umma_commit(&empty[s]);
+            for (int k = 0; k < 4; ++k) umma<KIND_F16>(tacc, dA + uint64_t(k * 2), dW + uint64_t(k * 2), idesc, (kb | k) != 0);
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
         }
-        umma_commit(&tfull[as]);
+        if (elect_one()) umma_commit(&tfull[as]);
+        __syncwarp();
       }
     }
   } else {

@@ -61,6 +61,15 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
+// one elected lane of a converged warp (the same lane on every call with the full mask).  The producer and MMA loops run
+// warp-uniform with only the asynchronous instruction under this predicate: their operands then stay in uniform registers
+// (UTCHMMA / UTMALDG straight from URs) instead of going through a per-instruction ELECT + R2UR + retry loop, which made
+// the single-thread MMA issue stream (~110 SASS instructions per k-block) the pacing item next to a busy epilogue.
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred;
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -259,8 +268,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
       uint32_t it = 0;                                   // running k-block counter across tiles
       for (int t = unit0; t < ntiles; t += nunits) {
         const int m0 = ((t / tiles_n) * CG + (int)crank) * G::BM, n0 = (t % tiles_n) * BN + (int)crank * G::BN_CTA;
@@ -272,25 +281,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           const int k0 = kb * G::BK;
           if (CG == 2) {
             // both CTAs' bytes are counted on the leader's barrier (armed by the leader alone, for the pair)
-            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * G::STAGE_BYTES);
             const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);
-            tma_load_2d_pair(st, &mA0, fb, k0, m0);
-            if (G::PLANES == 2) tma_load_2d_pair(st + G::A_BYTES, &mA1, fb, k0, m0);
-            tma_load_2d_pair(st + G::PLANES * G::A_BYTES, &mW0, fb, k0, n0);
-            if (G::PLANES == 2) tma_load_2d_pair(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, fb, k0, n0);
-          } else {
+            if (elect_one()) {
+              if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * G::STAGE_BYTES);
+              tma_load_2d_pair(st, &mA0, fb, k0, m0);
+              if (G::PLANES == 2) tma_load_2d_pair(st + G::A_BYTES, &mA1, fb, k0, m0);
+              tma_load_2d_pair(st + G::PLANES * G::A_BYTES, &mW0, fb, k0, n0);
+              if (G::PLANES == 2) tma_load_2d_pair(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, fb, k0, n0);
+            }
+          } else if (elect_one()) {
             mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
             tma_load_2d(st, &mA0, &full[s], k0, m0);
             if (G::PLANES == 2) tma_load_2d(st + G::A_BYTES, &mA1, &full[s], k0, m0);
             tma_load_2d(st + G::PLANES * G::A_BYTES, &mW0, &full[s], k0, n0);
             if (G::PLANES == 2) tma_load_2d(st + G::PLANES * G::A_BYTES + G::W_BYTES, &mW1, &full[s], k0, n0);
           }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && crank == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    if (crank == 0) {
       constexpr uint32_t idesc = umma_idesc(KIND == KIND_TF32 ? 2 : (KIND == KIND_BF16X3 ? 1 : 0), G::BM * CG, BN);
       uint32_t it = 0, lt = 0;                           // lt = local tile counter
       for (int t = unit0; t < ntiles; t += nunits, ++lt) {
@@ -309,25 +321,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           const uint32_t w0 = a0 + G::PLANES * G::A_BYTES;
           const uint64_t dA0 = umma_desc(a0), dW0 = umma_desc(w0);
           const uint64_t dA1 = umma_desc(a0 + G::A_BYTES), dW1 = umma_desc(w0 + G::W_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < G::BK / G::UK; ++k) {
-            if (p.dbg & 2) break;
-            const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
-            if (G::PLANES == 1) {
-              umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
-            } else {
-              umma<KIND, CG>(tacc, dA1 + adv, dW0 + adv, idesc, (kb | k) != 0);    // lo * hi
-              umma<KIND, CG>(tacc, dA0 + adv, dW1 + adv, idesc, 1);                // hi * lo
-              umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, 1);                // hi * hi
+            for (int k = 0; k < G::BK / G::UK; ++k) {
+              if (p.dbg & 2) break;
+              const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
+              if (G::PLANES == 1) {
+                umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
+              } else {
+                umma<KIND, CG>(tacc, dA1 + adv, dW0 + adv, idesc, (kb | k) != 0);    // lo * hi
+                umma<KIND, CG>(tacc, dA0 + adv, dW1 + adv, idesc, 1);                // hi * lo
+                umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, 1);                // hi * hi
+              }
             }
+            // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
+            if (CG == 2) umma_commit_pair(&empty[s]);
+            else umma_commit(&empty[s]);
           }
-          // smem slot reusable once these MMAs have read it (in both CTAs of a pair)
-          if (CG == 2) umma_commit_pair(&empty[s]);
-          else umma_commit(&empty[s]);
+          __syncwarp();
         }
-        // accumulator complete
-        if (CG == 2) umma_commit_pair(&tfull[as]);
-        else umma_commit(&tfull[as]);
+        // accumulator complete (tcgen05.commit covers the MMAs of the issuing thread: the same elected lane)
+        if (elect_one()) {
+          if (CG == 2) umma_commit_pair(&tfull[as]);
+          else umma_commit(&tfull[as]);
+        }
+        __syncwarp();
       }
     }
   } else {
@@ -368,18 +386,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         }
         continue;
       }
+      // the TMEM load of chunk c + 1 is issued as soon as chunk c has left its registers, so it is in flight while chunk c
+      // is packed, parked in shared memory and handed to the TMA unit
+      uint32_t v[32];
+      if (n0 + half * HALF_N < p.N) tmem_ld32(tacc, v);
 #pragma unroll 1
       for (int c = 0; c < NCH; ++c) {
         const int col0 = n0 + half * HALF_N + c * 32;
         const bool live = col0 < p.N;                       // warp-uniform
-        uint32_t v[32];
-        if (live) tmem_ld32(tacc + uint32_t(c * 32), v);
         if (live && p.tma_res) {
           // fp16 residual box (32 rows x 32 columns, 64B swizzle) into the upper half of the warp's slot; rows / columns
           // beyond the matrix are zero-filled by the TMA unit
           // (the previous chunk's lanes finished reading this half before their fence.proxy.async + __syncwarp below;
           //  the output box is the lower half, so an in-flight store of the previous chunk does not touch it)
-          if (lane == 0) {
+          if (elect_one()) {
             mbar_arrive_expect_tx(&rbar[ew], 2048);
             tma_load_2d(box + 2048, &mR, &rbar[ew], col0, m0 + lg * 32);
           }
@@ -410,6 +430,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           }
         }
         if (live) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        float x[32];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          x[4 * q] = __uint_as_float(v[4 * q]) + bb[q].x;
+          x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb[q].y;
+          x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb[q].z;
+          x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb[q].w;
+        }
+        if (c + 1 < NCH && col0 + 32 < p.N) tmem_ld32(tacc + uint32_t((c + 1) * 32), v);
         if (c == NCH - 1) {
           // last TMEM read of this tile by this warp: hand the accumulator back to the MMA warp
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -419,14 +448,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           }
         }
         if (!live) continue;
-        float x[32];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          x[4 * q] = __uint_as_float(v[4 * q]) + bb[q].x;
-          x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb[q].y;
-          x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb[q].z;
-          x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb[q].w;
-        }
         if (p.epi.relu == 1) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) x[e] = fmaxf(x[e], 0.f);
@@ -452,7 +473,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         }
         const int crow = m0 + lg * 32;
         if (out_f) {
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the box is free again
+          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the box is free again
           __syncwarp();
 #pragma unroll
           for (uint32_t q = 0; q < 8; ++q)
@@ -460,13 +481,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                    __float_as_uint(x[4 * q + 2]), __float_as_uint(x[4 * q + 3]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 4)) {
+          if (elect_one() && !(p.dbg & 4)) {
             tma_store_2d(&mCf, box, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
         if (out_hi) {
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           __syncwarp();
 #pragma unroll
           for (uint32_t q = 0; q < 4; ++q) {
@@ -485,7 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 4)) {
+          if (elect_one() && !(p.dbg & 4)) {
             tma_store_2d(&mChi, box, col0, crow);
             if (out_lo) tma_store_2d(&mClo, box + 2048, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -495,7 +516,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           // an fp16 box is 2 KB: when it is the only plane the two halves of the warp's 4 KB slot alternate
           const bool solo = !out_f && !out_hi && !p.tma_res;
           const uint32_t hb = solo ? uint32_t(c & 1) * 2048u : 0u;
-          if (lane == 0) {
+          if (elect_one()) {
             if (solo) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
             else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           }
@@ -506,14 +527,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                    pack_half2(x[8 * q + 4], x[8 * q + 5]), pack_half2(x[8 * q + 6], x[8 * q + 7]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (lane == 0 && !(p.dbg & 4)) {
+          if (elect_one() && !(p.dbg & 4)) {
             tma_store_2d(&mCh, box + hb, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
         }
       }
     }
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
