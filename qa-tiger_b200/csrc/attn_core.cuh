@@ -23,6 +23,14 @@ struct AttnP {
   int nseq, H, Lq, Lk;
   float scale;
   int causal = 0;        // 1: key j attends only to queries i >= j (CLIP text tower; attn_mma16_kernel only)
+  // optional: Q / K / V as fp16 (hi, lo) plane pairs written by the in-projection GEMM (same strides, in elements); when
+  // set, q / k / v are ignored and the call runs on attn_mma16p_kernel
+  const __half* qh = nullptr;
+  const __half* ql = nullptr;
+  const __half* kh = nullptr;
+  const __half* kl = nullptr;
+  const __half* vh = nullptr;
+  const __half* vl = nullptr;
 };
 
 constexpr int HD = 64;
@@ -628,14 +636,6 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], u
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits
-__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half2 h = __floats2half2_rn(a, b);
-  const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
-  hi = *reinterpret_cast<const uint32_t*>(&h);
-  lo = *reinterpret_cast<const uint32_t*>(&l);
-}
 // D += (ah + al) (bh + bl) without the lo*lo term
 __device__ __forceinline__ void mma3_f16(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], uint32_t bh0, uint32_t bh1,
                                          uint32_t bl0, uint32_t bl1) {
@@ -646,11 +646,18 @@ __device__ __forceinline__ void mma3_f16(float (&d)[4], const uint32_t (&ah)[4],
 
 // ---- tensor-core core for the 60..128-token sequences of AVQCrossAttn, second generation --------------------
 // mma.sync m16n8k16 on fp16 (hi, lo) pairs (x = hi + lo keeps 22 bits: fp32-faithful, the serial chain into the
-// router needs it): K and V are split ONCE while they are staged into shared memory (fp16 planes,
-// 144-byte rows: conflict-free ldmatrix), Q is split in registers straight from global memory, P never leaves
-// registers (the S accumulator fragments of two key tiles are exactly the A fragment of one P*V k-step).
+// router needs it).  K and V sit in shared memory as fp16 planes (144-byte rows: conflict-free ldmatrix),
+// P never leaves registers (the S accumulator fragments of two key tiles are exactly the A fragment of one P*V k-step).
 // One CTA (4 warps) per (sequence, head); warp w owns query rows 16w..16w+15 of each 64-row pass.
-template <int NT16>   // key tiles of 16: Lk <= 16*NT16
+//   PL = false: fp32 operands; K / V are split ONCE while they are staged, Q is split in registers (fp32 mode, the exported
+//               qat_attention_fwd, the text tower);
+//   PL = true : the operands ARRIVE as fp16 (hi, lo) plane pairs written by the in-projection GEMM's epilogue (same bytes
+//               as fp32): K / V are 16-byte async copies, Q fragments 32-bit loads issued while those are in flight -- one
+//               memory round trip per CTA, no conversion work.
+// The kernel is issue / latency bound (ncu: 2 460 warp instructions per warp, 51 % issue utilisation, tensor pipe 32 %), so
+// the softmax multiplies by one reciprocal per row instead of dividing every element, masks only the key tiles that reach
+// past the limit, and the output addresses are formed once per row.
+template <int NT16, bool PL>   // key tiles of 16: Lk <= 16*NT16
 __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
   extern __shared__ __align__(16) unsigned char smraw[];
   constexpr int LKP = 16 * NT16, RSB = 144;              // padded key count, row stride in bytes (72 halves)
@@ -663,64 +670,105 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
   const int kn = (n + p.k_shift) % p.k_mod;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  const float* kb = p.k + kn * p.k_sn + h * HD;
-  const float* vb = p.v + kn * p.k_sn + h * HD;
-  // staging in batches of 4 iterations: all 8 loads of a batch are issued before the first is consumed (the kernel is
-  // latency-bound: every exposed global-load round trip costs as much as the whole MMA work of the CTA; prefetching the
-  // Q fragments as well was measured slower -- it costs the fourth resident CTA)
-  constexpr int ITERS = LKP * 16 / 128;
+  if constexpr (PL) {
+    const long long kbase = kn * p.k_sn + h * HD;
+    const __half* kbh = p.kh + kbase;
+    const __half* kbl = p.kl + kbase;
+    const __half* vbh = p.vh + kbase;
+    const __half* vbl = p.vl + kbase;
+    for (int f = tid; f < LKP * 8; f += 128) {
+      const int j = f >> 3, c8 = f & 7;
+      const bool ok = j < Lk;                              // rows beyond Lk are zero-filled
+      const long long off = ok ? j * p.k_si + c8 * 8 : 0;
+      cp_async16_zfill(Kh + j * RSB + c8 * 16, kbh + off, ok);
+      cp_async16_zfill(Kl + j * RSB + c8 * 16, kbl + off, ok);
+      cp_async16_zfill(Vh + j * RSB + c8 * 16, vbh + off, ok);
+      cp_async16_zfill(Vl + j * RSB + c8 * 16, vbl + off, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  } else {
+    const float* kb = p.k + kn * p.k_sn + h * HD;
+    const float* vb = p.v + kn * p.k_sn + h * HD;
+    // staging in batches of 4 iterations: all 8 loads of a batch are issued before the first is consumed (prefetching the
+    // Q fragments as well was measured slower -- it costs the fourth resident CTA)
+    constexpr int ITERS = LKP * 16 / 128;
 #pragma unroll
-  for (int it0 = 0; it0 < ITERS; it0 += 4) {
-    float4 kv[4], vv[4];
+    for (int it0 = 0; it0 < ITERS; it0 += 4) {
+      float4 kv[4], vv[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int f = tid + (it0 + u) * 128;
-      const int j = f >> 4, c4 = f & 15;
-      kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      vv[u] = kv[u];
-      if (it0 + u < ITERS && j < Lk) {
-        kv[u] = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
-        vv[u] = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+      for (int u = 0; u < 4; ++u) {
+        const int f = tid + (it0 + u) * 128;
+        const int j = f >> 4, c4 = f & 15;
+        kv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        vv[u] = kv[u];
+        if (it0 + u < ITERS && j < Lk) {
+          kv[u] = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
+          vv[u] = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (it0 + u >= ITERS) break;
+        const int f = tid + (it0 + u) * 128;
+        const int j = f >> 4, c4 = f & 15;
+        uint2 hi, lo;
+        split_half2(kv[u].x, kv[u].y, hi.x, lo.x);
+        split_half2(kv[u].z, kv[u].w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(Kh + j * RSB + c4 * 8) = hi;
+        *reinterpret_cast<uint2*>(Kl + j * RSB + c4 * 8) = lo;
+        split_half2(vv[u].x, vv[u].y, hi.x, lo.x);
+        split_half2(vv[u].z, vv[u].w, hi.y, lo.y);
+        *reinterpret_cast<uint2*>(Vh + j * RSB + c4 * 8) = hi;
+        *reinterpret_cast<uint2*>(Vl + j * RSB + c4 * 8) = lo;
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      if (it0 + u >= ITERS) break;
-      const int f = tid + (it0 + u) * 128;
-      const int j = f >> 4, c4 = f & 15;
-      uint2 hi, lo;
-      split_half2(kv[u].x, kv[u].y, hi.x, lo.x);
-      split_half2(kv[u].z, kv[u].w, hi.y, lo.y);
-      *reinterpret_cast<uint2*>(Kh + j * RSB + c4 * 8) = hi;
-      *reinterpret_cast<uint2*>(Kl + j * RSB + c4 * 8) = lo;
-      split_half2(vv[u].x, vv[u].y, hi.x, lo.x);
-      split_half2(vv[u].z, vv[u].w, hi.y, lo.y);
-      *reinterpret_cast<uint2*>(Vh + j * RSB + c4 * 8) = hi;
-      *reinterpret_cast<uint2*>(Vl + j * RSB + c4 * 8) = lo;
-    }
+    __syncthreads();
   }
-  __syncthreads();
+  bool staged = !PL;
   const uint32_t sKh = tc::smem_u32(Kh), sKl = tc::smem_u32(Kl), sVh = tc::smem_u32(Vh), sVl = tc::smem_u32(Vl);
   const int m8 = lane >> 3, r8 = lane & 7;
   const uint32_t koff = uint32_t((r8 + (m8 >> 1) * 8) * RSB + (m8 & 1) * 16);   // + np*16 rows, + ks*32 bytes
   const uint32_t voff = uint32_t((r8 + (m8 & 1) * 8) * RSB + (m8 >> 1) * 16);   // + kk*16 rows, + dp*32 bytes
   const float invH = 1.f / p.H;
-  for (int r0 = warp * 16; r0 < Lq; r0 += 64) {
-    // ---- Q fragments (pre-scaled), rows r0+g / r0+g+8 ----
+  // PL: every warp passes the staging barrier exactly once, inside its first pass (a warp without query rows still takes it)
+  for (int r0 = warp * 16; r0 < Lq || !staged; r0 += 64) {
+    // ---- Q fragments, rows r0+g / r0+g+8 ----
     const int i0 = r0 + g, i1 = r0 + g + 8;
-    const float* q0 = p.q + n * p.q_sn + (long long)min(i0, Lq - 1) * p.q_si + h * HD + 2 * t;
-    const float* q1 = p.q + n * p.q_sn + (long long)min(i1, Lq - 1) * p.q_si + h * HD + 2 * t;
     uint32_t qh[4][4], ql[4][4];
+    if constexpr (PL) {
+      // the scale (a power of two on this path) is applied to S
+      const long long qo0 = n * p.q_sn + (long long)min(i0, Lq - 1) * p.q_si + h * HD + 2 * t;
+      const long long qo1 = n * p.q_sn + (long long)min(i1, Lq - 1) * p.q_si + h * HD + 2 * t;
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const float2 a0 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16));
-      const float2 a1 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16));
-      const float2 a2 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16 + 8));
-      const float2 a3 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16 + 8));
-      split_half2(a0.x * p.scale, a0.y * p.scale, qh[ks][0], ql[ks][0]);
-      split_half2(a1.x * p.scale, a1.y * p.scale, qh[ks][1], ql[ks][1]);
-      split_half2(a2.x * p.scale, a2.y * p.scale, qh[ks][2], ql[ks][2]);
-      split_half2(a3.x * p.scale, a3.y * p.scale, qh[ks][3], ql[ks][3]);
+      for (int ks = 0; ks < 4; ++ks) {
+        qh[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(p.qh + qo0 + ks * 16));
+        qh[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(p.qh + qo1 + ks * 16));
+        qh[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(p.qh + qo0 + ks * 16 + 8));
+        qh[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(p.qh + qo1 + ks * 16 + 8));
+        ql[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(p.ql + qo0 + ks * 16));
+        ql[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(p.ql + qo1 + ks * 16));
+        ql[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(p.ql + qo0 + ks * 16 + 8));
+        ql[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(p.ql + qo1 + ks * 16 + 8));
+      }
+      if (!staged) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+        staged = true;
+      }
+    } else {
+      const float* q0 = p.q + n * p.q_sn + (long long)min(i0, Lq - 1) * p.q_si + h * HD + 2 * t;
+      const float* q1 = p.q + n * p.q_sn + (long long)min(i1, Lq - 1) * p.q_si + h * HD + 2 * t;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const float2 a0 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16));
+        const float2 a1 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16));
+        const float2 a2 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16 + 8));
+        const float2 a3 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16 + 8));
+        split_half2(a0.x * p.scale, a0.y * p.scale, qh[ks][0], ql[ks][0]);
+        split_half2(a1.x * p.scale, a1.y * p.scale, qh[ks][1], ql[ks][1]);
+        split_half2(a2.x * p.scale, a2.y * p.scale, qh[ks][2], ql[ks][2]);
+        split_half2(a3.x * p.scale, a3.y * p.scale, qh[ks][3], ql[ks][3]);
+      }
     }
     // ---- S = Q K^T ----
     float s[2 * NT16][4];
@@ -742,13 +790,19 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
     // ---- softmax over the two rows this thread shares with its quad ----
     float mx0 = -INFINITY, mx1 = -INFINITY;
     const int lim0 = p.causal ? min(Lk, i0 + 1) : Lk, lim1 = p.causal ? min(Lk, i1 + 1) : Lk;
+    const int lim_min = p.causal ? min(Lk, r0 + 1) : Lk;     // warp-uniform: key tiles wholly below it need no mask
 #pragma unroll
     for (int nt = 0; nt < 2 * NT16; ++nt) {
-      const int c = nt * 8 + 2 * t;
-      if (c >= lim0) s[nt][0] = -INFINITY;
-      if (c >= lim1) s[nt][2] = -INFINITY;
-      if (c + 1 >= lim0) s[nt][1] = -INFINITY;
-      if (c + 1 >= lim1) s[nt][3] = -INFINITY;
+      if constexpr (PL) {
+        s[nt][0] *= p.scale; s[nt][1] *= p.scale; s[nt][2] *= p.scale; s[nt][3] *= p.scale;
+      }
+      if (nt * 8 + 8 > lim_min) {
+        const int c = nt * 8 + 2 * t;
+        if (c >= lim0) s[nt][0] = -INFINITY;
+        if (c >= lim1) s[nt][2] = -INFINITY;
+        if (c + 1 >= lim0) s[nt][1] = -INFINITY;
+        if (c + 1 >= lim1) s[nt][3] = -INFINITY;
+      }
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -770,9 +824,10 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
     s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
     s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float r0inv = 1.f / s0, r1inv = 1.f / s1;        // one reciprocal per row (<= 1 ulp from the per-element division)
 #pragma unroll
     for (int nt = 0; nt < 2 * NT16; ++nt) {
-      s[nt][0] /= s0; s[nt][1] /= s0; s[nt][2] /= s1; s[nt][3] /= s1;
+      s[nt][0] *= r0inv; s[nt][1] *= r0inv; s[nt][2] *= r1inv; s[nt][3] *= r1inv;
     }
     if (p.attw) {
       float* w0 = p.attw + ((long long)n * Lq + i0) * Lk;
@@ -808,34 +863,48 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
         mma3_f16(o[2 * dp + 1], ph, pl, bh[2], bh[3], bl[2], bl[3]);
       }
     }
+    // the row's output planes, advanced to (row, h*64 + 2t) once: the eight stores of a row differ by a constant column
+    if (i0 < Lq) {
+      const Act orow = p.o.rows(n * p.o_rn + i0 * p.o_ri).cols(h * HD + 2 * t);
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      const int col = h * HD + dt * 8 + 2 * t;
-      if (i0 < Lq) act_store2(p.o, n * p.o_rn + i0 * p.o_ri, col, o[dt][0], o[dt][1]);
-      if (i1 < Lq) act_store2(p.o, n * p.o_rn + i1 * p.o_ri, col, o[dt][2], o[dt][3]);
+      for (int dt = 0; dt < 8; ++dt) act_store2(orow, 0, dt * 8, o[dt][0], o[dt][1]);
+    }
+    if (i1 < Lq) {
+      const Act orow = p.o.rows(n * p.o_rn + i1 * p.o_ri).cols(h * HD + 2 * t);
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) act_store2(orow, 0, dt * 8, o[dt][2], o[dt][3]);
     }
   }
 }
 
-template <int NT16>
+template <int NT16, bool PL>
 inline int attn_mma16_launch(Ctx& c, const AttnP& p) {
   const size_t smem = (size_t)4 * 16 * NT16 * 144;
-  auto kern = attn_mma16_kernel<NT16>;
+  auto kern = attn_mma16_kernel<NT16, PL>;
   if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
   return check_launch("attn_mma16_kernel");
+}
+template <bool PL>
+inline int attn_mma16_dispatch(Ctx& c, const AttnP& p) {
+  if (p.Lk <= 64) return attn_mma16_launch<4, PL>(c, p);
+  if (p.Lk <= 80) return attn_mma16_launch<5, PL>(c, p);
+  if (p.Lk <= 96) return attn_mma16_launch<6, PL>(c, p);
+  return attn_mma16_launch<8, PL>(c, p);
 }
 
 inline int attention(Ctx& c, const AttnP& p) {
   QAT_REQUIRE(p.Lk >= 1 && p.Lk <= 128, "attention: key length %d outside [1,128]", p.Lk);
   QAT_REQUIRE(p.Lq >= 1 && p.nseq >= 0 && p.H >= 1, "attention: bad shape");
   if (c.dry || p.nseq == 0) return QAT_OK;
+  if (p.qh) {
+    QAT_REQUIRE(p.ql && p.kh && p.kl && p.vh && p.vl, "attention: fp16 plane pairs need all six planes");
+    QAT_REQUIRE(p.q_si % 8 == 0 && p.k_si % 8 == 0 && p.q_sn % 8 == 0 && p.k_sn % 8 == 0, "attention: plane strides must be multiples of 8 elements");
+    return attn_mma16_dispatch<true>(c, p);
+  }
   if (p.causal) {
     QAT_REQUIRE(p.attw == nullptr, "attention: causal attention has no weights output");
-    if (p.Lk <= 64) return attn_mma16_launch<4>(c, p);
-    if (p.Lk <= 80) return attn_mma16_launch<5>(c, p);
-    if (p.Lk <= 96) return attn_mma16_launch<6>(c, p);
-    return attn_mma16_launch<8>(c, p);
+    return attn_mma16_dispatch<false>(c, p);
   }
   if (p.Lq <= 2 && p.attw == nullptr) {
     const long long probs = (long long)p.nseq * p.H;
@@ -854,10 +923,7 @@ inline int attention(Ctx& c, const AttnP& p) {
   if (p.Lk > 32 || p.Lq >= 32) {
     const char* ffma = getenv("QAT_ATTN_FFMA");     // A/B switches: 1 = register-tiled FFMA core, 2 = 3xTF32 m16n8k8 core
     if (!ffma || ffma[0] == '0') {
-      if (p.Lk <= 64) return attn_mma16_launch<4>(c, p);
-      if (p.Lk <= 80) return attn_mma16_launch<5>(c, p);
-      if (p.Lk <= 96) return attn_mma16_launch<6>(c, p);
-      return attn_mma16_launch<8>(c, p);
+      return attn_mma16_dispatch<false>(c, p);
     }
     if (ffma[0] == '2') {
       if (p.Lk <= 64) return attn_mma_launch<8>(c, p);

@@ -148,10 +148,6 @@ constexpr int SMALL_BK = 32;
 constexpr int SMALL_LD = 36;   // floats per staged row (32 + 4 pad: rows r, r+1, .. land 4 banks apart)
 constexpr int SMALL_SMEM = SMALL_KG * SMALL_NS * 2 * 32 * SMALL_LD * 4;
 
-__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
-  const int n = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled, the source is not read
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(n) : "memory");
-}
 
 __global__ void __launch_bounds__(64 * SMALL_KG) gemm_small_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw,
                                                                     Epi epi, Act C, int M, int N, int K) {

@@ -164,6 +164,7 @@ struct GemmP {
   int M, N, K;
   Epi epi;
   Act C;
+  int pair_f16;    // 1: the (hi, lo) output pair is fp16 (Act::ph / pl, through the mChi / mClo maps) instead of bf16
   int tma_res;     // 1: the fp16 residual (epi.res_h) arrives through the mR tensor map into the warp's box (fp16-only output)
   int dbg;         // profiling switches (QAT_GEMM_DBG): 1 = epilogue releases the accumulator without reading it,
                    // 2 = MMA issuer skips the MMAs, 4 = epilogue skips its global stores
@@ -354,8 +355,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     // Per 32-column chunk: tcgen05.ld (lane = row) -> bias / ReLU / residual in registers -> the warp's 32 x 32 box in
     // shared memory in the TMA swizzle layout -> one lane issues cp.async.bulk.tensor stores (one per output plane);
     // the TMA unit clips row / column tails, so the LSU never sees the (row-strided) output.
-    const bool out_f = EPI == 0 ? p.C.f != nullptr : EPI == 2, out_hi = EPI == 0 ? p.C.hi != nullptr : EPI == 3;
-    const bool out_lo = EPI == 0 ? p.C.lo != nullptr : EPI == 3, out_h = EPI == 0 ? p.C.h != nullptr : EPI == 1;
+    const bool out_f = EPI == 0 ? p.C.f != nullptr : EPI == 2, out_hi = EPI == 0 ? (p.C.hi != nullptr || p.C.ph != nullptr) : EPI == 3;
+    const bool out_lo = EPI == 0 ? (p.C.lo != nullptr || p.C.pl != nullptr) : EPI == 3, out_h = EPI == 0 ? p.C.h != nullptr : EPI == 1;
     const float* const res_f = EPI == 1 ? nullptr : p.epi.res;
     const __half* const res_h = (EPI == 1 && !p.tma_res) ? nullptr : p.epi.res_h;
     const int ew = warp - 2;
@@ -492,6 +493,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 #pragma unroll
           for (uint32_t q = 0; q < 4; ++q) {
             uint32_t hw[4], lw[4];
+            if (p.pair_f16) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) split_half2(x[8 * q + 2 * e], x[8 * q + 2 * e + 1], hw[e], lw[e]);
+            } else
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               bf16 h0, h1, l0, l1;
@@ -614,20 +619,26 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
     mA1 = mA0;
     mW1 = mW0;
   }
-  QAT_REQUIRE(C.f || C.hi || C.h, "gemm_tc: no output plane");
+  QAT_REQUIRE(C.f || C.hi || C.h || C.ph, "gemm_tc: no output plane");
   QAT_REQUIRE(!C.lo || C.hi, "gemm_tc: a lo plane needs its hi plane");
+  QAT_REQUIRE((C.ph != nullptr) == (C.pl != nullptr) && !(C.ph && C.hi), "gemm_tc: the fp16 pair needs both planes and excludes the bf16 pair");
   mCf = mChi = mClo = mCh = mA0;
   if (C.f) QAT_TRY(make_store_map(&mCf, C.f, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, M, N, C.ld));
   if (C.hi) QAT_TRY(make_store_map(&mChi, C.hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
   if (C.lo) QAT_TRY(make_store_map(&mClo, C.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
   if (C.h) QAT_TRY(make_store_map(&mCh, C.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
+  if (C.ph) {
+    QAT_TRY(make_store_map(&mChi, C.ph, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
+    QAT_TRY(make_store_map(&mClo, C.pl, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
+  }
   GemmP p;
+  p.pair_f16 = C.ph ? 1 : 0;
   p.M = (int)M; p.N = N; p.K = K; p.epi = epi; p.C = C;
   // fp16 residual next to an fp16-only output: through the TMA unit as well (lane-per-row LSU loads of a row-strided
   // residual cost 32 L1 wavefronts per instruction and made the PatchSelecter out-proj epilogue-bound)
   mR = mA0;
   p.tma_res = 0;
-  if (epi.res_h && !epi.res && C.h && !C.f && !C.hi && (reinterpret_cast<uintptr_t>(epi.res_h) & 15) == 0 && epi.ldr % 8 == 0) {
+  if (epi.res_h && !epi.res && C.h && !C.f && !C.hi && !C.ph && (reinterpret_cast<uintptr_t>(epi.res_h) & 15) == 0 && epi.ldr % 8 == 0) {
     QAT_TRY(make_store_map(&mR, epi.res_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, epi.ldr));
     p.tma_res = 1;
   }
@@ -641,9 +652,9 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   const long long units = sms / CG;
   const unsigned grid = (unsigned)(ntiles < units ? ntiles : units) * CG;
   int mode = 0;
-  if (KIND != KIND_BF16X3 && C.h && !C.f && !C.hi && !epi.res && (!epi.res_h || p.tma_res)) mode = 1;
-  else if (C.f && !C.hi && !C.lo && !C.h) mode = 2;
-  else if (KIND == KIND_BF16X3 && C.hi && C.lo && !C.f && !C.h) mode = 3;
+  if (KIND != KIND_BF16X3 && C.h && !C.f && !C.hi && !C.ph && !epi.res && (!epi.res_h || p.tma_res)) mode = 1;
+  else if (C.f && !C.hi && !C.lo && !C.h && !C.ph) mode = 2;
+  else if (KIND == KIND_BF16X3 && ((C.hi && C.lo) || C.ph) && !C.f && !C.h) mode = 3;
 #define QAT_GEMM_LAUNCH(EPI_)                                                                                 \
   do {                                                                                                        \
     auto kern = gemm_tc_kernel<KIND, BN, STAGES, EPI_, CG>;                                                   \

@@ -98,6 +98,7 @@ static int gemm(Ctx& c, GemmKind kind, const Act& A, long long M, const WView& W
   switch (kind) {
     case G_SIMT:
       QAT_REQUIRE(c.dry || A.f, "gemm: fp32 operand missing");
+      QAT_REQUIRE(!C.ph, "gemm: the fp16 (hi, lo) output pair is written by the tcgen05 epilogue only");
       return gemm_simt(c, A.f, A.ld, M, W.w, W.n, W.k, epi, C);
     case G_TF32:
       QAT_REQUIRE(c.dry || A.f, "gemm: fp32 operand missing");
@@ -227,9 +228,17 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
   QAT_TRY(ensure_operand(c, Xv, BT, D, k_src));
   QAT_TRY(ensure_operand(c, Xw, BL, D, k_words));
   // S = in-projections of both modalities, rows [0,BT) audio, [BT,2BT) video; cols as in_src
+  // bf16 mode: the in-projections leave as fp16 (hi, lo) plane pairs (same bytes as fp32), the form the attention cores eat
+  const bool pp = k_src == G_BF16X3 && k_words == G_BF16X3 && D % 8 == 0 &&
+                  !(getenv("QAT_ATTN_FP32_IN") && getenv("QAT_ATTN_FP32_IN")[0] == '1');
   Act S, KVw, O, X1, Hh, Y;
-  QAT_TRY(act_alloc(c, S, 2 * BT, 7 * D, true, false));
-  QAT_TRY(act_alloc(c, KVw, BL, 2 * D, true, false));
+  if (pp) {
+    QAT_TRY(act_alloc_pp(c, S, 2 * BT, 7 * D));
+    QAT_TRY(act_alloc_pp(c, KVw, BL, 2 * D));
+  } else {
+    QAT_TRY(act_alloc(c, S, 2 * BT, 7 * D, true, false));
+    QAT_TRY(act_alloc(c, KVw, BL, 2 * D, true, false));
+  }
   QAT_TRY(gemm(c, k_src, Xa, BT, Wsrc, Epi(), S));
   QAT_TRY(gemm(c, k_src, Xv, BT, Wsrc, Epi(), S.rows(BT)));
   QAT_TRY(gemm(c, k_words, Xw, BL, Wwords, Epi(), KVw));
@@ -241,7 +250,14 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
   p.q_sn = (long long)T * 7 * D; p.q_si = 7 * D;
   p.o_rn = T; p.o_ri = 1;
   // qst: keys/values = words of sample n % B
-  p.q = S.f; p.k = KVw.f; p.v = KVw.f + D; p.k_sn = (long long)L * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B; p.Lk = L;
+  // q / k / v of the three attentions are column slices of S (and of KVw): the same offsets in fp32 or in the plane pairs
+  auto set_q = [&](AttnP& a, long long off) { a.q = pp ? nullptr : S.f + off; a.qh = pp ? S.ph + off : nullptr; a.ql = pp ? S.pl + off : nullptr; };
+  auto set_kv = [&](AttnP& a, const Act& src, long long koff, long long voff) {
+    a.k = pp ? nullptr : src.f + koff; a.v = pp ? nullptr : src.f + voff;
+    a.kh = pp ? src.ph + koff : nullptr; a.kl = pp ? src.pl + koff : nullptr;
+    a.vh = pp ? src.ph + voff : nullptr; a.vl = pp ? src.pl + voff : nullptr;
+  };
+  set_q(p, 0); set_kv(p, KVw, 0, D); p.k_sn = (long long)L * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B; p.Lk = L;
   p.o = O.cols(0); p.attw = nullptr;
   if (attw_audio || attw_video) {
     QAT_REQUIRE(attw_audio && attw_video, "avq: pass both attention-weight outputs or neither");
@@ -250,18 +266,18 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
     pa.nseq = B; pa.attw = attw_audio;
     QAT_TRY(attention(c, pa));
     AttnP pv = p;
-    pv.nseq = B; pv.attw = attw_video; pv.q = S.f + BT * 7 * D; pv.o = O.rows(BT).cols(0);
+    pv.nseq = B; pv.attw = attw_video; set_q(pv, BT * 7 * D); pv.o = O.rows(BT).cols(0);
     QAT_TRY(attention(c, pv));
   } else {
     QAT_TRY(attention(c, p));
   }
   // slf: own keys/values
   p.attw = nullptr;
-  p.q = S.f + D; p.k = S.f + 2 * D; p.v = S.f + 3 * D; p.k_sn = p.q_sn; p.k_si = 7 * D; p.k_shift = 0; p.k_mod = 2 * B; p.Lk = T;
+  set_q(p, D); set_kv(p, S, 2 * D, 3 * D); p.k_sn = p.q_sn; p.k_si = 7 * D; p.k_shift = 0; p.k_mod = 2 * B; p.Lk = T;
   p.o = O.cols(D);
   QAT_TRY(attention(c, p));
   // crs: keys/values of the OTHER modality (direction 2 sees the original audio, modules.py:257-259)
-  p.q = S.f + 4 * D; p.k = S.f + 5 * D; p.v = S.f + 6 * D; p.k_shift = B; p.k_mod = 2 * B;
+  set_q(p, 4 * D); set_kv(p, S, 5 * D, 6 * D); p.k_shift = B; p.k_mod = 2 * B;
   p.o = O.cols(2 * D);
   QAT_TRY(attention(c, p));
   // x1 = LN1(src + [o_qst|o_slf|o_crs] Wout^T + (b_qst+b_slf+b_crs))

@@ -46,13 +46,17 @@ extern thread_local long long g_launches;
 // ------------------------------------------------------------------------------------------------
 // An activation as the kernels see it: fp32 and/or a bf16 (hi, lo) pair and/or one fp16 plane, all with
 // the same leading dimension.  x ~= hi + lo carries 16 mantissa bits, which is what the bf16x3 tensor-core
-// GEMMs eat; the fp16 plane (11 significant bits, round-to-nearest) is the storage format of the patch path.
+// GEMMs eat; the fp16 plane (11 significant bits, round-to-nearest) is the storage format of the patch path; the fp16
+// (ph, pl) pair (x ~= ph + pl, 22 significant bits) is what the mma.sync attention cores on the router path eat -- the
+// in-projection GEMM writes it instead of fp32 (same bytes), so the attention kernel stages K / V with plain async copies.
 // ------------------------------------------------------------------------------------------------
 struct Act {
   float* f = nullptr;
   bf16* hi = nullptr;
   bf16* lo = nullptr;
   __half* h = nullptr;
+  __half* ph = nullptr;
+  __half* pl = nullptr;
   int ld = 0;
   __host__ __device__ Act cols(int c0) const {
     Act a = *this;
@@ -60,6 +64,8 @@ struct Act {
     if (a.hi) a.hi += c0;
     if (a.lo) a.lo += c0;
     if (a.h) a.h += c0;
+    if (a.ph) a.ph += c0;
+    if (a.pl) a.pl += c0;
     return a;
   }
   __host__ __device__ Act rows(long long r0) const {
@@ -68,6 +74,8 @@ struct Act {
     if (a.hi) a.hi += r0 * ld;
     if (a.lo) a.lo += r0 * ld;
     if (a.h) a.h += r0 * ld;
+    if (a.ph) a.ph += r0 * ld;
+    if (a.pl) a.pl += r0 * ld;
     return a;
   }
 };
@@ -78,6 +86,15 @@ __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
 }
 __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
   return __half22float2(*reinterpret_cast<__half2*>(&u));
+}
+
+// x ~= hi + lo with hi = fp16(x), lo = fp16(x - hi): 22 significant bits
+__device__ __forceinline__ void split_half2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
 __device__ __forceinline__ void split_bf16(float v, bf16& hi, bf16& lo) {
@@ -134,6 +151,11 @@ __device__ __forceinline__ void act_store1(const Act& a, long long row, int col,
     if (a.lo) a.lo[off] = l;
   }
   if (a.h) a.h[off] = __float2half_rn(v);
+}
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, bool valid) {
+  const int n = valid ? 16 : 0;   // src-size 0: the 16 destination bytes are zero-filled, the source is not read
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(n) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -260,6 +282,16 @@ inline int act_alloc_h(Ctx& c, Act& a, long long rows, int ld) {
   a.ld = ld;
   a.h = reinterpret_cast<__half*>(c.alloc(size_t(rows) * ld * 2));
   if (!a.h) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+  return QAT_OK;
+}
+
+// an fp16 (hi, lo) pair [rows, ld] (operands of the mma.sync attention cores)
+inline int act_alloc_pp(Ctx& c, Act& a, long long rows, int ld) {
+  a = Act();
+  a.ld = ld;
+  a.ph = reinterpret_cast<__half*>(c.alloc(size_t(rows) * ld * 2));
+  a.pl = reinterpret_cast<__half*>(c.alloc(size_t(rows) * ld * 2));
+  if (!a.ph || !a.pl) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
   return QAT_OK;
 }
 

@@ -38,7 +38,7 @@ def test_projection(sd, prec, rows, k):
 
 
 @pytest.mark.parametrize("prec", PRECS)
-@pytest.mark.parametrize("B,T,L", [(4, 60, 77), (1, 60, 77), (20, 60, 77), (3, 120, 77), (2, 7, 5)])
+@pytest.mark.parametrize("B,T,L", [(4, 60, 77), (1, 60, 77), (20, 60, 77), (3, 120, 77), (2, 7, 5), (10, 120, 77), (40, 30, 100)])
 def test_avq_cross_attn(sd, prec, B, T, L):
     M = _mods()
     m = M.AVQCrossAttn(512, 8)
