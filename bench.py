@@ -431,11 +431,11 @@ def run_ours(args):
                                                "traffic": None, "ms": t_ms, "bytes": byts, "shape": [2 * B, 8, T, T],
                                                "note": "252 MB working set: partly L2-resident between replays"}
             del qa
-            # (3) ToMe 577->14 chain (config 3 shape, 480 frames = 1.1 GB of tokens > L2): frames/s and the stepwise
+            # (3) ToMe 577->14 chain (config 3 shape, 592 frames = 1.4 GB of tokens > L2): frames/s and the stepwise
             #     merge traffic of SURVEY 8d (56.49 MB per frame) over the WHOLE chain time (match kernels included)
             try:
                 from qa_tiger_b200.tome import merge as tm
-                nfr = 480
+                nfr = 592                                  # 4 x 148: the match kernel runs one frame per CTA, one CTA per SM
                 xt = torch.randn(nfr, 577, 1024, device=dev)
                 for _ in range(2):
                     tm.chain(xt)

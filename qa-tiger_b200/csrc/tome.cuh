@@ -150,6 +150,171 @@ __global__ void __launch_bounds__(640) tome_match_kernel(const float* __restrict
   }
 }
 
+// ---- T1, register-tiled -----------------------------------------------------------------------------
+// One CTA per frame.  All t rows are normalised ONCE into shared memory (rows of 68 floats: consecutive rows land 16 bytes
+// apart modulo 128, so a warp's 128-bit reads of 32 consecutive rows are conflict-free), then the ta x tb score matrix is
+// computed in R x 8 register tiles (R = 2, 3 or 4, whichever pads the A rows least): lane l of an A-warp owns rows l, l+32, ..
+// of its 32R-row band and walks one segment of the B rows eight at a time; the B reads of a warp are broadcasts.  4R + 8
+// shared-memory wavefronts per 32R FMA instructions keeps the FMA pipe the bound; the class-token row, whose scores are
+// discarded (merge.py:55), is not computed (the row-per-thread kernel above re-read B once per A row: 1 wavefront per 4
+// FMAs, and spent as long again normalising its A rows twice).  Every score is still ONE sequential FMA chain over the
+// channel index and the winners are compared in ascending j, so the indices are bit-identical to the reference's.
+constexpr int TM_LD = 68;
+
+template <int C, int R>
+__global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __restrict__ metric, int t, int r, int class_token, int nseg,
+                                                               int seg_len, int* __restrict__ unm_idx, int* __restrict__ src_idx,
+                                                               int* __restrict__ dst_idx) {
+  static_assert(C == 64, "metric channels");
+  extern __shared__ __align__(16) float smem[];
+  const int ta = (t + 1) / 2, tb = t / 2, tb_pad = nseg * seg_len;
+  float* An = smem;                                          // [ta][TM_LD] normalised even tokens
+  float* Bn = An + (size_t)ta * TM_LD;                       // [tb_pad][TM_LD] normalised odd tokens (+ zero rows)
+  float* segmax = Bn + (size_t)tb_pad * TM_LD;               // [nseg][ta]
+  int* segidx = reinterpret_cast<int*>(segmax + (size_t)nseg * ta);
+  float* nmax = reinterpret_cast<float*>(segidx + (size_t)nseg * ta);   // [ta]
+  int* nidx = reinterpret_cast<int*>(nmax + ta);             // [ta]
+  int* rank = nidx + ta;                                     // [ta]
+  const int n = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
+  const float* mf = metric + (size_t)n * t * C;
+
+  // ---- phase 1: row / ||row|| (merge.py:50) in the reference's summation order ----
+  for (int row = tid; row < t + (tb_pad - tb); row += NT) {
+    if (row >= t) {                                          // zero rows behind B: read by the last tile, never compared
+      float4* z = reinterpret_cast<float4*>(Bn + (size_t)(tb + row - t) * TM_LD);
+#pragma unroll
+      for (int d = 0; d < C / 4; ++d) z[d] = make_float4(0.f, 0.f, 0.f, 0.f);
+      continue;
+    }
+    float o[C];
+    const float* src = mf + (size_t)row * C;
+#pragma unroll
+    for (int d = 0; d < C; d += 4) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
+      o[d] = v.x; o[d + 1] = v.y; o[d + 2] = v.z; o[d + 3] = v.w;
+    }
+    float acc[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) acc[l] = 0.f;
+#pragma unroll
+    for (int d = 0; d < C; d += 8)
+#pragma unroll
+      for (int l = 0; l < 8; ++l) acc[l] = __fadd_rn(acc[l], __fmul_rn(o[d + l], o[d + l]));
+    float sq = acc[0];
+#pragma unroll
+    for (int l = 1; l < 8; ++l) sq = __fadd_rn(sq, acc[l]);
+    const float nrm = __fsqrt_rn(sq);
+    float4* dst = reinterpret_cast<float4*>(((row & 1) ? Bn : An) + (size_t)(row >> 1) * TM_LD);
+#pragma unroll
+    for (int d = 0; d < C; d += 4)
+      dst[d / 4] = make_float4(__fdiv_rn(o[d], nrm), __fdiv_rn(o[d + 1], nrm), __fdiv_rn(o[d + 2], nrm), __fdiv_rn(o[d + 3], nrm));
+  }
+  __syncthreads();
+
+  // ---- phase 2: scores = a . b (merge.py:52) and the running (max, first argmax) of every A row within a B segment ----
+  {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int row0 = class_token ? 1 : 0;
+    const int aw_n = (ta - row0 + 32 * R - 1) / (32 * R);
+    const int seg = warp / aw_n, aw = warp % aw_n;
+    if (seg < nseg) {
+      int ri[R];
+      const float* ap[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        ri[i] = row0 + aw * 32 * R + lane + 32 * i;
+        ap[i] = An + (size_t)min(ri[i], ta - 1) * TM_LD;
+      }
+      float best[R];
+      int bidx[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) { best[i] = -INFINITY; bidx[i] = seg * seg_len; }
+      for (int j0 = seg * seg_len; j0 < (seg + 1) * seg_len; j0 += 8) {
+        float sc[R][8];
+#pragma unroll
+        for (int i = 0; i < R; ++i)
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) sc[i][jj] = 0.f;
+        const float* bp = Bn + (size_t)j0 * TM_LD;
+        // NOT unrolled: a fully unrolled tile lets the scheduler hoist all 192 loads ahead of the 2 048 FMAs (spills)
+#pragma unroll 1
+        for (int d4 = 0; d4 < C / 4; ++d4) {
+          float4 a[R];
+#pragma unroll
+          for (int i = 0; i < R; ++i) a[i] = *reinterpret_cast<const float4*>(ap[i] + d4 * 4);
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float4 b = *reinterpret_cast<const float4*>(bp + jj * TM_LD + d4 * 4);
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+              sc[i][jj] = __fmaf_rn(a[i].x, b.x, sc[i][jj]);
+              sc[i][jj] = __fmaf_rn(a[i].y, b.y, sc[i][jj]);
+              sc[i][jj] = __fmaf_rn(a[i].z, b.z, sc[i][jj]);
+              sc[i][jj] = __fmaf_rn(a[i].w, b.w, sc[i][jj]);
+            }
+          }
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          if (j0 + jj < tb) {
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+              if (sc[i][jj] > best[i]) { best[i] = sc[i][jj]; bidx[i] = j0 + jj; }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+        if (ri[i] < ta) { segmax[(size_t)seg * ta + ri[i]] = best[i]; segidx[(size_t)seg * ta + ri[i]] = bidx[i]; }
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < ta; i += NT) {
+    float m0 = -INFINITY;
+    int i0 = 0;
+    if (!(class_token && i == 0)) {                            // merge.py:55: the class token's row is -inf -> argmax 0
+      m0 = segmax[i];
+      i0 = segidx[i];
+      // a later segment only wins with a strictly larger score (first index on ties, merge.py:59)
+      for (int sg = 1; sg < nseg; ++sg) {
+        const float m = segmax[(size_t)sg * ta + i];
+        if (m > m0) { m0 = m; i0 = segidx[(size_t)sg * ta + i]; }
+      }
+    }
+    nmax[i] = m0;
+    nidx[i] = i0;
+  }
+  __syncthreads();
+  // descending, index-stable rank by counting
+  for (int i = tid; i < ta; i += NT) {
+    const float v = nmax[i];
+    int rk = 0;
+    for (int k = 0; k < ta; ++k) {
+      float u = nmax[k];
+      rk += (u > v) || (u == v && k < i);
+    }
+    rank[i] = rk;
+  }
+  __syncthreads();
+  const int n_unm = ta - r;
+  int* unm = unm_idx + (size_t)n * n_unm;
+  int* src = src_idx + (size_t)n * r;
+  int* dst = dst_idx + (size_t)n * r;
+  for (int i = tid; i < ta; i += NT) {
+    const int rk = rank[i];
+    if (rk < r) {
+      src[rk] = i;
+      dst[rk] = nidx[i];
+    } else if (!class_token) {
+      unm[rk - r] = i;                                         // stays in sorted-score order
+    } else {
+      int pos = 0;                                             // merge.py:66-68: ascending token order
+      for (int k = 0; k < i; ++k) pos += rank[k] >= r;
+      unm[pos] = i;
+    }
+  }
+}
+
 // ---- T2 + T3 ------------------------------------------------------------------------------------
 // grid (N, RS): CTA (n, s) writes output rows s, s+RS, ... of frame n.  A dst row scans the (<= r) edge
 // list held in shared memory for its sources, in ascending edge order (the CPU scatter order).
@@ -375,6 +540,29 @@ inline size_t tome_match_smem(int t, int C) {
 inline int tome_match(Ctx& c, const float* metric, int N, int t, int C, int r, int class_token, int* unm, int* src, int* dst) {
   QAT_REQUIRE(C == 64, "tome_match: metric channels C=%d unsupported (the ViT-L head dim 64 is built)", C);
   QAT_REQUIRE(r > 0 && r <= tome_clamp_r(t, r, class_token), "tome_match: r=%d not clamped for t=%d", r, t);
+  // register-tiled kernel whenever the frame's normalised rows fit one CTA's shared memory (t <= ~700)
+  {
+    const int ta = (t + 1) / 2, tb = t / 2;
+    const int rows = ta - (class_token ? 1 : 0);
+    int R = 4;                                                // the tile height that pads the A rows least (ties: the taller)
+    for (int cand = 3; cand >= 2; --cand)
+      if ((rows + 32 * cand - 1) / (32 * cand) * cand < (rows + 32 * R - 1) / (32 * R) * R) R = cand;
+    const int aw_n = rows > 0 ? (rows + 32 * R - 1) / (32 * R) : 1;
+    int nseg = 20 / aw_n;
+    if (nseg > (tb + 7) / 8) nseg = (tb + 7) / 8;
+    if (nseg < 1) nseg = 1;
+    const int seg_len = (((tb + nseg - 1) / nseg) + 7) / 8 * 8;
+    nseg = (tb + seg_len - 1) / seg_len;
+    const size_t smem_t = ((size_t)(ta + nseg * seg_len) * TM_LD + (size_t)2 * nseg * ta + (size_t)3 * ta) * 4 + 16;
+    const char* old = getenv("QAT_TOME_MATCH_ROWS");          // A/B switch: 1 = the row-per-thread kernel
+    if (rows > 0 && aw_n * nseg <= 20 && smem_t <= 220 * 1024 && !(old && old[0] == '1')) {
+      if (c.dry || N == 0) return QAT_OK;
+      auto kern = R == 4 ? tome_match_tiled_kernel<64, 4> : (R == 3 ? tome_match_tiled_kernel<64, 3> : tome_match_tiled_kernel<64, 2>);
+      if (smem_t > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
+      kern<<<N, 32 * aw_n * nseg, smem_t, c.stream>>>(metric, t, r, class_token, nseg, seg_len, unm, src, dst);
+      return check_launch("tome_match_tiled_kernel");
+    }
+  }
   size_t smem = tome_match_smem(t, C);
   QAT_REQUIRE(smem <= 200 * 1024, "tome_match: t=%d too long for one CTA", t);
   if (c.dry || N == 0) return QAT_OK;
