@@ -392,7 +392,7 @@ def run_ours(args):
             ps = model.patch_selecter._prepared(_cabi.PREC_BF16)
             cr = model.crs_attn._prepared(_cabi.PREC_BF16)
             pp = model.patch_proj._prepared(_cabi.PREC_BF16)
-            chunk_rows = min(B * T, 8192) * P          # rows of one PatchSelecter pass (chunk_frames default 8192)
+            chunk_rows = min(B * T, 16384) * P         # rows of one PatchSelecter pass (chunk_frames default 16384)
             for nm, kind, lin, M_, div, f16out in (("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], B * T, 3.0, False),
                                                    ("gemm_f16_patch_slf_in", _cabi.GEMM_F16, ps["slf_in"], chunk_rows, 1.0, True),
                                                    ("gemm_tf32_patch_proj", _cabi.GEMM_TF32, pp, chunk_rows, 2.0, True)):
@@ -412,9 +412,9 @@ def run_ours(args):
                                  "note": f"nominal 2MNK FLOPs; peak = burst bf16 / {div:g} (kernel timed alone)"}
                 del xin, planes
             # (2b) attention cores (HBM class: the (sequence, head) problems are far below a tensor tile):
-            #     patch self-attention, 8192 frames x 14 tokens, fp16 planes in and out (one PatchSelecter pass);
+            #     patch self-attention, one PatchSelecter pass (15360 frames x 14 tokens at B = 256), fp16 planes in and out;
             #     AVQ self-attention, 2*B sequences x 60 tokens, fp32 in / out, fp16 hi/lo mma.sync inside
-            nf = min(B * T, 8192)
+            nf = min(B * T, 16384)
             q16 = torch.randn(nf, P, 8, 64, device=dev).half()
             kv16 = torch.randn(nf, P, 2, 8, 64, device=dev).half()
             t_ms = time_ms(lambda: _cabi.attention(q16, kv16, None), n=6)

@@ -330,8 +330,9 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
   QAT_TRY(check_w(a->mlp2, D, D / 2, "patch.mlp2", c.prec));
   const long long BT = (long long)B * T;
   const int Cin = a->has_proj ? a->Cin : D;
-  // frames per pass: keep the per-pass intermediates (~ P*D*4*(1+3+1+1+2) bytes per frame) near L2 size
-  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 8192;
+  // frames per pass: 16 384 (B = 256, T = 60 is ONE pass: fewer launches and ragged last waves than two passes of 8 192, measured
+  // 2 % of the step; 1.7 GB of workspace).  Smaller, L2-sized passes were measured slower still
+  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 16384;
   if (a->chunk_frames <= 0 && getenv("QAT_PATCH_CHUNK")) chunk = atoll(getenv("QAT_PATCH_CHUNK")) > 0 ? atoll(getenv("QAT_PATCH_CHUNK")) : chunk;
   if (chunk > BT) chunk = BT;
   const float scale = 0.125f;
@@ -778,12 +779,20 @@ static int run_clip_text(const QatClipTextArgs* a, Ctx& c) {
     // x = x + out_proj(attn(ln_1 x))
     QAT_TRY(act_alloc_for(c, Y, BL, W, k_i));
     QAT_TRY(ln(c, X.f, W, nullptr, 0, nullptr, 0, 1.f, w.ln_1, Y, BL, W));
-    QAT_TRY(act_alloc(c, QKV, BL, 3 * W, true, false));
+    // bf16 mode: [q | k | v] leaves the GEMM as an fp16 (hi, lo) plane pair, the form the attention core eats
+    const bool pp = k_i == G_BF16X3 && W % 8 == 0;
+    if (pp) QAT_TRY(act_alloc_pp(c, QKV, BL, 3 * W));
+    else QAT_TRY(act_alloc(c, QKV, BL, 3 * W, true, false));
     QAT_TRY(gemm(c, k_i, Y, BL, Wi, Epi(), QKV));
     QAT_TRY(act_alloc_for(c, O, BL, W, k_o));
     AttnP p;
     p.nseq = B; p.H = H; p.Lq = L; p.Lk = L; p.scale = 0.125f; p.causal = 1;
-    p.q = QKV.f; p.k = QKV.f + W; p.v = QKV.f + 2 * W;
+    if (pp) {
+      p.q = p.k = p.v = nullptr;
+      p.qh = QKV.ph; p.ql = QKV.pl; p.kh = QKV.ph + W; p.kl = QKV.pl + W; p.vh = QKV.ph + 2 * W; p.vl = QKV.pl + 2 * W;
+    } else {
+      p.q = QKV.f; p.k = QKV.f + W; p.v = QKV.f + 2 * W;
+    }
     p.q_sn = (long long)L * 3 * W; p.q_si = 3 * W; p.k_sn = p.q_sn; p.k_si = 3 * W; p.k_shift = 0; p.k_mod = B;
     p.o = O; p.o_rn = L; p.o_ri = 1; p.attw = nullptr;
     QAT_TRY(attention(c, p));
