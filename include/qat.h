@@ -177,7 +177,7 @@ typedef struct {
   QatLayerNormW anorm, vnorm;
   float* out_a;          /* [B,T,D] anorm(a) */
   float* out_v;          /* [B,T,D] vnorm(v) */
-  int32_t chunk_frames;  /* frames (b,t pairs) per pass, 0 = library default (keeps a pass L2-resident) */
+  int32_t chunk_frames;  /* frames (b,t pairs) per pass, 0 = library default (16 384: B = 256, T = 60 is one pass) */
   void* workspace;
   size_t workspace_bytes;
 } QatPatchArgs;
