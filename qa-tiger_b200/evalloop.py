@@ -166,6 +166,8 @@ def _main():
         raise SystemExit("qa_tiger_b200.evalloop needs a GPU (there is no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    from . import hostbind
+    hostbind.bind_to_gpu(local)          # host threads / pinned buffers on the GPU's NUMA node (no-op on one node)
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":     # the version banner goes to stdout regardless of the file
