@@ -436,7 +436,9 @@ def run_ours(args):
             byts = (q16.numel() + kv16.numel() + q16.numel()) * 2
             ach = byts / (t_ms * 1e-3) / 1e9
             rooflines["attn_small_f16_patch_slf"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                                     "traffic": None, "ms": t_ms, "bytes": byts, "shape": [nf, 8, P, P]}
+                                                     "traffic": None, "ms": t_ms, "bytes": byts, "shape": [nf, 8, P, P],
+                                                     "note": "read-dominated (3 bytes read per byte written): can exceed the peak, which is a "
+                                                             "COPY bandwidth (1:1 read/write)"}
             del q16, kv16
             qa = [torch.randn(2 * B, T, 8, 64, device=dev) for _ in range(3)]
             t_ms = time_ms(lambda: _cabi.attention(qa[0], qa[1], qa[2]), n=6)
