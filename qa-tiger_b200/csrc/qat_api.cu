@@ -134,11 +134,12 @@ static int planes_of(Ctx& c, const float* x, long long rows, int cols, bool want
 }
 
 static int ln(Ctx& c, const float* x0, long long ld0, const float* x1, long long ld1, const float* x2, long long ld2, float c01,
-              const QatLayerNormW& w, Act out, long long rows, int D) {
+              const QatLayerNormW& w, Act out, long long rows, int D, const float* post = nullptr, long long ldp = 0) {
   QAT_REQUIRE(w.gamma && w.beta, "layer_norm: affine parameters missing");
   LnP p;
   p.x0 = x0; p.ld0 = ld0; p.x1 = x1; p.ld1 = ld1; p.x2 = x2; p.ld2 = ld2;
   p.c01 = c01; p.gamma = w.gamma; p.beta = w.beta; p.out = out; p.rows = rows; p.D = D; p.eps = 1e-5f;
+  p.post = post; p.ldp = ldp;
   return layer_norm(c, p);
 }
 
@@ -315,7 +316,10 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
 // =================================================================================================
 // P1(patch) + S1  PatchSelecter
 // =================================================================================================
-static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const float* patch, Act Xaud, Act Xvid, Act out_a, Act out_v) {
+// post (optional, qat_forward_fwd): the outputs leave as post + anorm(a) / post + vnorm(v) -- the expert inputs `data + sub_data[i]`
+// of the vt TempMoE (modules.py:587,597), whose only consumer they are
+static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const float* patch, Act Xaud, Act Xvid, Act out_a, Act out_v,
+                      const float* post = nullptr, long long ldp = 0) {
   const int D = a->D, H = a->H;
   const __half* patch_h = reinterpret_cast<const __half*>(a->patch_f16);
   QAT_REQUIRE(c.dry || patch || patch_h, "patch_select: patch tensor missing");
@@ -482,8 +486,8 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
   QAT_TRY(act_alloc(c, Mo, 2 * BT, D, true, false));
   QAT_TRY(gemm(c, k_m2, Hm, 2 * BT, Wm2, Epi(), Mo));
   // rows (bt,0) = video-related, (bt,1) = audio-related (:706); returned as [anorm(a), vnorm(v)] (:713-716)
-  QAT_TRY(ln(c, Mo.f + D, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->anorm, out_a, BT, D));
-  QAT_TRY(ln(c, Mo.f, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->vnorm, out_v, BT, D));
+  QAT_TRY(ln(c, Mo.f + D, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->anorm, out_a, BT, D, post, ldp));
+  QAT_TRY(ln(c, Mo.f, 2 * D, nullptr, 0, nullptr, 0, 1.f, a->vnorm, out_v, BT, D, post, ldp));
   return QAT_OK;
 }
 
@@ -514,8 +518,10 @@ static int run_gauss(const QatGaussArgs* a, Ctx& c) {
 // =================================================================================================
 // M1-M4 (+LN)  TempMoE
 // =================================================================================================
+// xe_a / xe_v (optional, qat_forward_fwd): the expert inputs data + sub_data[i] already formed by the producer of sub_data
+// (sub_a / sub_v are then only markers for "two branches" and are not read)
 static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst, Act Xd, const float* sub_a, const float* sub_v, float* out_a,
-                    float* out_v, const float* qpre = nullptr, int ldq = 0) {
+                    float* out_v, const float* qpre = nullptr, int ldq = 0, const Act* xe_a = nullptr, const Act* xe_v = nullptr) {
   const int D = a->D, H = a->H, E = a->E, K = a->K;
   QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
   QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
@@ -564,7 +570,9 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
   for (int br = 0; br < nbranch; ++br) {
     const size_t mark = c.mark();
     Act Xe = Xd;
-    if (two) {
+    if (two && xe_a && xe_v) {
+      Xe = br == 0 ? *xe_a : *xe_v;
+    } else if (two) {
       QAT_TRY(act_alloc(c, Xe, BT, D, !reads_planes(k_w1), reads_planes(k_w1)));
       QAT_TRY(add_rows(c, Xd.f, Xd.ld, br == 0 ? sub_a : sub_v, D, Xe, BT, D));     // :587,597
     }
@@ -709,8 +717,11 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
     QAT_TRY(act_alloc_h(c, h, BT, D)); Ax.h = h.h;
     QAT_TRY(act_alloc_h(c, h, BT, D)); Vx.h = h.h;
   }
-  QAT_TRY(act_alloc(c, Ap, BT, D, true, false));
-  QAT_TRY(act_alloc(c, Vp, BT, D, true, false));
+  // PatchSelecter outputs: their only consumer is the vt TempMoE, as `video + patch feature` (modules.py:587,597), so the two
+  // LayerNorms that end the block write that sum, in the storage form the expert GEMM reads
+  const GemmKind k_w1vt = pick_kind(c, BT, a->vt.E * (D / 2), D, false, wview(a->vt.w1_cat));
+  QAT_TRY(act_alloc(c, Ap, BT, D, !reads_planes(k_w1vt), reads_planes(k_w1vt)));
+  QAT_TRY(act_alloc(c, Vp, BT, D, !reads_planes(k_w1vt), reads_planes(k_w1vt)));
   // ap_global | vp_global | fusion1 | a_global | fusion2: both QstGrounding passes find their two inputs back to back
   float* glob = reinterpret_cast<float*>(c.alloc((size_t)5 * B * D * 4));
   if (!c.dry && !glob) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
@@ -735,11 +746,11 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
   const size_t mark = c.mark();
   QAT_TRY(avq_core(&a->avq, B, T, L, c, A0, V0, W0, Ax, Vx, nullptr, nullptr));
   c.release(mark);
-  QAT_TRY(patch_core(&a->patch_sel, B, T, P, c, a->patch, Ax, Vx, Ap, Vp));
+  QAT_TRY(patch_core(&a->patch_sel, B, T, P, c, a->patch, Ax, Vx, Ap, Vp, Vx.f, Vx.ld));
   c.release(mark);
   QAT_TRY(moe_core(&a->at, B, T, c, Q0.f, Ax, nullptr, nullptr, a_global, nullptr, q_at, ldq));
   c.release(mark);
-  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Ap.f, Vp.f, ap_global, vp_global, q_vt, ldq));
+  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Vx.f, Vx.f, ap_global, vp_global, q_vt, ldq, &Ap, &Vp));
   c.release(mark);
   QAT_TRY(ground_core(&a->ground, B, c, Q0.f, ap_global, vp_global, fusion1, false, nullptr, q_gr, ldq));
   c.release(mark);

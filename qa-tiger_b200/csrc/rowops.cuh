@@ -16,6 +16,8 @@ struct LnP {
   const float* gamma;
   const float* beta;
   Act out;             // row r -> out row r
+  const float* post = nullptr;   // optional: out = post[r, :] + LN(...)  (the `data + sub_data` of TempMoE, modules.py:587,597,
+  long long ldp = 0;             //           fused into the LayerNorm that produces sub_data)
   long long rows;
   int D;
   float eps;
@@ -63,6 +65,10 @@ __global__ void __launch_bounds__(256) ln_kernel(LnP p) {
     o.y = v[i].y * rstd * g.y + b.y;
     o.z = v[i].z * rstd * g.z + b.z;
     o.w = v[i].w * rstd * g.w + b.w;
+    if (p.post) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.post + row * p.ldp) + c4);
+      o.x = a.x + o.x; o.y = a.y + o.y; o.z = a.z + o.z; o.w = a.w + o.w;
+    }
     act_store4(p.out, row, c4 * 4, o);
   }
 }
