@@ -1,6 +1,7 @@
 // Softmax(QK^T)V cores for the short sequences of the hot path: lengths 1/2/14/60/77/120,
-// head dim 64.  These are <1% of the FLOPs; they run on CUDA cores in fp32 straight out of the
-// projection GEMM outputs (strided views, no head split / transpose is ever materialised).
+// head dim 64.  These are <1% of the FLOPs; they read strided views of the projection GEMM outputs (no head split /
+// transpose is ever materialised): the 60..128-token cores on warp-level mma.sync with fp16 (hi, lo) operand pairs
+// (attn_mma16_kernel), the rest on CUDA cores in fp32.
 // Semantics: torch MHA slow path, F.multi_head_attention_forward -- q is scaled by hd^-0.5 BEFORE the
 // dot product, softmax = exp(s - max)/sum, no masks (modules.py:217-221,338,562,688,698).
 #pragma once
@@ -24,7 +25,7 @@ struct AttnP {
   float scale;
   int causal = 0;        // 1: key j attends only to queries i >= j (CLIP text tower; attn_mma16_kernel only)
   // optional: Q / K / V as fp16 (hi, lo) plane pairs written by the in-projection GEMM (same strides, in elements); when
-  // set, q / k / v are ignored and the call runs on attn_mma16p_kernel
+  // set, q / k / v are ignored and the call runs on attn_mma16_kernel<NT16, true>
   const __half* qh = nullptr;
   const __half* ql = nullptr;
   const __half* kh = nullptr;

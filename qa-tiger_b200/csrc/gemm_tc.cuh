@@ -9,13 +9,13 @@
 //                 tf32 MMA rate and half the bytes).  Used inside PatchSelecter, whose activations live in HBM/L2
 //                 as fp16 planes (error budget in DESIGN.md).
 //
-// Epilogue: every output plane (fp32 / bf16 hi, lo / fp16) leaves through the TMA unit: an epilogue warp packs its
+// Epilogue: every output plane (fp32 / bf16 hi, lo / fp16 / fp16 hi, lo) leaves through the TMA unit: an epilogue warp packs its
 // 32 x 32 sub-tile into a swizzled smem box and one lane issues cp.async.bulk.tensor (row / column tails clipped
 // by the TMA unit, no strided LSU stores).
 //
-// Structure (one 128 x BN output tile per CTA, 320 threads):
+// Structure (one 128 x BN output tile per CTA -- or one 256 x BN tile per CTA PAIR, `CG = 2`, cta_group::2 --, 320 threads):
 //   warp 0      : TMA producer  - cp.async.bulk.tensor.2d (128B swizzle) into a STAGES-deep smem ring
-//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit frees smem slots
+//   warp 1      : TMEM allocator + tcgen05.mma issuer (warp-uniform loop, one elected lane); tcgen05.commit frees smem slots
 //   warps 2..9  : epilogue - tcgen05.ld (32 lanes x 32 columns) -> bias/ReLU/residual in registers -> swizzled
 //                 smem box -> TMA store per plane (two warps per TMEM lane quarter, one per column half)
 // Both operands are K-major; smem tiles are rows of 128 bytes (32 tf32 / 64 bf16), 8-row 1024-byte swizzle atoms.
