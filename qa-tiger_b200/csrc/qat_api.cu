@@ -240,8 +240,19 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
     QAT_TRY(act_alloc(c, S, 2 * BT, 7 * D, true, false));
     QAT_TRY(act_alloc(c, KVw, BL, 2 * D, true, false));
   }
-  QAT_TRY(gemm(c, k_src, Xa, BT, Wsrc, Epi(), S));
-  QAT_TRY(gemm(c, k_src, Xv, BT, Wsrc, Epi(), S.rows(BT)));
+  // the two modalities share every weight of the block: when their rows sit back to back (qat_forward_fwd lays them out
+  // so) each per-modality contraction is ONE launch over 2*BT rows (one ragged last wave instead of two)
+  auto behind = [&](const Act& x, const Act& y) {
+    return x.ld == D && y.ld == D && (!x.f || y.f == x.f + BT * D) && (!x.hi || y.hi == x.hi + BT * D) && (!x.lo || y.lo == x.lo + BT * D) &&
+           (x.f != nullptr) == (y.f != nullptr) && (x.hi != nullptr) == (y.hi != nullptr) && (x.lo != nullptr) == (y.lo != nullptr);
+  };
+  const bool stacked = !c.dry ? behind(Xa, Xv) : false;
+  if (stacked) {
+    QAT_TRY(gemm(c, k_src, Xa, 2 * BT, Wsrc, Epi(), S));
+  } else {
+    QAT_TRY(gemm(c, k_src, Xa, BT, Wsrc, Epi(), S));
+    QAT_TRY(gemm(c, k_src, Xv, BT, Wsrc, Epi(), S.rows(BT)));
+  }
   QAT_TRY(gemm(c, k_words, Xw, BL, Wwords, Epi(), KVw));
   // O = [o_qst | o_slf | o_crs] per row, both directions
   QAT_TRY(act_alloc(c, O, 2 * BT, 3 * D, !reads_planes(k_out), reads_planes(k_out)));
@@ -286,9 +297,13 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
   {
     Epi e;
     e.res = Xa.f; e.ldr = Xa.ld;
-    QAT_TRY(gemm(c, k_out, O, BT, Wout, e, Y));
-    e.res = Xv.f; e.ldr = Xv.ld;
-    QAT_TRY(gemm(c, k_out, O.rows(BT), BT, Wout, e, Y.rows(BT)));
+    if (stacked) {
+      QAT_TRY(gemm(c, k_out, O, 2 * BT, Wout, e, Y));
+    } else {
+      QAT_TRY(gemm(c, k_out, O, BT, Wout, e, Y));
+      e.res = Xv.f; e.ldr = Xv.ld;
+      QAT_TRY(gemm(c, k_out, O.rows(BT), BT, Wout, e, Y.rows(BT)));
+    }
   }
   QAT_TRY(act_alloc(c, X1, 2 * BT, D, true, reads_planes(k_f1)));
   QAT_TRY(ln(c, Y.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm1, X1, 2 * BT, D));
@@ -519,9 +534,11 @@ static int run_gauss(const QatGaussArgs* a, Ctx& c) {
 // M1-M4 (+LN)  TempMoE
 // =================================================================================================
 // xe_a / xe_v (optional, qat_forward_fwd): the expert inputs data + sub_data[i] already formed by the producer of sub_data
-// (sub_a / sub_v are then only markers for "two branches" and are not read)
+// (sub_a / sub_v are then only markers for "two branches" and are not read); xe_stacked: xe_v's rows follow xe_a's in memory, so
+// the two branches, which share every weight, run their expert GEMMs as single launches over 2*BT (2*B) rows
 static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst, Act Xd, const float* sub_a, const float* sub_v, float* out_a,
-                    float* out_v, const float* qpre = nullptr, int ldq = 0, const Act* xe_a = nullptr, const Act* xe_v = nullptr) {
+                    float* out_v, const float* qpre = nullptr, int ldq = 0, const Act* xe_a = nullptr, const Act* xe_v = nullptr,
+                    bool xe_stacked = false) {
   const int D = a->D, H = a->H, E = a->E, K = a->K;
   QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
   QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
@@ -566,6 +583,36 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
   QAT_TRY(gemm(c, G_SIMT, TW, B, Wrg, Epi(), RG));
   // RG rows are [router(E) | gauss(2E)] with ld 3E: the reduce kernel reads both through a row pitch
 
+  if (two && xe_a && xe_v && xe_stacked) {
+    Act Hd, Hb, Ob;
+    QAT_TRY(act_alloc(c, Hd, 2 * BT, E * Ch, true, false));
+    {
+      Epi e;
+      e.relu = 1;
+      QAT_TRY(gemm(c, k_w1, *xe_a, 2 * BT, W1, e, Hd));
+    }
+    QAT_TRY(act_alloc(c, Hb, 2ll * B, KE, true, false));
+    for (int br = 0; br < 2; ++br) {
+      GaussP g;
+      g.x = Hd.f + (size_t)br * BT * E * Ch; g.st = (long long)E * Ch; g.sb = (long long)T * E * Ch;
+      g.rl = RG.f; g.gr = RG.f + E; g.rl_ld = 3 * E; g.gr_ld = 3 * E; g.B = B; g.T = T; g.E = E; g.K = K; g.C = Ch; g.sigma = a->sigma;
+      g.per_expert = 1; g.out = Hb.rows((long long)br * B);
+      g.topk_inds = br == 0 ? reinterpret_cast<long long*>(a->topk_inds) : nullptr;
+      g.topk_probs = br == 0 ? a->topk_probs : nullptr;
+      g.gauss_weight = br == 0 ? a->gauss_weight : nullptr;
+      QAT_TRY(gauss_reduce(c, g, QAT_DT_F32, 0));
+    }
+    QAT_TRY(act_alloc(c, Ob, 2ll * B, D, true, false));
+    {
+      Epi e;
+      WView w2 = W2;
+      w2.bias = nullptr;
+      QAT_TRY(gemm(c, G_SIMT, Hb, 2ll * B, w2, e, Ob));
+    }
+    QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm_a, act_of(out_a, D), B, D));
+    QAT_TRY(ln(c, Ob.f + (size_t)B * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm_v, act_of(out_v, D), B, D));
+    return QAT_OK;
+  }
   const int nbranch = two ? 2 : 1;
   for (int br = 0; br < nbranch; ++br) {
     const size_t mark = c.mark();
@@ -701,8 +748,13 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
   const bool tc = c.prec == QAT_PREC_BF16;
   // projected inputs: fp32 (residuals) + bf16 hi/lo planes (the AVQ in-projections read those in bf16 mode)
   Act A0, V0, W0, Q0, Ax, Vx, Ap, Vp;
-  QAT_TRY(act_alloc(c, A0, BT, D, true, tc));
-  QAT_TRY(act_alloc(c, V0, BT, D, true, tc));
+  // audio rows then video rows of ONE activation: the AVQ block then runs its per-modality contractions as single launches
+  {
+    Act AV0;
+    QAT_TRY(act_alloc(c, AV0, 2 * BT, D, true, tc));
+    A0 = AV0;
+    V0 = AV0.rows(BT);
+  }
   QAT_TRY(act_alloc(c, W0, BL, D, true, tc));
   QAT_TRY(act_alloc(c, Q0, B, D, true, false));
   QAT_TRY(linear_core(c, a->audio_proj, act_of(a->audio, a->audio_proj.k), BT, 0, A0));
@@ -720,8 +772,12 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
   // PatchSelecter outputs: their only consumer is the vt TempMoE, as `video + patch feature` (modules.py:587,597), so the two
   // LayerNorms that end the block write that sum, in the storage form the expert GEMM reads
   const GemmKind k_w1vt = pick_kind(c, BT, a->vt.E * (D / 2), D, false, wview(a->vt.w1_cat));
-  QAT_TRY(act_alloc(c, Ap, BT, D, !reads_planes(k_w1vt), reads_planes(k_w1vt)));
-  QAT_TRY(act_alloc(c, Vp, BT, D, !reads_planes(k_w1vt), reads_planes(k_w1vt)));
+  {
+    Act APV;                                              // audio-related rows, then video-related rows
+    QAT_TRY(act_alloc(c, APV, 2 * BT, D, !reads_planes(k_w1vt), reads_planes(k_w1vt)));
+    Ap = APV;
+    Vp = APV.rows(BT);
+  }
   // ap_global | vp_global | fusion1 | a_global | fusion2: both QstGrounding passes find their two inputs back to back
   float* glob = reinterpret_cast<float*>(c.alloc((size_t)5 * B * D * 4));
   if (!c.dry && !glob) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
@@ -750,7 +806,7 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
   c.release(mark);
   QAT_TRY(moe_core(&a->at, B, T, c, Q0.f, Ax, nullptr, nullptr, a_global, nullptr, q_at, ldq));
   c.release(mark);
-  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Vx.f, Vx.f, ap_global, vp_global, q_vt, ldq, &Ap, &Vp));
+  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Vx.f, Vx.f, ap_global, vp_global, q_vt, ldq, &Ap, &Vp, true));
   c.release(mark);
   QAT_TRY(ground_core(&a->ground, B, c, Q0.f, ap_global, vp_global, fusion1, false, nullptr, q_gr, ldq));
   c.release(mark);
