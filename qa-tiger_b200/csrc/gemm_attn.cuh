@@ -11,6 +11,12 @@
 //               frame: mma.sync m16n8k16 attention out of that tile (ldmatrix, softmax in the accumulator fragments,
 //               P re-used as the A fragment) -> O rows in a 128B-swizzled box -> (named barrier) -> one TMA store.
 //   warps 10,11 attention only: with 9 frames per tile, ten attention warps finish in one round instead of two
+//
+// CROSS = true is the cross-attention of the same block (modules.py:692-698): the contraction is the packed K | V projection of
+// the frame's tokens (B tile = the head's 64 k rows and 64 v rows, N = 128), the two queries of the frame ([video; audio], already
+// projected) come from global memory, and the epilogue runs softmax(q k^T / 8) v for those two rows, so the [rows, 2D] K | V
+// projection (0.44 GB written + read back per 256-question batch) never reaches HBM either.  The two output rows of a (frame,
+// head) leave as plain 32-bit stores.
 #pragma once
 #include "attn_core.cuh"
 #include "gemm_tc.cuh"
@@ -21,8 +27,11 @@ namespace tc {
 struct GemmAttnP {
   int M;            // rows = nframes * P
   int nframes, P, H, K;
-  const float* bias;   // [3 * H * 64]
+  const float* bias;   // [3 * H * 64]  (CROSS: [2 * H * 64], k then v)
   float scale;
+  const __half* q;     // CROSS: projected queries [nframes, 2, H * 64]
+  __half* o;           // CROSS: output [nframes * 2, ldo]
+  int ldo;
 };
 
 constexpr int GA_STAGES = 4;
@@ -39,6 +48,7 @@ constexpr int GA_BAR_BYTES = (2 * GA_STAGES + 4) * 8 + 16;
 constexpr int GA_SMEM = GA_STAGES * GA_STAGE_BYTES + GA_O_BYTES + GA_QKV_BYTES + GA_BAR_BYTES + 1024;
 static_assert(GA_SMEM <= 232448, "gemm_attn: shared-memory budget");
 
+template <bool CROSS>
 __global__ void __launch_bounds__(384, 1)
 gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO,
                  GemmAttnP p) {
@@ -96,11 +106,11 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
           unsigned char* st = tiles + s * GA_STAGE_BYTES;
           const int k0 = kb * 64;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&full[s], GA_STAGE_BYTES);
+            mbar_arrive_expect_tx(&full[s], CROSS ? GA_A_BYTES + 16384 : GA_STAGE_BYTES);
             tma_load_2d(st, &mA, &full[s], k0, m0);
             tma_load_2d(st + GA_A_BYTES, &mW, &full[s], k0, h * 64);
             tma_load_2d(st + GA_A_BYTES + 8192, &mW, &full[s], k0, D + h * 64);
-            tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
+            if (!CROSS) tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
           }
           __syncwarp();
         }
@@ -108,7 +118,7 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     }
   } else if (warp == 1) {
     {
-      constexpr uint32_t idesc = umma_idesc(0, 128, GA_BN);
+      constexpr uint32_t idesc = umma_idesc(0, 128, CROSS ? 128 : GA_BN);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
         const uint32_t as = lt & 1;
@@ -145,19 +155,21 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
       if (ew < 8) {
       mbar_wait(&tfull[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + as * 256 + half * 96 + (uint32_t(lg * 32) << 16);
-      // ---- 1. accumulator -> (+bias) -> fp16 [126][192] tile ----
+      constexpr int HALF_COLS = CROSS ? 64 : 96, NCH = HALF_COLS / 32, SCOL = CROSS ? 64 : 0;
+      const uint32_t tacc = tmem_base + as * 256 + half * HALF_COLS + (uint32_t(lg * 32) << 16);
+      // ---- 1. accumulator -> (+bias) -> fp16 [126][192] tile (CROSS: the q columns stay unused) ----
 #pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        const int col0 = half * 96 + c * 32;                          // q: [0,64), k: [64,128), v: [128,192)
+      for (int c = 0; c < NCH; ++c) {
+        const int acol = half * HALF_COLS + c * 32;                   // accumulator column: (q,) k, v blocks of 64
+        const int col0 = SCOL + acol;                                 // tile column: q: [0,64), k: [64,128), v: [128,192)
         uint32_t v[32];
         tmem_ld32(tacc + uint32_t(c * 32), v);
-        const float* bptr = p.bias + (col0 >> 6) * D + h * 64 + (col0 & 63);
+        const float* bptr = p.bias + (acol >> 6) * D + h * 64 + (acol & 63);
         float4 bb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(bptr) + q);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == 2) {
+        if (c == NCH - 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
         }
@@ -174,8 +186,90 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
       }
       }
       // the previous tile's O box must have left shared memory before anyone overwrites it
-      if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (!CROSS && ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 320;" ::: "memory");
+      if constexpr (CROSS) {
+        // ---- 2x. one warp per frame: the frame's two queries against its P keys / values ----
+        for (int f = ew; f < FPT; f += 10) {
+          const long long frame = (long long)mt * FPT + f;
+          if (frame >= p.nframes) break;
+          const uint32_t fb = sqkv + (f * P) * GA_QKV_STRIDE;
+          // A fragments of the 16 x 64 query tile: rows 0, 1 are the queries, the other rows are zero
+          uint32_t qa[4][4];
+          {
+            const __half* qrow = p.q + (frame * 2 + g) * D + h * 64 + 2 * tq;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              qa[ks][0] = g < 2 ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16)) : 0u;
+              qa[ks][2] = g < 2 ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8)) : 0u;
+              qa[ks][1] = 0u;
+              qa[ks][3] = 0u;
+            }
+          }
+          float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+          {
+            const int krow = min(r8 + (m8 >> 1) * 8, P - 1), kcol = (m8 & 1) * 8;
+            const uint32_t ka = fb + krow * GA_QKV_STRIDE + (64 + kcol) * 2;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              uint32_t b[4];
+              ldsm_x4(b, ka + ks * 32);
+              mma_f16(s[0], qa[ks], b[0], b[1]);
+              mma_f16(s[1], qa[ks], b[2], b[3]);
+            }
+          }
+          float mx0 = -INFINITY;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const bool ok = nt * 8 + 2 * tq + e < P;
+              s[nt][e] = ok ? s[nt][e] * p.scale : -INFINITY;
+              mx0 = fmaxf(mx0, s[nt][e]);
+            }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          float s0 = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              s[nt][e] = expf(s[nt][e] - mx0);
+              s0 += s[nt][e];
+            }
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+          const float i0 = 1.f / s0;
+          uint32_t pa[4];
+          pa[0] = pack_half2(s[0][0] * i0, s[0][1] * i0);
+          pa[1] = 0u;
+          pa[2] = pack_half2(s[1][0] * i0, s[1][1] * i0);
+          pa[3] = 0u;
+          float o[8][4];
+#pragma unroll
+          for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+            for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
+          {
+            const int vrow = min(r8 + (m8 & 1) * 8, P - 1), vcol = (m8 >> 1) * 8;
+            const uint32_t va = fb + vrow * GA_QKV_STRIDE + (128 + vcol) * 2;
+#pragma unroll
+            for (int dp = 0; dp < 4; ++dp) {
+              uint32_t b[4];
+              ldsm_x4_t(b, va + dp * 32);
+              mma_f16(o[2 * dp], pa, b[0], b[1]);
+              mma_f16(o[2 * dp + 1], pa, b[2], b[3]);
+            }
+          }
+          if (g < 2) {
+            __half* orow = p.o + (frame * 2 + g) * p.ldo + h * 64 + 2 * tq;
+#pragma unroll
+            for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_half2(o[dt][0], o[dt][1]);
+          }
+        }
+        asm volatile("bar.sync 1, 320;" ::: "memory");       // the tile may be overwritten by the next drain
+        continue;
+      }
       // ---- 2. one warp per frame: softmax(q k^T * scale) v on mma.sync ----
       for (int f = ew; f < FPT; f += 10) {
         if (mt * FPT + f >= p.nframes) break;
@@ -262,7 +356,7 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (!CROSS && ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
@@ -302,14 +396,44 @@ inline int gemm_attn_f16(Ctx& c, const __half* X, int ldx, int nframes, int P, i
   }
   tc::GemmAttnP p;
   p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
-  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
+  p.q = nullptr; p.o = nullptr; p.ldo = 0;
+  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
   const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  tc::gemm_attn_kernel<<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
+  tc::gemm_attn_kernel<false><<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
   return check_launch("gemm_attn_kernel");
+}
+
+// O[nframes * 2, D] (fp16) = per-frame softmax(Q (X Wk^T + bk)^T / 8)(X Wv^T + bv) for the two projected query rows
+// Q [nframes, 2, D] (fp16) of every frame; X [nframes * P, K] fp16, W [2D, K] fp16 = in_proj_weight[D:], bias [2D] fp32
+inline int gemm_attn_cross_f16(Ctx& c, const __half* X, int ldx, int nframes, int P, int H, int K, const __half* W, const float* bias,
+                               float scale, const __half* Q, __half* O, int ldo) {
+  QAT_REQUIRE(P >= 1 && P <= 16 && H >= 1 && K % 64 == 0 && bias, "gemm_attn_cross: need P <= 16, K %% 64 == 0 and a bias (P=%d K=%d)", P, K);
+  QAT_REQUIRE((128 / P) * P <= tc::GA_QKV_ROWS, "gemm_attn_cross: P=%d fills more than %d rows of a tile", P, tc::GA_QKV_ROWS);
+  QAT_REQUIRE(ldx % 8 == 0 && ldo % 2 == 0, "gemm_attn_cross: row pitches must be multiples of 16 (X) / 4 (O) bytes");
+  if (c.dry || nframes == 0) return QAT_OK;
+  QAT_REQUIRE(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0 &&
+                  ((reinterpret_cast<uintptr_t>(Q) | reinterpret_cast<uintptr_t>(O)) & 3) == 0,
+              "gemm_attn_cross: tensors must be 16-byte (X, W, bias) / 4-byte (Q, O) aligned");
+  const int D = H * 64, FPT = 128 / P;
+  const long long M = (long long)nframes * P;
+  CUtensorMap mA, mW;
+  QAT_TRY(tc::make_map(&mA, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, K, ldx, 128));
+  QAT_TRY(tc::make_map(&mW, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * D, K, K, 64));
+  tc::GemmAttnP p;
+  p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
+  p.q = Q; p.o = O; p.ldo = ldo;
+  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
+  const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+  tc::gemm_attn_kernel<true><<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mA, p);     // the output map is unused
+  return check_launch("gemm_attn_kernel<cross>");
 }
 
 }  // namespace qat

@@ -442,6 +442,13 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
         e.res_h = Pp.h; e.ldr = Pp.ld;
         QAT_TRY(gemm(c, G_F16, Oa, rows, Wso, e, P2));
       }
+      const char* nocross = getenv("QAT_PATCH_NO_FUSED_CROSS");    // A/B switch: K | V GEMM + separate cross-attention kernel
+      if (Q2.h && O2.h && !O2.f && !O2.hi && Wkv.bias && (128 / P) * P <= tc::GA_QKV_ROWS && !(nocross && nocross[0] == '1')) {
+        // K | V projection and the two-query cross-attention in one kernel: [k | v] never reaches HBM
+        QAT_TRY(gemm_attn_cross_f16(c, P2.h, P2.ld, (int)nf, P, H, D, Wkv.h16, Wkv.bias, scale, Q2.h + (size_t)f0 * 2 * D,
+                                    O2.h + (size_t)f0 * 2 * D, D));
+        continue;
+      }
       QAT_TRY(act_alloc_h(c, KV, rows, 2 * D));
       QAT_TRY(gemm(c, G_F16, P2, rows, Wkv, Epi(), KV));
       if (Q2.h && O2.h && !O2.f && !O2.hi) {
