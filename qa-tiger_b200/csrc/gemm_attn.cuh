@@ -11,12 +11,6 @@
 //               frame: mma.sync m16n8k16 attention out of that tile (ldmatrix, softmax in the accumulator fragments,
 //               P re-used as the A fragment) -> O rows in a 128B-swizzled box -> (named barrier) -> one TMA store.
 //   warps 10,11 attention only: with 9 frames per tile, ten attention warps finish in one round instead of two
-//
-// CROSS = true is the cross-attention of the same block (modules.py:692-698): the contraction is the packed K | V projection of
-// the frame's tokens (B tile = the head's 64 k rows and 64 v rows, N = 128), the two queries of the frame ([video; audio], already
-// projected) come from global memory, and the epilogue runs softmax(q k^T / 8) v for those two rows, so the [rows, 2D] K | V
-// projection (0.44 GB written + read back per 256-question batch) never reaches HBM either.  The two output rows of a (frame,
-// head) leave as plain 32-bit stores.
 #pragma once
 #include "attn_core.cuh"
 #include "gemm_tc.cuh"
@@ -27,11 +21,11 @@ namespace tc {
 struct GemmAttnP {
   int M;            // rows = nframes * P
   int nframes, P, H, K;
-  const float* bias;   // [3 * H * 64]  (CROSS: [2 * H * 64], k then v)
+  const float* bias;   // [3 * H * 64]  (cross form: [2 * H * 64], k then v)
   float scale;
-  const __half* q;     // CROSS: projected queries [nframes, 2, H * 64]
-  __half* o;           // CROSS: output [nframes * 2, ldo]
-  int ldo;
+  const __half* q = nullptr;   // cross form: projected queries [nframes, 2, H * 64]
+  __half* o = nullptr;         // cross form: output [nframes * 2, ldo]
+  int ldo = 0;
 };
 
 constexpr int GA_STAGES = 4;
@@ -48,7 +42,6 @@ constexpr int GA_BAR_BYTES = (2 * GA_STAGES + 4) * 8 + 16;
 constexpr int GA_SMEM = GA_STAGES * GA_STAGE_BYTES + GA_O_BYTES + GA_QKV_BYTES + GA_BAR_BYTES + 1024;
 static_assert(GA_SMEM <= 232448, "gemm_attn: shared-memory budget");
 
-template <bool CROSS>
 __global__ void __launch_bounds__(384, 1)
 gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO,
                  GemmAttnP p) {
@@ -106,11 +99,11 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
           unsigned char* st = tiles + s * GA_STAGE_BYTES;
           const int k0 = kb * 64;
           if (elect_one()) {
-            mbar_arrive_expect_tx(&full[s], CROSS ? GA_A_BYTES + 16384 : GA_STAGE_BYTES);
+            mbar_arrive_expect_tx(&full[s], GA_STAGE_BYTES);
             tma_load_2d(st, &mA, &full[s], k0, m0);
             tma_load_2d(st + GA_A_BYTES, &mW, &full[s], k0, h * 64);
             tma_load_2d(st + GA_A_BYTES + 8192, &mW, &full[s], k0, D + h * 64);
-            if (!CROSS) tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
+            tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
           }
           __syncwarp();
         }
@@ -118,7 +111,7 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
     }
   } else if (warp == 1) {
     {
-      constexpr uint32_t idesc = umma_idesc(0, 128, CROSS ? 128 : GA_BN);
+      constexpr uint32_t idesc = umma_idesc(0, 128, GA_BN);
       uint32_t it = 0, lt = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
         const uint32_t as = lt & 1;
@@ -155,21 +148,19 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
       if (ew < 8) {
       mbar_wait(&tfull[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      constexpr int HALF_COLS = CROSS ? 64 : 96, NCH = HALF_COLS / 32, SCOL = CROSS ? 64 : 0;
-      const uint32_t tacc = tmem_base + as * 256 + half * HALF_COLS + (uint32_t(lg * 32) << 16);
-      // ---- 1. accumulator -> (+bias) -> fp16 [126][192] tile (CROSS: the q columns stay unused) ----
+      const uint32_t tacc = tmem_base + as * 256 + half * 96 + (uint32_t(lg * 32) << 16);
+      // ---- 1. accumulator -> (+bias) -> fp16 [126][192] tile ----
 #pragma unroll 1
-      for (int c = 0; c < NCH; ++c) {
-        const int acol = half * HALF_COLS + c * 32;                   // accumulator column: (q,) k, v blocks of 64
-        const int col0 = SCOL + acol;                                 // tile column: q: [0,64), k: [64,128), v: [128,192)
+      for (int c = 0; c < 3; ++c) {
+        const int col0 = half * 96 + c * 32;                          // q: [0,64), k: [64,128), v: [128,192)
         uint32_t v[32];
         tmem_ld32(tacc + uint32_t(c * 32), v);
-        const float* bptr = p.bias + (acol >> 6) * D + h * 64 + (acol & 63);
+        const float* bptr = p.bias + (col0 >> 6) * D + h * 64 + (col0 & 63);
         float4 bb[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(bptr) + q);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == NCH - 1) {
+        if (c == 2) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
         }
@@ -186,90 +177,8 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
       }
       }
       // the previous tile's O box must have left shared memory before anyone overwrites it
-      if (!CROSS && ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
       asm volatile("bar.sync 1, 320;" ::: "memory");
-      if constexpr (CROSS) {
-        // ---- 2x. one warp per frame: the frame's two queries against its P keys / values ----
-        for (int f = ew; f < FPT; f += 10) {
-          const long long frame = (long long)mt * FPT + f;
-          if (frame >= p.nframes) break;
-          const uint32_t fb = sqkv + (f * P) * GA_QKV_STRIDE;
-          // A fragments of the 16 x 64 query tile: rows 0, 1 are the queries, the other rows are zero
-          uint32_t qa[4][4];
-          {
-            const __half* qrow = p.q + (frame * 2 + g) * D + h * 64 + 2 * tq;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              qa[ks][0] = g < 2 ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16)) : 0u;
-              qa[ks][2] = g < 2 ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8)) : 0u;
-              qa[ks][1] = 0u;
-              qa[ks][3] = 0u;
-            }
-          }
-          float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-          {
-            const int krow = min(r8 + (m8 >> 1) * 8, P - 1), kcol = (m8 & 1) * 8;
-            const uint32_t ka = fb + krow * GA_QKV_STRIDE + (64 + kcol) * 2;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
-              uint32_t b[4];
-              ldsm_x4(b, ka + ks * 32);
-              mma_f16(s[0], qa[ks], b[0], b[1]);
-              mma_f16(s[1], qa[ks], b[2], b[3]);
-            }
-          }
-          float mx0 = -INFINITY;
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const bool ok = nt * 8 + 2 * tq + e < P;
-              s[nt][e] = ok ? s[nt][e] * p.scale : -INFINITY;
-              mx0 = fmaxf(mx0, s[nt][e]);
-            }
-          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-          float s0 = 0.f;
-#pragma unroll
-          for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              s[nt][e] = expf(s[nt][e] - mx0);
-              s0 += s[nt][e];
-            }
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-          s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-          const float i0 = 1.f / s0;
-          uint32_t pa[4];
-          pa[0] = pack_half2(s[0][0] * i0, s[0][1] * i0);
-          pa[1] = 0u;
-          pa[2] = pack_half2(s[1][0] * i0, s[1][1] * i0);
-          pa[3] = 0u;
-          float o[8][4];
-#pragma unroll
-          for (int dt = 0; dt < 8; ++dt)
-#pragma unroll
-            for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
-          {
-            const int vrow = min(r8 + (m8 & 1) * 8, P - 1), vcol = (m8 >> 1) * 8;
-            const uint32_t va = fb + vrow * GA_QKV_STRIDE + (128 + vcol) * 2;
-#pragma unroll
-            for (int dp = 0; dp < 4; ++dp) {
-              uint32_t b[4];
-              ldsm_x4_t(b, va + dp * 32);
-              mma_f16(o[2 * dp], pa, b[0], b[1]);
-              mma_f16(o[2 * dp + 1], pa, b[2], b[3]);
-            }
-          }
-          if (g < 2) {
-            __half* orow = p.o + (frame * 2 + g) * p.ldo + h * 64 + 2 * tq;
-#pragma unroll
-            for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_half2(o[dt][0], o[dt][1]);
-          }
-        }
-        asm volatile("bar.sync 1, 320;" ::: "memory");       // the tile may be overwritten by the next drain
-        continue;
-      }
       // ---- 2. one warp per frame: softmax(q k^T * scale) v on mma.sync ----
       for (int f = ew; f < FPT; f += 10) {
         if (mt * FPT + f >= p.nframes) break;
@@ -356,13 +265,297 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
-    if (!CROSS && ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   }
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// ---- both attentions of the block with a PIPELINED epilogue ----------------------------------------------------------------
+// CROSS = false: the self-attention above.  CROSS = true: the cross-attention of the same block (modules.py:692-698): the
+// contraction is the packed K | V projection of the frame's tokens (B tile = the head's 64 k rows and 64 v rows, N = 128), the two
+// queries of the frame ([video; audio], already projected) come from global memory, and the epilogue runs softmax(q k^T / 8) v for
+// those two rows, so the [rows, 2D] K | V projection (0.44 GB written + read back per 256-question batch) never reaches HBM either.
+// The epilogue is split into two warp groups that work on different tiles at the same time: four drain warps (one per TMEM lane
+// quarter) turn accumulator i+1 into the fp16 [126][(q |) k | v] tile while six attention warps run the attention of tile i out of
+// the other buffer; the output rows leave as plain 32-bit stores.  Cross form: the N = 128 tile's MMA time is 1.8 us; with a serial
+// drain -> barrier -> attention -> barrier epilogue it ran at 3.1 us per tile, with this one at 2.8 us -- an N = 128 tile moves
+// 256 KB of operands per 16.8 MFLOP, which the L2 -> SM fabric (about 21 TB/s in aggregate) bounds next.
+// Shared memory: STAGES x (A 16 KB + 8 KB per W box) + two [126][BN + 8] fp16 tiles.
+template <bool CROSS>
+struct GxCfg {
+  static constexpr int NW = CROSS ? 2 : 3;                 // W boxes of 64 rows per stage: (q,) k, v of the head
+  static constexpr int BN = 64 * NW;
+  static constexpr int STAGES = CROSS ? 4 : 3;
+  static constexpr int STAGE_BYTES = GA_A_BYTES + NW * 8192;
+  static constexpr int STRIDE = (BN + 8) * 2;              // bytes per tile row: conflict-free ldmatrix / 16-byte stores
+  static constexpr int TILE_BYTES = ((GA_QKV_ROWS * STRIDE + 1023) / 1024) * 1024;
+  static constexpr int ACC_COLS = CROSS ? 128 : 256;       // TMEM columns per accumulator (two of them)
+  static constexpr int BAR_BYTES = (2 * STAGES + 8) * 8 + 16;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * TILE_BYTES + BAR_BYTES + 1024;
+  static_assert(SMEM <= 232448, "gemm_attn_pipe: shared-memory budget");
+};
+
+template <bool CROSS>
+__global__ void __launch_bounds__(384, 1)
+gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, GemmAttnP p) {
+  typedef GxCfg<CROSS> G;
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* tiles = smem;
+  unsigned char* sT = smem + G::STAGES * G::STAGE_BYTES;                   // two tiles
+  uint64_t* full = reinterpret_cast<uint64_t*>(sT + 2 * G::TILE_BYTES);
+  uint64_t* empty = full + G::STAGES;
+  uint64_t* tfull = empty + G::STAGES;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* kvfull = tempty + 2;
+  uint64_t* kvempty = kvfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kvempty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.P, H = p.H, D = H * 64;
+  const int FPT = 128 / P, RPT = FPT * P;                                 // frames / rows per tile
+  const int nkb = p.K / 64;
+  const int tiles_m = (p.nframes + FPT - 1) / FPT;
+  const int ntiles = tiles_m * H;
+  constexpr int KOFF = CROSS ? 0 : 64, VOFF = KOFF + 64;                  // tile columns of k and v (q: [0,64) in the self form)
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mW)) : "memory");
+    for (int s = 0; s < G::STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], 4);          // the four drain warps
+      mbar_init(&kvfull[a], 4);          // the four drain warps
+      mbar_init(&kvempty[a], 6);         // the six attention warps
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * G::ACC_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      const int m0 = (t / H) * RPT, h = t % H;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % G::STAGES;
+        mbar_wait(&empty[s], ((it / G::STAGES) & 1) ^ 1);
+        unsigned char* st = tiles + s * G::STAGE_BYTES;
+        const int k0 = kb * 64;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
+          tma_load_2d(st, &mA, &full[s], k0, m0);
+#pragma unroll
+          for (int w = 0; w < G::NW; ++w) tma_load_2d(st + GA_A_BYTES + w * 8192, &mW, &full[s], k0, w * D + h * 64);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = umma_idesc(0, 128, G::BN);
+    uint32_t it = 0, lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const uint32_t as = lt & 1;
+      mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t tacc = tmem_base + as * G::ACC_COLS;
+      for (int kb = 0; kb < nkb; ++kb, ++it) {
+        const int s = it % G::STAGES;
+        mbar_wait(&full[s], (it / G::STAGES) & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = smem_u32(tiles + s * G::STAGE_BYTES);
+        const uint64_t dA = umma_desc(a0), dW = umma_desc(a0 + GA_A_BYTES);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) umma<KIND_F16>(tacc, dA + uint64_t(k * 2), dW + uint64_t(k * 2), idesc, (kb | k) != 0);
+          umma_commit(&empty[s]);
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&tfull[as]);
+      __syncwarp();
+    }
+  } else if (warp < 6) {
+    // ===================== drain warps 2..5: accumulator -> (+bias) -> fp16 [126][(q |) k | v] tile =====================
+    const int lg = warp & 3;
+    const int row = lg * 32 + lane;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int h = t % H;
+      const uint32_t as = lt & 1, ph = (lt >> 1) & 1;
+      mbar_wait(&tfull[as], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      mbar_wait(&kvempty[as], ph ^ 1);                                  // the attention warps are done with this buffer
+      const uint32_t tacc = tmem_base + as * G::ACC_COLS + (uint32_t(lg * 32) << 16);
+      const uint32_t st = smem_u32(sT + as * G::TILE_BYTES);
+#pragma unroll 1
+      for (int c = 0; c < G::BN / 32; ++c) {
+        const int acol = c * 32;                                        // blocks of 64: (q,) k, v
+        uint32_t v[32];
+        tmem_ld32(tacc + uint32_t(acol), v);
+        const float* bptr = p.bias + (acol >> 6) * D + h * 64 + (acol & 63);
+        float4 bb[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(bptr) + q);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c == G::BN / 32 - 1) {
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+        }
+#pragma unroll
+        for (uint32_t q = 0; q < 4; ++q) {
+          if (row >= RPT) break;                                        // rows beyond the tile's frames belong to the next tile
+          const float4 b0 = bb[2 * q], b1 = bb[2 * q + 1];
+          sts128(st + row * G::STRIDE + acol * 2 + q * 16,
+                 pack_half2(__uint_as_float(v[8 * q]) + b0.x, __uint_as_float(v[8 * q + 1]) + b0.y),
+                 pack_half2(__uint_as_float(v[8 * q + 2]) + b0.z, __uint_as_float(v[8 * q + 3]) + b0.w),
+                 pack_half2(__uint_as_float(v[8 * q + 4]) + b1.x, __uint_as_float(v[8 * q + 5]) + b1.y),
+                 pack_half2(__uint_as_float(v[8 * q + 6]) + b1.z, __uint_as_float(v[8 * q + 7]) + b1.w));
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&kvfull[as])) : "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ===================== attention warps 6..11: one (frame, head) at a time on mma.sync =====================
+    const int aw = warp - 6;
+    const int g = lane >> 2, tq = lane & 3, m8 = lane >> 3, r8 = lane & 7;
+    uint32_t lt = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+      const int mt = t / H, h = t % H;
+      const uint32_t as = lt & 1, ph = (lt >> 1) & 1;
+      const uint32_t st = smem_u32(sT + as * G::TILE_BYTES);
+      bool waited = false;
+      for (int f = aw; f < FPT; f += 6) {
+        const long long frame = (long long)mt * FPT + f;
+        if (frame >= p.nframes) break;
+        const uint32_t fb = st + (f * P) * G::STRIDE;
+        // A fragments of the 16 x 64 query tile.  Cross form: rows 0, 1 are the frame's queries, fetched from global memory
+        // before the tile is awaited, the other rows are zero.  Self form: the frame's own q rows, out of the tile.
+        uint32_t qa[4][4];
+        if constexpr (CROSS) {
+          const __half* qrow = p.q + (frame * 2 + g) * D + h * 64 + 2 * tq;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            qa[ks][0] = g < 2 ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16)) : 0u;
+            qa[ks][2] = g < 2 ? __ldg(reinterpret_cast<const uint32_t*>(qrow + ks * 16 + 8)) : 0u;
+            qa[ks][1] = 0u;
+            qa[ks][3] = 0u;
+          }
+        }
+        if (!waited) {
+          mbar_wait(&kvfull[as], ph);
+          waited = true;
+        }
+        if constexpr (!CROSS) {
+          const int qrow = min(r8 + (m8 & 1) * 8, P - 1), qcol = (m8 >> 1) * 8;
+          const uint32_t qaddr = fb + qrow * G::STRIDE + qcol * 2;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) ldsm_x4(qa[ks], qaddr + ks * 32);
+        }
+        float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+        {
+          const int krow = min(r8 + (m8 >> 1) * 8, P - 1), kcol = (m8 & 1) * 8;
+          const uint32_t ka = fb + krow * G::STRIDE + (KOFF + kcol) * 2;
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            uint32_t b[4];
+            ldsm_x4(b, ka + ks * 32);
+            mma_f16(s[0], qa[ks], b[0], b[1]);
+            mma_f16(s[1], qa[ks], b[2], b[3]);
+          }
+        }
+        // rows g (and, self form, g + 8) of the score tile: masked softmax over the P keys
+        float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const bool ok = nt * 8 + 2 * tq + e < P;
+            s[nt][e] = ok ? s[nt][e] * p.scale : -INFINITY;
+            s[nt][2 + e] = ok ? s[nt][2 + e] * p.scale : -INFINITY;
+            mx0 = fmaxf(mx0, s[nt][e]);
+            mx1 = fmaxf(mx1, s[nt][2 + e]);
+          }
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 2; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            s[nt][e] = expf(s[nt][e] - mx0);
+            s[nt][2 + e] = expf(s[nt][2 + e] - mx1);
+            s0 += s[nt][e];
+            s1 += s[nt][2 + e];
+          }
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+        const float i0 = 1.f / s0, i1 = 1.f / s1;
+        uint32_t pa[4];
+        pa[0] = pack_half2(s[0][0] * i0, s[0][1] * i0);
+        pa[1] = CROSS ? 0u : pack_half2(s[0][2] * i1, s[0][3] * i1);
+        pa[2] = pack_half2(s[1][0] * i0, s[1][1] * i0);
+        pa[3] = CROSS ? 0u : pack_half2(s[1][2] * i1, s[1][3] * i1);
+        float o[8][4];
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
+        {
+          const int vrow = min(r8 + (m8 & 1) * 8, P - 1), vcol = (m8 >> 1) * 8;
+          const uint32_t va = fb + vrow * G::STRIDE + (VOFF + vcol) * 2;
+#pragma unroll
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t b[4];
+            ldsm_x4_t(b, va + dp * 32);
+            mma_f16(o[2 * dp], pa, b[0], b[1]);
+            mma_f16(o[2 * dp + 1], pa, b[2], b[3]);
+          }
+        }
+        // output rows: cross form (frame, query g < 2); self form (frame, token g) and (frame, token g + 8)
+        const int nq = CROSS ? 2 : P;
+        if (g < nq) {
+          __half* orow = p.o + (frame * nq + g) * p.ldo + h * 64 + 2 * tq;
+#pragma unroll
+          for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_half2(o[dt][0], o[dt][1]);
+        }
+        if (!CROSS && g + 8 < nq) {
+          __half* orow = p.o + (frame * nq + g + 8) * p.ldo + h * 64 + 2 * tq;
+#pragma unroll
+          for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(orow + dt * 8) = pack_half2(o[dt][2], o[dt][3]);
+        }
+      }
+      if (!waited) mbar_wait(&kvfull[as], ph);           // a warp without a frame in this tile still follows the phases
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&kvempty[as])) : "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * G::ACC_COLS) : "memory");
   }
 }
 
@@ -396,14 +589,21 @@ inline int gemm_attn_f16(Ctx& c, const __half* X, int ldx, int nframes, int P, i
   }
   tc::GemmAttnP p;
   p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
-  p.q = nullptr; p.o = nullptr; p.ldo = 0;
-  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
+  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
   const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  tc::gemm_attn_kernel<false><<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
+  const char* serial = getenv("QAT_PATCH_ATTN_SERIAL");       // A/B switch: 1 = the serial-epilogue kernel with the TMA-store box
+  if (!(serial && serial[0] == '1')) {
+    p.o = O;
+    p.ldo = ldo;
+    QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GxCfg<false>::SMEM));
+    tc::gemm_attn_pipe_kernel<false><<<grid, 384, tc::GxCfg<false>::SMEM, c.stream>>>(mA, mW, p);
+    return check_launch("gemm_attn_pipe_kernel<self>");
+  }
+  tc::gemm_attn_kernel<<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
   return check_launch("gemm_attn_kernel");
 }
 
@@ -426,14 +626,14 @@ inline int gemm_attn_cross_f16(Ctx& c, const __half* X, int ldx, int nframes, in
   tc::GemmAttnP p;
   p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
   p.q = Q; p.o = O; p.ldo = ldo;
-  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
   const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  tc::gemm_attn_kernel<true><<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mA, p);     // the output map is unused
-  return check_launch("gemm_attn_kernel<cross>");
+  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GxCfg<true>::SMEM));
+  tc::gemm_attn_pipe_kernel<true><<<grid, 384, tc::GxCfg<true>::SMEM, c.stream>>>(mA, mW, p);
+  return check_launch("gemm_attn_pipe_kernel<cross>");
 }
 
 }  // namespace qat
