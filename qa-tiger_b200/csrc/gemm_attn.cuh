@@ -284,7 +284,7 @@ gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__
 // quarter) turn accumulator i+1 into the fp16 [126][(q |) k | v] tile while six attention warps run the attention of tile i out of
 // the other buffer; the output rows leave as plain 32-bit stores.  Cross form: the N = 128 tile's MMA time is 1.8 us; with a serial
 // drain -> barrier -> attention -> barrier epilogue it ran at 3.1 us per tile, with this one at 2.8 us -- an N = 128 tile moves
-// 256 KB of operands per 16.8 MFLOP, which the L2 -> SM fabric (about 21 TB/s in aggregate) bounds next.
+// 256 KB of operands per 16.8 MFLOP (ncu: 14 TB/s of L2 -> SM traffic, tensor pipe 55 % active), so operand delivery is next.
 // Shared memory: STAGES x (A 16 KB + 8 KB per W box) + two [126][BN + 8] fp16 tiles.
 template <bool CROSS>
 struct GxCfg {
