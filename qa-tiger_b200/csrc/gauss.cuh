@@ -227,21 +227,42 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   } else {
     __syncthreads();
   }
-  if (rank == 0) {
+  {
+    // every rank combines an interleaved share of the outputs (always in rank order); four outputs at a time, so that the
+    // distributed-shared-memory loads of a batch are in flight together (one output at a time on rank 0 alone cost ~8 us of
+    // back-to-back remote-load latency per launch)
     const int nout = p.per_expert ? E * C : C;
-    for (int o = tid; o < nout; o += NT) {
-      float sum = 0.f;
+    constexpr int U = 4;
+    const int stride = NT * nrank;
+    for (int o0 = rank * NT + tid; o0 < nout; o0 += stride * U) {
+      float sum[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) sum[u] = 0.f;
       for (int r = 0; r < nrank; ++r) {
         const float* part = s_part;
         if (CLUSTER) part = cg::this_cluster().map_shared_rank(s_part, r);
         if (p.per_expert) {
-          sum += part[o];
+          float v[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) v[u] = (o0 + u * stride < nout) ? part[o0 + u * stride] : 0.f;
+#pragma unroll
+          for (int u = 0; u < U; ++u) sum[u] += v[u];
         } else {
-          for (int e = 0; e < E; ++e) sum += part[e * C + o];
+          for (int e = 0; e < E; ++e) {
+            float v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = (o0 + u * stride < nout) ? part[e * C + o0 + u * stride] : 0.f;
+#pragma unroll
+            for (int u = 0; u < U; ++u) sum[u] += v[u];
+          }
         }
       }
-      act_store1(p.out, b, o, sum);
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (o0 + u * stride < nout) act_store1(p.out, b, o0 + u * stride, sum[u]);
     }
+  }
+  if (rank == 0) {
     if (p.per_expert) {
       for (int e = tid; e < 64; e += NT) {
         float sum = 0.f;
@@ -251,7 +272,7 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
       }
     }
   }
-  if (CLUSTER) cg::this_cluster().sync();   // keep every CTA's smem alive until rank 0 has read it
+  if (CLUSTER) cg::this_cluster().sync();   // keep every CTA's smem alive until all ranks have read it
 }
 
 inline size_t gauss_smem_bytes(const GaussP& p, size_t row_bytes) {
