@@ -1,0 +1,74 @@
+"""The library's A/B switches select alternative kernels for the same arithmetic; these tests keep
+those alternatives alive by checking each against the default path on the same inputs."""
+import pytest
+import torch
+
+from oracle import synth
+
+from gpu_util import dev, relerr, sub_sd
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sd():
+    return synth.make_state_dict(716, num_experts=7, text_tower=False)
+
+
+def _patch_block(sd):
+    from qa_tiger_b200.models import modules as M
+    m = M.PatchSelecter(512, 8)
+    m.load_state_dict(sub_sd(sd, "patch_selecter"))
+    m = m.to(dev()).eval()
+    m.precision = "bf16"
+    proj = M.Projection(1024, 512)
+    proj.load_state_dict(sub_sd(sd, "patch_proj"))
+    proj = proj.to(dev()).eval()
+    proj.precision = "bf16"
+    return m, proj
+
+
+@pytest.mark.parametrize("switch", ["QAT_PATCH_ATTN_SERIAL", "QAT_PATCH_NO_FUSED_CROSS", "QAT_PATCH_NO_FUSED_ATTN"])
+def test_patch_selecter_kernel_alternatives(sd, switch, monkeypatch):
+    """Serial-epilogue fused kernel, unfused cross-attention, unfused self-attention: same fp16-plane arithmetic."""
+    m, proj = _patch_block(sd)
+    g = torch.Generator().manual_seed(7)
+    raw = torch.randn(12, 60, 14, 1024, generator=g).to(dev())
+    a, v = torch.randn(12, 60, 512, generator=g).to(dev()), torch.randn(12, 60, 512, generator=g).to(dev())
+    with torch.no_grad():
+        da, dv = m(raw, a, v, proj=proj)
+        monkeypatch.setenv(switch, "1")
+        sa, sv = m(raw, a, v, proj=proj)
+    # identical operands and fp32 accumulation; only the softmax / store schedule differs (fp16 rounding of P and O)
+    assert relerr(sa, da) < 5e-4 and relerr(sv, dv) < 5e-4
+
+
+@pytest.mark.parametrize("switch,val", [("QAT_ATTN_FP32_IN", "1"), ("QAT_GEMM_CG", "1")])
+def test_avq_kernel_alternatives(sd, switch, val, monkeypatch):
+    """fp32 instead of plane-pair in-projections into the attention cores; single-CTA instead of CTA-pair GEMM tiles."""
+    from qa_tiger_b200.models import modules as M
+    m = M.AVQCrossAttn(512, 8)
+    m.load_state_dict(sub_sd(sd, "crs_attn"))
+    m = m.to(dev()).eval()
+    m.precision = "bf16"
+    g = torch.Generator().manual_seed(11)
+    a, v, w = (torch.randn(20, 60, 512, generator=g).to(dev()), torch.randn(20, 60, 512, generator=g).to(dev()),
+               torch.randn(20, 77, 512, generator=g).to(dev()))
+    with torch.no_grad():
+        da, dv = m(a, v, w)
+        monkeypatch.setenv(switch, val)
+        sa, sv = m(a, v, w)
+    assert relerr(sa, da) < 2e-5 and relerr(sv, dv) < 2e-5
+
+
+def test_tome_match_kernels_agree(monkeypatch):
+    """Register-tiled and row-per-thread match kernels: the same indices and merged tokens, bit for bit."""
+    from qa_tiger_b200.tome import merge as tm
+    x = torch.randn(5, 577, 1024, generator=torch.Generator().manual_seed(3)).to(dev())
+    xo, size, group, steps = tm.chain(x, trace=True)
+    monkeypatch.setenv("QAT_TOME_MATCH_ROWS", "1")
+    xo2, size2, group2, steps2 = tm.chain(x, trace=True)
+    assert torch.equal(xo, xo2) and torch.equal(size, size2) and torch.equal(group, group2)
+    for s1, s2 in zip(steps, steps2):
+        for t1, t2 in zip(s1, s2):
+            assert torch.equal(t1, t2)
