@@ -45,6 +45,11 @@ def parse():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--hot-only", action="store_true", help="profiling aid: time only the hot path (no e2e / rooflines / cpu legs)")
     ap.add_argument("--no-dp-eval", action="store_true", help="skip the configs[3] leg (DP eval over 9 129 synthetic questions)")
+    ap.add_argument("--no-streaming", action="store_true", help="skip the configs[3] streaming-eval legs (SURVEY 8f-N3 input pipeline)")
+    ap.add_argument("--tome", action="store_true",
+                    help="BASELINE configs[2] instead of configs[1]: ToMe 577->14 merge chain over 60 x 256 = 15 360 frames, chunked, "
+                         "frame-sharded over the ranks; prints frames/s and the stepwise-traffic roofline")
+    ap.add_argument("--tome-frames", type=int, default=15360)
     ap.add_argument("--stress", action="store_true",
                     help="BASELINE configs[4] shape instead of configs[1]: T=120, E=K=14, 128 questions per GPU (combine with --hot-only)")
     a = ap.parse_args()
@@ -167,6 +172,196 @@ def run_reference(args):
         "gpu_launches": 0, "wall_s": time.perf_counter() - t0,
     }
     print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def streaming_eval_legs(model, dev, rank, world, B):
+    """BASELINE configs[3] through the product input pipeline (qa_tiger_b200/datapipe.py): a MUSIC-AVQA-test-shaped
+    question list (9 129 questions over 6 399 videos, 33 question strings) evaluated from a PINNED HOST feature store.  Timed
+    region of a pass (CUDA events on the consumer's stream around evalloop.evaluate, max over ranks): host->device copies of every
+    video the device cache does not hold yet, token / label / slot vectors, text tower on unseen questions (side stream), batch
+    gather, hot path, argmax, on-device counters, the final all_gather / all_reduce and the D2H of predictions + counters.
+      cold = empty device cache and empty question memo: every video crosses the host link exactly once;
+      warm = the next eval of the same set (the reference evaluates its val set every epoch): nothing crosses but vectors."""
+    import torch
+    import torch.distributed as dist
+
+    from qa_tiger_b200 import datapipe as dp
+    from qa_tiger_b200 import evalloop as EL
+
+    def one_store(n_q, patch_dtype, passes):
+        qs = dp.QuestionSet.synthetic_music_avqa(n=n_q)
+        lo, hi = EL.shard_range(qs.n, rank, world)
+        vids = qs.videos_of(lo, hi)
+        layout = dp.RowLayout(patch_dtype=patch_dtype)
+        t0 = time.perf_counter()
+        store = dp.FeatureStore.synthetic(vids, layout, device=dev)
+        torch.cuda.synchronize()
+        t_store = time.perf_counter() - t0
+        enc = model.quest_encoder
+        enc.memo, enc.dedup = True, False
+        loader = dp.StreamingLoader(store, qs, dev, batch_size=B, rank=rank, world=world, encoder=enc)
+        fwd = lambda b_: model(b_)["out"]
+        # warm-up: one pass (kernels loaded, workspaces and memo tensors sized), then forget what it cached
+        EL.evaluate(fwd, loader, dev, B, rank, world)
+        res = {}
+        for name in passes:
+            if name == "cold":
+                loader.cache.clear()
+                enc.__dict__.pop("_memo_state", None)
+            loader.h2d_bytes = 0
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            a_.record()
+            r = EL.evaluate(fwd, loader, dev, B, rank, world)
+            b_.record()
+            torch.cuda.synchronize()
+            wall = time.perf_counter() - w0
+            t = torch.tensor([a_.elapsed_time(b_), wall * 1e3, float(loader.h2d_bytes)], device=dev, dtype=torch.float64)
+            if world > 1:
+                tm = t.clone()
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                t[0], t[1] = tm[0], tm[1]
+            res[name] = {"questions_per_s": qs.n / (float(t[0]) * 1e-3), "ms": float(t[0]), "wall_ms": float(t[1]),
+                         "h2d_bytes": int(t[2]), "total_counted": r["total"]}
+        st = loader.cache.stats()
+        res["store"] = {"questions": qs.n, "videos_total": qs.n_videos, "videos_this_rank": len(vids), "row_bytes": layout.row_bytes,
+                        "patch_dtype": str(patch_dtype).replace("torch.", ""), "host_store_bytes_rank0": store.nbytes,
+                        "build_s_rank0": t_store, "cache_misses_rank0": st["misses"], "cache_evictions_rank0": st["evictions"],
+                        "memo_entries_rank0": len(enc.__dict__.get("_memo_state", {}).get("slots", {}))}
+        enc.memo = False
+        enc.__dict__.pop("_memo_state", None)
+        del loader, store
+        torch.cuda.empty_cache()
+        return res
+
+    out = {"fp16_store": one_store(9129, torch.float16, ("cold", "warm"))}
+    # the reference's own fp32 store on a bounded sample (2 304 questions: 9 batches; the full fp32 set would pin 23 GB of host
+    # memory on rank 0 for no extra information -- the pass is bound by the host link either way)
+    out["fp32_store_sample"] = one_store(2304, torch.float32, ("cold",))
+    return out
+
+
+def run_tome(args):
+    """BASELINE configs[2]: ToMe 577 -> 14 over 60 frames x 256 videos = 15 360 frames (scripts/extract_ToMe/extract_tome14.py:153-170
+    runs this one frame at a time), frame-sharded over the ranks, `chunk` frames per chain call, tokens resident in HBM."""
+    import torch
+    import torch.distributed as dist
+
+    from qa_tiger_b200 import _cabi
+    from qa_tiger_b200.tome import merge as tm
+
+    world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --tome needs a GPU")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _cabi.lib()
+    hbm_peak, _, _, peak_src = peaks()
+    n_frames, chunk = args.tome_frames, 592
+    lo, hi = tm.frame_shard(n_frames, rank, world)
+    g = torch.Generator(device=dev).manual_seed(42 + rank)
+    # this rank's frames resident in HBM (36.3 GB fp32 for the whole set on one GPU), generated chunk by chunk
+    x = torch.empty(hi - lo, 577, 1024, device=dev)
+    for c0 in range(0, hi - lo, chunk):
+        x[c0:c0 + chunk].normal_(generator=g)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    for _ in range(max(1, args.warmup)):
+        tm.chain_frames(x, hi - lo, chunk=chunk)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    lib.qat_launch_count(1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.armed = True
+    e0.record()
+    for _ in range(args.steps):
+        xo, so, _ = tm.chain_frames(x, hi - lo, chunk=chunk)
+    e1.record()
+    torch.cuda.synchronize()
+    sampler.armed = False
+    launches = lib.qat_launch_count(1)
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e: the same pass from a pinned host token store, chunk by chunk (copy stream, double-buffered), outputs read back
+    e2e = None
+    try:
+        nb = min(hi - lo, 4 * chunk)
+        host = x[:nb].cpu().pin_memory()
+        out_host = torch.empty(nb, 14, 1024).pin_memory()
+        bufs = [torch.empty(chunk, 577, 1024, device=dev) for _ in range(2)]
+        cs = torch.cuda.Stream()
+        ready, freed = [torch.cuda.Event() for _ in range(2)], [torch.cuda.Event() for _ in range(2)]
+        cur = torch.cuda.current_stream()
+
+        def run_e2e():
+            for ev in freed:
+                ev.record(cur)
+            chunks = [(c0, min(nb, c0 + chunk)) for c0 in range(0, nb, chunk)]
+
+            def issue(i):
+                c0, c1 = chunks[i]
+                with torch.cuda.stream(cs):
+                    cs.wait_event(freed[i % 2])
+                    bufs[i % 2][:c1 - c0].copy_(host[c0:c1], non_blocking=True)
+                    ready[i % 2].record(cs)
+            issue(0)
+            for i, (c0, c1) in enumerate(chunks):
+                if i + 1 < len(chunks):
+                    issue(i + 1)
+                cur.wait_event(ready[i % 2])
+                o, _, _, _ = tm.chain(bufs[i % 2][:c1 - c0], want_group=False)
+                out_host[c0:c1].copy_(o, non_blocking=True)
+                freed[i % 2].record(cur)
+        run_e2e()
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        run_e2e()
+        f1.record()
+        torch.cuda.synchronize()
+        te = torch.tensor([f0.elapsed_time(f1)], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * nb / (float(te[0]) * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": nb * 577 * 1024 * 4,
+               "d2h_bytes_per_step": nb * 14 * 1024 * 4, "frames_per_rank": nb,
+               "note": "bound by the host link: 2.36 MB of fp32 tokens per frame in, 57 KB out"}
+    except Exception as e_:   # noqa: BLE001
+        sys.stderr.write(f"[bench] ToMe e2e leg skipped: {e_}\n")
+    if rank == 0:
+        tmax = float(t[0]) * 1e-3
+        fps = n_frames * args.steps / tmax
+        byts = 56.49e6 * (hi - lo) * args.steps          # rank 0's shard over rank 0's... all shards are equal-sized up to 1 frame
+        ach = 56.49e6 * n_frames * args.steps / tmax / 1e9 / world
+        line = {"metric": "frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": tmax * 1e3 / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic",
+                "config": {"workload": f"ToMe bipartite soft matching 577->14 (configs[2]): {n_frames} frames = 60 x 256, 23 merge steps "
+                                       "(r = 25 x 22, then 13), class token, stand-in metric x.view(N,t,16,64).mean(2) (SURVEY 8d), "
+                                       "bit-exact indices", "frames_per_rank": hi - lo, "chunk_frames": chunk,
+                           "parallelism": f"frame-sharded dp{world}, no collective", "l2": "1.4 GB of tokens per chunk exceeds L2"},
+                "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
+                             "kernel": "tome chain (tome_match_tiled_kernel + tome_merge_wavg_kernel x 23 steps)",
+                             "note": "per GPU: stepwise algorithmic traffic 56.49 MB per frame (SURVEY 8d) over the whole chain time"},
+                "e2e": e2e, "peaks_source": peak_src}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -343,7 +538,13 @@ def run_ours(args):
             torch.cuda.synchronize()
             parts[nm] = f0.elapsed_time(f1) / e2e_steps
             parts[nm.replace("_ms", "_cpu_issue_ms")] = t_issue * 1e3 / e2e_steps
-        e2e_parity = float((model(bufs[0])["out"] - out).norm() / out.norm())   # same batch: bf16x3 tower vs fp32 tower
+        # same batch through the torch fp32 tower (the reference's arithmetic) and through the native bf16x3 tower
+        o_native = model(bufs[0])["out"]
+        model.quest_encoder.compute = "fp32"
+        o_fp32tower = model(bufs[0])["out"]
+        model.quest_encoder.compute = "native"
+        e2e_parity = float((o_native - o_fp32tower).norm() / o_fp32tower.norm())
+        del o_native, o_fp32tower
         # ---- the same e2e step on an fp16 patch feature store: `patch` is stored, copied and consumed as
         # fp16 (half the H2D bytes; patch_proj becomes a kind::f16 pass).  Reported next to the headline, not as it: the
         # reference's store is fp32.
@@ -401,14 +602,15 @@ def run_ours(args):
                                  "traffic": None, "ms": t_ms, "bytes": byts}
                 del xs
             # (2) the three tensor-core GEMM kinds at the largest shapes of the step (nominal 2*M*N*K FLOPs):
-            #     bf16x3: AVQ packed in-proj [B*T,512] x [3584,512]^T, 3 MMAs per product  (peak = burst bf16 / 3)
+            #     bf16x3: AVQ packed in-proj of both modalities [2*B*T,512] x [3584,512]^T (one launch in the step), 3 MMAs per
+            #             product  (peak = burst bf16 / 3)
             #     f16   : PatchSelecter self-attention in-proj [B*T*P,512] x [1536,512]^T, fp16 planes in and out
             #     tf32  : patch_proj [B*T*P,1024] x [512,1024]^T straight from the fp32 input  (peak = burst bf16 / 2)
             ps = model.patch_selecter._prepared(_cabi.PREC_BF16)
             cr = model.crs_attn._prepared(_cabi.PREC_BF16)
             pp = model.patch_proj._prepared(_cabi.PREC_BF16)
             chunk_rows = min(B * T, 16384) * P         # rows of one PatchSelecter pass (chunk_frames default 16384)
-            for nm, kind, lin, M_, div, f16out in (("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], B * T, 3.0, False),
+            for nm, kind, lin, M_, div, f16out in (("gemm_bf16x3_avq_in_src", _cabi.GEMM_BF16X3, cr["in_src"], 2 * B * T, 3.0, False),
                                                    ("gemm_f16_patch_slf_in", _cabi.GEMM_F16, ps["slf_in"], chunk_rows, 1.0, True),
                                                    ("gemm_tf32_patch_proj", _cabi.GEMM_TF32, pp, chunk_rows, 2.0, True)):
                 N_, K_ = lin.w.shape
@@ -426,20 +628,8 @@ def run_ours(args):
                                  "ms": t_ms, "shape": [M_, N_, K_],
                                  "note": f"nominal 2MNK FLOPs; peak = burst bf16 / {div:g} (kernel timed alone)"}
                 del xin, planes
-            # (2b) attention cores (HBM class: the (sequence, head) problems are far below a tensor tile):
-            #     patch self-attention, one PatchSelecter pass (15360 frames x 14 tokens at B = 256), fp16 planes in and out;
-            #     AVQ self-attention, 2*B sequences x 60 tokens, fp32 in / out, fp16 hi/lo mma.sync inside
-            nf = min(B * T, 16384)
-            q16 = torch.randn(nf, P, 8, 64, device=dev).half()
-            kv16 = torch.randn(nf, P, 2, 8, 64, device=dev).half()
-            t_ms = time_ms(lambda: _cabi.attention(q16, kv16, None), n=6)
-            byts = (q16.numel() + kv16.numel() + q16.numel()) * 2
-            ach = byts / (t_ms * 1e-3) / 1e9
-            rooflines["attn_small_f16_patch_slf"] = {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak,
-                                                     "traffic": None, "ms": t_ms, "bytes": byts, "shape": [nf, 8, P, P],
-                                                     "note": "read-dominated (3 bytes read per byte written): can exceed the peak, which is a "
-                                                             "COPY bandwidth (1:1 read/write)"}
-            del q16, kv16
+            # (2b) AVQ self-attention core (HBM class: a (sequence, head) problem is far below a tensor tile): 2*B sequences x 60
+            #     tokens, fp32 in / out, fp16 hi/lo mma.sync inside
             qa = [torch.randn(2 * B, T, 8, 64, device=dev) for _ in range(3)]
             t_ms = time_ms(lambda: _cabi.attention(qa[0], qa[1], qa[2]), n=6)
             byts = 4 * qa[0].numel() * 4
@@ -521,6 +711,15 @@ def run_ours(args):
                            "and memoised across batches"}
         del cache
 
+    streaming = None
+    if not args.no_streaming and not args.stress:
+        try:
+            with torch.no_grad():
+                streaming = streaming_eval_legs(model, dev, rank, world, B)
+        except Exception as e_:   # noqa: BLE001 -- an auxiliary leg must not sink the bench line
+            sys.stderr.write(f"[bench] streaming eval legs failed: {e_!r}\n")
+            streaming = {"error": repr(e_)}
+
     tmax = torch.tensor([ms, ms_e2e / e2e_steps * args.steps, ms_full, ms_e2e16], device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -544,11 +743,10 @@ def run_ours(args):
                        "l2": "inputs per step (881 MB patch + 54 MB other) exceed the 126 MB L2; no explicit flush",
                        "cuda_graph": graph is not None, "parallelism": f"dp{world}, contiguous shards, no data-path collective"},
             "clocks": clocks,
-            "e2e": {"value": qps_e2e, "unit": "questions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
-                    "ms_per_step": ms_e2e_max, "breakdown": parts, "text_tower_vs_fp32_logit_relerr": e2e_parity,
-                    "includes": "per step: H2D of the batch from pinned host (copy stream, double-buffered), CLIP text tower "
-                                "(qat_clip_text_fwd, SURVEY 8f-N1), hot path, argmax, D2H of predictions; bound by the PCIe copy "
-                                "of 936 MB per 256 questions (breakdown.h2d_only_ms)"},
+            "e2e_detail": {"breakdown": parts,
+                           "includes": "per step: H2D of the batch from pinned host (copy stream, double-buffered), CLIP text tower "
+                                       "(qat_clip_text_fwd, SURVEY 8f-N1), hot path, argmax, D2H of predictions; bound by the PCIe copy "
+                                       "of 936 MB per 256 questions (breakdown.h2d_only_ms)"},
             "e2e_fp16_patch_store": {"value": world * B / (ms_e2e16_max * 1e-3), "unit": "questions/s", "ms_per_step": ms_e2e16_max,
                                      "h2d_bytes_per_step": h2d16,
                                      "note": "SURVEY 8f-N3: the same e2e step with `patch` stored / copied / consumed as fp16 (audio, video, "
@@ -558,26 +756,26 @@ def run_ours(args):
                                               "12-layer CLIP text tower (no dedup: synthetic questions are all distinct; "
                                               "MUSIC-AVQA test has 33 unique question strings)"},
             "dp_eval_config4": dp_eval,
-            "gpu_launches": launches_per_step * args.steps,
-            "launches_per_step": launches_per_step,
-            "hot_path_tensor_frac_nominal": (flops_q * B / (step_ms * 1e-3)) / (tf_sust * 1e12),
+            "e2e_config4_streaming": streaming,
             "peaks": {"hbm_gbs": hbm_peak, "bf16_tflops_burst": tf_burst, "bf16_tflops_sustained": tf_sust, "source": peak_src},
         }
-        # per-launch DRAM traffic from the committed `ncu --set full` captures (profiles/r1_traffic.json), if present
-        tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        # per-launch DRAM traffic from the committed `ncu --set full` captures, attached only when the captured shape is the
+        # timed one (profiles/r2_traffic.json: {name: {"bytes": n, "shape": [...]}})
+        tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.exists(tpath):
             for k, v in json.load(open(tpath)).items():
-                if k in rooflines:
-                    rooflines[k]["traffic"] = v
-        # headline roofline = the dominant kernel of the step per the ncu launch list (profiles/r1_launches_step_v16.txt:
-        # the bf16x3 tcgen05 GEMM, 30 % of the step; the f16 kind and the fused in-proj + attention kernel follow at 13 % each), at its largest shape; the other GEMM
-        # kinds, the HBM-class Gaussian-expert kernel north_star names and the ToMe chain ride along in rooflines_all
-        key = "gemm_bf16x3_avq_in_src"
-        line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "frac_of_sustained", "traffic")}
-        line["roofline"]["kernel"] = ("tc::gemm_tc_kernel<KIND_BF16X3,256,3,EPI,CG=2> (cta_group::2 pair tiles 256x256) AVQCrossAttn packed "
-                                       "in-proj [15360,512]x[3584,512]^T")
-        line["roofline"]["note"] = rooflines[key]["note"]
-        line["rooflines_all"] = rooflines
+                if k in rooflines and (v.get("shape") is None or v.get("shape") == rooflines[k].get("shape")):
+                    rooflines[k]["traffic"] = v["bytes"]
+        # the full per-kernel table goes to stderr and to a side file (the driver keeps a short stdout tail; the keys that must
+        # survive it are scalars at the END of the line); the line itself carries a compact copy
+        try:
+            sys.stderr.write("[bench] rooflines_all " + json.dumps(rooflines) + "\n")
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump(rooflines, open(os.path.join(ROOT, "gpurun_out", f"rooflines_all_{world}gpu.json"), "w"), indent=1)
+        except OSError:
+            pass
+        line["rooflines_all"] = {k: {"frac": round(v["frac"], 4), "achieved": round(v["achieved"], 1), "unit": v["unit"], "ms": round(v["ms"], 4)}
+                                 for k, v in rooflines.items()}
         if world == 1 and not args.no_cpu_baseline:
             if prev_affinity:
                 os.sched_setaffinity(0, prev_affinity)
@@ -587,6 +785,32 @@ def run_ours(args):
                                     "sample": "5 forwards of B=8,T=60 (configs[0]) after 2 warm-up, hot path only; "
                                               f"with the text tower: {qps_cpu_t:.1f} questions/s",
                                     "with_text_tower": qps_cpu_t}
+        # ---- the keys the driver record keeps, last (scalars only inside e2e / roofline) -------------------------------------
+        line["gpu_launches"] = launches_per_step * args.steps
+        line["launches_per_step"] = launches_per_step
+        line["hot_path_tensor_frac_nominal"] = (flops_q * B / (step_ms * 1e-3)) / (tf_sust * 1e12)
+        # headline roofline = the dominant kernel family of the step per the ncu launch list (profiles/): the bf16x3 tcgen05 GEMM
+        # at its largest shape; the other kinds, the HBM-class Gaussian-expert kernel north_star names and the ToMe chain ride
+        # along in rooflines_all
+        key = "gemm_bf16x3_avq_in_src"
+        line["roofline"] = {k: rooflines[key][k] for k in ("bound", "achieved", "peak", "unit", "frac", "frac_of_sustained", "traffic")}
+        line["roofline"]["kernel"] = ("tc::gemm_tc_kernel<KIND_BF16X3,256,3,EPI,CG=2> (cta_group::2 pair tiles 256x256) AVQCrossAttn packed "
+                                       "in-proj [30720,512]x[3584,512]^T")
+        line["roofline"]["note"] = rooflines[key]["note"]
+        for nm in ("gauss_reduce_f32", "gauss_reduce_bf16", "tome_chain_577_to_14"):
+            if nm in rooflines:
+                line["roofline"][nm + "_frac"] = round(rooflines[nm]["frac"], 4)
+        e2e = {"value": qps_e2e, "unit": "questions/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 8,
+               "ms_per_step": ms_e2e_max, "h2d_only_ms": parts.get("h2d_only_ms"), "compute_only_ms": parts.get("compute_only_ms"),
+               "text_tower_vs_fp32_logit_relerr": e2e_parity,
+               "fp16_patch_store_qps": world * B / (ms_e2e16_max * 1e-3),
+               "dp_eval_config4_resident_qps": dp_eval["questions_per_s"] if dp_eval else None}
+        if streaming and "fp16_store" in streaming:
+            f16, f32 = streaming["fp16_store"], streaming["fp32_store_sample"]
+            e2e.update(streaming_config4_fp16_cold_qps=f16["cold"]["questions_per_s"], streaming_config4_fp16_warm_qps=f16["warm"]["questions_per_s"],
+                       streaming_config4_fp16_cold_h2d_bytes=f16["cold"]["h2d_bytes"], streaming_config4_fp16_warm_h2d_bytes=f16["warm"]["h2d_bytes"],
+                       streaming_fp32_sample_cold_qps=f32["cold"]["questions_per_s"], streaming_fp32_sample_cold_h2d_bytes=f32["cold"]["h2d_bytes"])
+        line["e2e"] = e2e
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -596,5 +820,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.tome:
+        run_tome(a)
     else:
         run_ours(a)

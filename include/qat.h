@@ -15,7 +15,8 @@
  *  - every tensor is dense, row-major, in the reference's [B,T,...] order, fp32 unless noted.
  *  - return 0 on success; otherwise a QAT_E* code, with a thread-local message in
  *    qat_last_error().  Unsupported shapes / arch (!= sm_100) are errors, never fallbacks.
- *  - re-entrant: no global mutable state (nn.DataParallel drives one thread per GPU).
+ *  - re-entrant: no global mutable state on the data path (nn.DataParallel drives one thread per GPU); the only process-wide
+ *    state is the A/B option table (qat_set_option), atomics that each call snapshots on entry.
  */
 #ifndef QAT_H_
 #define QAT_H_
@@ -361,6 +362,25 @@ typedef struct {
 } QatClipTextArgs;
 int qat_clip_text_fwd(const QatClipTextArgs* a);
 
+/* ---- N3: batch assembly from a device-resident per-video feature cache.  dataset.py:132-159 loads the three
+ *      feature files of a question's video per QUESTION and trainutils.py:223-236 copies every batch to the device; with the
+ *      cache (qa_tiger_b200/datapipe.py) a video crosses the host link once and a batch is gathered in HBM:
+ *      dst[k][i, :] = src[k][slots[i], :] for k < n_tensors, one launch.  Rows are dense; row_bytes[k] % 16 == 0. ---- */
+#define QAT_GATHER_MAX 4
+typedef struct {
+  int32_t n;                    /* rows to gather (questions of the batch), <= 65535 */
+  int32_t n_tensors;            /* 1..QAT_GATHER_MAX (audio, video, patch) */
+  int32_t n_slots;              /* cache capacity in rows; a slot id outside [0, n_slots) fills the row with NaN bit patterns */
+  void* stream;
+  const int32_t* slots;         /* [n] device: cache row of each question's video */
+  const void* src[QAT_GATHER_MAX];   /* cache tensors: row s of tensor k starts at src[k] + s * src_stride[k] */
+  void* dst[QAT_GATHER_MAX];         /* batch tensors [n, row_bytes[k]], dense */
+  size_t row_bytes[QAT_GATHER_MAX];
+  size_t src_stride[QAT_GATHER_MAX]; /* bytes between cache rows (0 = dense = row_bytes[k]); the cache keeps a video's audio |
+                                        video | patch in ONE row so that a video is one host->device copy */
+} QatGatherArgs;
+int qat_gather_rows(const QatGatherArgs* a);
+
 /* ---- bookkeeping ---------------------------------------------------------------------------- */
 enum { QAT_OP_LINEAR = 0, QAT_OP_AVQ = 1, QAT_OP_PATCH = 2, QAT_OP_MOE = 3, QAT_OP_GROUND = 4,
        QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7, QAT_OP_CLIP_TEXT = 8, QAT_OP_FORWARD = 9 };
@@ -370,6 +390,12 @@ const char* qat_last_error(void);
 int qat_abi_version(void);
 /* number of kernel launches issued by this thread since the last reset (bench.py's gpu_launches) */
 long long qat_launch_count(int reset);
+/* A/B switches (profiling aids; defaults are the measured-faster paths): "gemm_cg", "gemm_bn", "attn_fp32_in", "patch_chunk",
+ * "patch_fp32_planes", "patch_no_fused_attn", "patch_no_fused_cross", "tome_match_rows", "moe_no_fused_reduce".  Process-wide;
+ * initialised once from the environment (QAT_<UPPER-CASE NAME>) when the library is loaded, never read from the environment
+ * again; every entry point snapshots them on entry, so sizing and execution of one call agree.  Set them between calls. */
+int qat_set_option(const char* name, int value);
+int qat_get_option(const char* name, int* value);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ FWD_CASES = {
     "fwd_k5": (5, 60, 10, 5, 714, 4),         # module defaults K<E
     "fwd_stress": (4, 120, 14, 14, 715, 5),   # BASELINE config 5 shape (T=120, E=K=14)
     "fwd_b256": (256, 60, 7, 7, 713, 1234),   # BASELINE config 2 batch (logits + ranks only)
+    "fwd_stress_b128": (128, 120, 14, 14, 715, 6),   # BASELINE config 5 at its own per-GPU batch (logits + ranks only)
 }
 
 

@@ -2,6 +2,7 @@
 point returns non-zero, a RuntimeError is raised ("errors, never fallbacks")."""
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import os
 import threading
@@ -142,6 +143,15 @@ class ClipTextArgs(C.Structure):
                 ("quest", C.c_void_p), ("words", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+GATHER_MAX = 4
+
+
+class GatherArgs(C.Structure):
+    _fields_ = [("n", C.c_int32), ("n_tensors", C.c_int32), ("n_slots", C.c_int32), ("stream", C.c_void_p), ("slots", C.c_void_p),
+                ("src", C.c_void_p * GATHER_MAX), ("dst", C.c_void_p * GATHER_MAX), ("row_bytes", C.c_size_t * GATHER_MAX),
+                ("src_stride", C.c_size_t * GATHER_MAX)]
+
+
 EXPORTS = {
     "qat_gemm": (C.c_int, [C.POINTER(GemmArgs)]),
     "qat_attention_fwd": (C.c_int, [C.POINTER(AttnArgs)]),
@@ -163,6 +173,9 @@ EXPORTS = {
     "qat_last_error": (C.c_char_p, []),
     "qat_abi_version": (C.c_int, []),
     "qat_launch_count": (C.c_longlong, [C.c_int]),
+    "qat_gather_rows": (C.c_int, [C.POINTER(GatherArgs)]),
+    "qat_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "qat_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
 }
 
 _lib = None
@@ -192,6 +205,28 @@ def lib():
 def check(rc: int, what: str):
     if rc != 0:
         raise RuntimeError(f"{what} failed (code {rc}): {lib().qat_last_error().decode()}")
+
+
+def set_option(name: str, value: int) -> None:
+    """A/B switch of the library (include/qat.h `qat_set_option`): process-wide, takes effect for calls entered afterwards."""
+    check(lib().qat_set_option(name.encode(), int(value)), "qat_set_option")
+
+
+def get_option(name: str) -> int:
+    v = C.c_int(0)
+    check(lib().qat_get_option(name.encode(), C.byref(v)), "qat_get_option")
+    return v.value
+
+
+@contextlib.contextmanager
+def option(name: str, value: int):
+    """with option("gemm_cg", 1): ...  -- set an A/B switch for the calls inside the block, restore it afterwards."""
+    prev = get_option(name)
+    set_option(name, value)
+    try:
+        yield
+    finally:
+        set_option(name, prev)
 
 
 def ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -238,8 +273,22 @@ class LN:
         self.c = LayerNormW(ptr(self.g), ptr(self.b))
 
 
+# Prepared (derived) weights -- concatenated in-projections, bf16 hi/lo and fp16 planes, W2ext -- are cached per module,
+# keyed on (epoch, data_ptr, _version) of every parameter.  `_version` moves on in-place tensor ops (`p.mul_()`, optimizer
+# steps) and `data_ptr` on `.to()` / load_state_dict into fresh storage, but writes through `.data` (`p.data.copy_(...)`,
+# EMA weight swaps) change NEITHER: call `invalidate_prepared()` after such writes.  nn.Module.load_state_dict and
+# `.to()/.cuda()/.half()` of the mirrored modules call it automatically (`_QatModule._apply` / `_load_from_state_dict`).
+_prepared_epoch = 0
+
+
+def invalidate_prepared() -> None:
+    """Drop every cached derived weight of every module (cheap: they are rebuilt lazily on the next forward)."""
+    global _prepared_epoch
+    _prepared_epoch += 1
+
+
 def params_version(module: torch.nn.Module):
-    return tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=True))
+    return (_prepared_epoch,) + tuple((p.data_ptr(), p._version) for p in module.parameters(recurse=True))
 
 
 GEMM_SIMT, GEMM_TF32, GEMM_BF16X3, GEMM_F16 = 0, 1, 2, 3
@@ -320,16 +369,24 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
 
 # ---- workspace ----------------------------------------------------------------------------------
 _ws: Dict[Tuple[int, int], torch.Tensor] = {}
+_ws_retired: list = []          # superseded buffers that a captured CUDA graph may still point into: never released
+_ws_lock = threading.Lock()     # nn.DataParallel drives one Python thread per GPU through this module
 
 
 def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Per (device, stream) grow-only scratch buffer owned by torch's caching allocator."""
+    """Per (device, stream) grow-only scratch buffer owned by torch's caching allocator.  A buffer that is outgrown while a
+    stream capture is (or may have been) using it is retired, not freed: a captured graph has its address baked in."""
     key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
-    buf = _ws.get(key)
-    if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _ws[key] = buf
-    return buf
+    with _ws_lock:
+        buf = _ws.get(key)
+        if buf is None or buf.numel() < nbytes:
+            if buf is not None and (getattr(buf, "_qat_captured", False) or torch.cuda.is_current_stream_capturing()):
+                _ws_retired.append(buf)
+            buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            _ws[key] = buf
+        if torch.cuda.is_current_stream_capturing():
+            buf._qat_captured = True
+        return buf
 
 
 def run(op: int, fn_name: str, args, device: torch.device):

@@ -313,318 +313,6 @@ __global__ void __launch_bounds__(256) attn_fewq_kernel(AttnP p) {
   }
 }
 
-// ---- register-tiled core for the 60..128-token sequences of AVQCrossAttn: one CTA (128 threads) per
-// (sequence, head).  S = (Q*scale) K^T and O = P V are both 4x(4*CK4) / 4x8 register-tiled FFMA GEMMs out of
-// shared memory (operands stored transposed so every read is a conflict-free LDS.128); the softmax of a row
-// lives in 8 adjacent lanes (3 xor-shuffles).  Queries are processed in passes of 64 rows.
-template <int CK4>   // key columns per thread = 4*CK4  (Lk <= 32*CK4)
-__global__ void __launch_bounds__(128) attn_tile_kernel(AttnP p) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int LKP = 32 * CK4;               // padded key count
-  constexpr int QS = 68, PS = 68;             // row strides (floats) of the transposed Q / P tiles
-  const int Lq = p.Lq, Lk = p.Lk;
-  float* Qt = smem;                           // [64 d][QS]   Q^T of the current 64-row pass (pre-scaled)
-  float* Kt = Qt + 64 * QS;                   // [64 d][LKP+4] K^T, zero padded
-  float* Vs = Kt + 64 * (LKP + 4);            // [LKP][64]
-  float* Pt = Vs + LKP * 64;                  // [LKP j][PS]  P^T of the current pass
-  const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int kn = (n + p.k_shift) % p.k_mod;
-  const int tid = threadIdx.x, tx = tid & 7, ty = tid >> 3;
-  const float* kb = p.k + kn * p.k_sn + h * HD;
-  const float* vb = p.v + kn * p.k_sn + h * HD;
-  // stage K^T (lanes walk the key index: conflict-free transposed stores) and V
-  for (int f = tid; f < LKP * 16; f += 128) {
-    const int j = f % LKP, c4 = f / LKP;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-    if (j < Lk) {
-      kv = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
-      vv = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
-    }
-    Kt[(c4 * 4 + 0) * (LKP + 4) + j] = kv.x;
-    Kt[(c4 * 4 + 1) * (LKP + 4) + j] = kv.y;
-    Kt[(c4 * 4 + 2) * (LKP + 4) + j] = kv.z;
-    Kt[(c4 * 4 + 3) * (LKP + 4) + j] = kv.w;
-    *reinterpret_cast<float4*>(Vs + j * 64 + c4 * 4) = vv;
-  }
-  const float invH = 1.f / p.H;
-  for (int r0 = 0; r0 < Lq; r0 += 64) {
-    __syncthreads();                           // previous pass done with Qt / Pt (and K/V staged on pass 0)
-    for (int f = tid; f < 64 * 16; f += 128) {
-      const int i = f & 63, c4 = f >> 6;
-      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + i < Lq) qv = __ldg(reinterpret_cast<const float4*>(p.q + n * p.q_sn + (r0 + i) * p.q_si + h * HD) + c4);
-      Qt[(c4 * 4 + 0) * QS + i] = qv.x * p.scale;
-      Qt[(c4 * 4 + 1) * QS + i] = qv.y * p.scale;
-      Qt[(c4 * 4 + 2) * QS + i] = qv.z * p.scale;
-      Qt[(c4 * 4 + 3) * QS + i] = qv.w * p.scale;
-    }
-    __syncthreads();
-    // ---- S tile: rows ty*4+r, cols tx*4 + 32*c + e ----
-    float acc[4][4 * CK4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4 * CK4; ++c) acc[r][c] = 0.f;
-#pragma unroll 4
-    for (int d = 0; d < 64; ++d) {
-      const float4 a = *reinterpret_cast<const float4*>(Qt + d * QS + ty * 4);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-      for (int c = 0; c < CK4; ++c) {
-        const float4 b = *reinterpret_cast<const float4*>(Kt + d * (LKP + 4) + tx * 4 + 32 * c);
-        const float bv[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) acc[r][4 * c + e] = fmaf(av[r], bv[e], acc[r][4 * c + e]);
-      }
-    }
-    // ---- softmax over each row (8 lanes share a row) and P^T to shared ----
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      float mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < CK4; ++c)
-#pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (tx * 4 + 32 * c + e < Lk) mx = fmaxf(mx, acc[r][4 * c + e]);
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
-      float sum = 0.f;
-#pragma unroll
-      for (int c = 0; c < CK4; ++c)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float ev = (tx * 4 + 32 * c + e < Lk) ? expf(acc[r][4 * c + e] - mx) : 0.f;
-          acc[r][4 * c + e] = ev;
-          sum += ev;
-        }
-      sum += __shfl_xor_sync(0xffffffffu, sum, 1);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 2);
-      sum += __shfl_xor_sync(0xffffffffu, sum, 4);
-      const int i = ty * 4 + r;
-#pragma unroll
-      for (int c = 0; c < CK4; ++c)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int j = tx * 4 + 32 * c + e;
-          const float pj = acc[r][4 * c + e] / sum;
-          Pt[j * PS + i] = pj;
-          if (p.attw && j < Lk && r0 + i < Lq) atomicAdd(p.attw + ((long long)n * Lq + r0 + i) * Lk + j, pj * invH);
-        }
-    }
-    __syncthreads();
-    // ---- O tile: rows ty*4+r, cols tx*4 + 32*c + e (c < 2) ----
-    float o[4][8];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 8; ++c) o[r][c] = 0.f;
-#pragma unroll 4
-    for (int j = 0; j < Lk; ++j) {
-      const float4 a = *reinterpret_cast<const float4*>(Pt + j * PS + ty * 4);
-      const float av[4] = {a.x, a.y, a.z, a.w};
-      const float4 b0 = *reinterpret_cast<const float4*>(Vs + j * 64 + tx * 4);
-      const float4 b1 = *reinterpret_cast<const float4*>(Vs + j * 64 + 32 + tx * 4);
-      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[r][e] = fmaf(av[r], bv[e], o[r][e]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int i = r0 + ty * 4 + r;
-      if (i < Lq) {
-        const long long row = n * p.o_rn + i * p.o_ri;
-        act_store4(p.o, row, h * HD + tx * 4, make_float4(o[r][0], o[r][1], o[r][2], o[r][3]));
-        act_store4(p.o, row, h * HD + 32 + tx * 4, make_float4(o[r][4], o[r][5], o[r][6], o[r][7]));
-      }
-    }
-  }
-}
-
-template <int CK4>
-inline int attn_tile_launch(Ctx& c, const AttnP& p) {
-  constexpr int LKP = 32 * CK4;
-  size_t smem = (size_t)(64 * 68 + 64 * (LKP + 4) + LKP * 64 + LKP * 68) * 4;
-  auto kern = attn_tile_kernel<CK4>;
-  if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
-  return check_launch("attn_tile_kernel");
-}
-
-// ---- tensor-core core for the 60..128-token sequences: mma.sync m16n8k8 TF32 with the 3xTF32 split
-// (x = hi + lo, hi = rna_tf32(x), lo = rna_tf32(x - hi); D += lo*hi + hi*lo + hi*hi => fp32-faithful, the
-// serial chain into the router needs it).  These sequences are far too short for a 128-row
-// tcgen05 tile per (sample, head); the warp-level MMA keeps Q/K/V/P in shared memory and S/O in registers.
-// One CTA (4 warps) per (sequence, head); warp w owns query rows 16w..16w+15 of each 64-row pass.
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], const uint32_t (&bh)[2],
-                                     const uint32_t (&bl)[2]) {
-  mma_tf32(d, al, bh);
-  mma_tf32(d, ah, bl);
-  mma_tf32(d, ah, bh);
-}
-
-template <int NT8>   // key tiles of 8 columns: Lk <= 8*NT8
-__global__ void __launch_bounds__(128) attn_mma_kernel(AttnP p) {
-  extern __shared__ __align__(16) float smem[];
-  constexpr int LKP = 8 * NT8;
-  constexpr int QS = 68, KS = 68, VS = 72, PS = LKP + 4;   // strides chosen so every fragment load hits 32 banks
-  const int Lq = p.Lq, Lk = p.Lk;
-  float* Qs = smem;                 // [64][QS]  pre-scaled queries of the current pass
-  float* Ks = Qs + 64 * QS;         // [LKP][KS]
-  float* Vs = Ks + LKP * KS;        // [LKP][VS]
-  float* Ps = Vs + LKP * VS;        // [64][PS]  probabilities of the current pass
-  const int n = blockIdx.x / p.H, h = blockIdx.x % p.H;
-  const int kn = (n + p.k_shift) % p.k_mod;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const float* kb = p.k + kn * p.k_sn + h * HD;
-  const float* vb = p.v + kn * p.k_sn + h * HD;
-  for (int f = tid; f < LKP * 16; f += 128) {
-    const int j = f >> 4, c4 = f & 15;
-    float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
-    if (j < Lk) {
-      kv = __ldg(reinterpret_cast<const float4*>(kb + j * p.k_si) + c4);
-      vv = __ldg(reinterpret_cast<const float4*>(vb + j * p.k_si) + c4);
-    }
-    *reinterpret_cast<float4*>(Ks + j * KS + c4 * 4) = kv;
-    *reinterpret_cast<float4*>(Vs + j * VS + c4 * 4) = vv;
-  }
-  const float invH = 1.f / p.H;
-  const int rb = warp * 16;
-  for (int r0 = 0; r0 < Lq; r0 += 64) {
-    __syncthreads();
-    for (int f = tid; f < 64 * 16; f += 128) {
-      const int i = f >> 4, c4 = f & 15;
-      float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (r0 + i < Lq) qv = __ldg(reinterpret_cast<const float4*>(p.q + n * p.q_sn + (r0 + i) * p.q_si + h * HD) + c4);
-      qv.x *= p.scale; qv.y *= p.scale; qv.z *= p.scale; qv.w *= p.scale;
-      *reinterpret_cast<float4*>(Qs + i * QS + c4 * 4) = qv;
-    }
-    __syncthreads();
-    // ---- S = Q K^T : C fragments, rows rb+g / rb+g+8, cols nt*8 + 2t + {0,1} ----
-    float sacc[NT8][4];
-#pragma unroll
-    for (int nt = 0; nt < NT8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) sacc[nt][e] = 0.f;
-#pragma unroll
-    for (int k0 = 0; k0 < HD; k0 += 8) {
-      uint32_t ah[4], al[4];
-      split_tf32(Qs[(rb + g) * QS + k0 + t], ah[0], al[0]);
-      split_tf32(Qs[(rb + g + 8) * QS + k0 + t], ah[1], al[1]);
-      split_tf32(Qs[(rb + g) * QS + k0 + t + 4], ah[2], al[2]);
-      split_tf32(Qs[(rb + g + 8) * QS + k0 + t + 4], ah[3], al[3]);
-#pragma unroll
-      for (int nt = 0; nt < NT8; ++nt) {
-        uint32_t bh[2], bl[2];
-        split_tf32(Ks[(nt * 8 + g) * KS + k0 + t], bh[0], bl[0]);
-        split_tf32(Ks[(nt * 8 + g) * KS + k0 + t + 4], bh[1], bl[1]);
-        mma3(sacc[nt], ah, al, bh, bl);
-      }
-    }
-    // ---- softmax over the two rows this thread shares with its 3 quad neighbours ----
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) {
-      const int c = nt * 8 + 2 * t;
-      if (c < Lk) { mx0 = fmaxf(mx0, sacc[nt][0]); mx1 = fmaxf(mx1, sacc[nt][2]); }
-      if (c + 1 < Lk) { mx0 = fmaxf(mx0, sacc[nt][1]); mx1 = fmaxf(mx1, sacc[nt][3]); }
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) {
-      const int c = nt * 8 + 2 * t;
-      sacc[nt][0] = c < Lk ? expf(sacc[nt][0] - mx0) : 0.f;
-      sacc[nt][1] = c + 1 < Lk ? expf(sacc[nt][1] - mx0) : 0.f;
-      sacc[nt][2] = c < Lk ? expf(sacc[nt][2] - mx1) : 0.f;
-      sacc[nt][3] = c + 1 < Lk ? expf(sacc[nt][3] - mx1) : 0.f;
-      s0 += sacc[nt][0] + sacc[nt][1];
-      s1 += sacc[nt][2] + sacc[nt][3];
-    }
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-    s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-    s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-#pragma unroll
-    for (int nt = 0; nt < NT8; ++nt) {
-      const int c = nt * 8 + 2 * t;
-      const float p00 = sacc[nt][0] / s0, p01 = sacc[nt][1] / s0, p10 = sacc[nt][2] / s1, p11 = sacc[nt][3] / s1;
-      *reinterpret_cast<float2*>(Ps + (rb + g) * PS + c) = make_float2(p00, p01);
-      *reinterpret_cast<float2*>(Ps + (rb + g + 8) * PS + c) = make_float2(p10, p11);
-      if (p.attw) {
-        const int i0 = r0 + rb + g, i1 = i0 + 8;
-        float* w0 = p.attw + ((long long)n * Lq + i0) * Lk;
-        float* w1 = p.attw + ((long long)n * Lq + i1) * Lk;
-        if (i0 < Lq && c < Lk) atomicAdd(w0 + c, p00 * invH);
-        if (i0 < Lq && c + 1 < Lk) atomicAdd(w0 + c + 1, p01 * invH);
-        if (i1 < Lq && c < Lk) atomicAdd(w1 + c, p10 * invH);
-        if (i1 < Lq && c + 1 < Lk) atomicAdd(w1 + c + 1, p11 * invH);
-      }
-    }
-    __syncwarp();    // P rows of this warp are private to it
-    // ---- O = P V : C fragments, rows rb+g / rb+g+8, cols dt*8 + 2t + {0,1} ----
-    float oacc[8][4];
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) oacc[dt][e] = 0.f;
-    const int kend = (Lk + 7) & ~7;
-    for (int k0 = 0; k0 < kend; k0 += 8) {
-      uint32_t ah[4], al[4];
-      split_tf32(Ps[(rb + g) * PS + k0 + t], ah[0], al[0]);
-      split_tf32(Ps[(rb + g + 8) * PS + k0 + t], ah[1], al[1]);
-      split_tf32(Ps[(rb + g) * PS + k0 + t + 4], ah[2], al[2]);
-      split_tf32(Ps[(rb + g + 8) * PS + k0 + t + 4], ah[3], al[3]);
-#pragma unroll
-      for (int dt = 0; dt < 8; ++dt) {
-        uint32_t bh[2], bl[2];
-        split_tf32(Vs[(k0 + t) * VS + dt * 8 + g], bh[0], bl[0]);
-        split_tf32(Vs[(k0 + t + 4) * VS + dt * 8 + g], bh[1], bl[1]);
-        mma3(oacc[dt], ah, al, bh, bl);
-      }
-    }
-    const int i0 = r0 + rb + g, i1 = i0 + 8;
-#pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      const int col = h * HD + dt * 8 + 2 * t;
-      if (i0 < Lq) act_store2(p.o, n * p.o_rn + i0 * p.o_ri, col, oacc[dt][0], oacc[dt][1]);
-      if (i1 < Lq) act_store2(p.o, n * p.o_rn + i1 * p.o_ri, col, oacc[dt][2], oacc[dt][3]);
-    }
-  }
-}
-
-template <int NT8>
-inline int attn_mma_launch(Ctx& c, const AttnP& p) {
-  constexpr int LKP = 8 * NT8;
-  size_t smem = (size_t)(64 * 68 + LKP * 68 + LKP * 72 + 64 * (LKP + 4)) * 4;
-  auto kern = attn_mma_kernel<NT8>;
-  QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)(p.nseq * p.H), 128, smem, c.stream>>>(p);
-  return check_launch("attn_mma_kernel");
-}
-
 // ---- fp16 tensor-core fragments (mma.sync m16n8k16, fp32 accumulate) -----------------------------------------
 __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t saddr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
@@ -922,18 +610,7 @@ inline int attention(Ctx& c, const AttnP& p) {
     return check_launch("attn_rows_kernel");
   }
   if (p.Lk > 32 || p.Lq >= 32) {
-    const char* ffma = getenv("QAT_ATTN_FFMA");     // A/B switches: 1 = register-tiled FFMA core, 2 = 3xTF32 m16n8k8 core
-    if (!ffma || ffma[0] == '0') {
-      return attn_mma16_dispatch<false>(c, p);
-    }
-    if (ffma[0] == '2') {
-      if (p.Lk <= 64) return attn_mma_launch<8>(c, p);
-      if (p.Lk <= 96) return attn_mma_launch<12>(c, p);
-      return attn_mma_launch<16>(c, p);
-    }
-    if (p.Lk <= 64) return attn_tile_launch<2>(c, p);
-    if (p.Lk <= 96) return attn_tile_launch<3>(c, p);
-    return attn_tile_launch<4>(c, p);
+    return attn_mma16_dispatch<false>(c, p);
   }
   if (p.Lk <= 32) {
     constexpr int WPB = 8;

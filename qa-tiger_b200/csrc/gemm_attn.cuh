@@ -28,252 +28,9 @@ struct GemmAttnP {
   int ldo = 0;
 };
 
-constexpr int GA_STAGES = 4;
-constexpr int GA_BN = 192;
 constexpr int GA_A_BYTES = 128 * 128;                  // 128 rows x 64 fp16
-constexpr int GA_W_BYTES = GA_BN * 128;                // 192 rows x 64 fp16
-constexpr int GA_STAGE_BYTES = GA_A_BYTES + GA_W_BYTES;
-constexpr int GA_QKV_STRIDE = (GA_BN + 8) * 2;         // 400 bytes per row: conflict-free ldmatrix / 16-byte stores
-constexpr int GA_QKV_ROWS = 126;                       // rows of the tile kept for the attention (9 frames x 14 tokens); with
-                                                       // 128 the 4-stage ring would exceed the 227 KB of shared memory
-constexpr int GA_QKV_BYTES = GA_QKV_ROWS * GA_QKV_STRIDE;
-constexpr int GA_O_BYTES = 128 * 128;                  // [128 rows][64 fp16], 128B swizzle (TMA store box)
-constexpr int GA_BAR_BYTES = (2 * GA_STAGES + 4) * 8 + 16;
-constexpr int GA_SMEM = GA_STAGES * GA_STAGE_BYTES + GA_O_BYTES + GA_QKV_BYTES + GA_BAR_BYTES + 1024;
-static_assert(GA_SMEM <= 232448, "gemm_attn: shared-memory budget");
-
-__global__ void __launch_bounds__(384, 1)
-gemm_attn_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, const __grid_constant__ CUtensorMap mO,
-                 GemmAttnP p) {
-  extern __shared__ unsigned char smem_dyn[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* tiles = smem;
-  unsigned char* sO = smem + GA_STAGES * GA_STAGE_BYTES;                  // 1024-aligned
-  unsigned char* sQKV = sO + GA_O_BYTES;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sQKV + GA_QKV_BYTES);
-  uint64_t* empty = full + GA_STAGES;
-  uint64_t* tfull = empty + GA_STAGES;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = p.P, H = p.H, D = H * 64;
-  const int FPT = 128 / P, RPT = FPT * P;                                 // frames / rows per tile
-  const int nkb = p.K / 64;
-  const int tiles_m = (p.nframes + FPT - 1) / FPT;
-  const int ntiles = tiles_m * H;
-
-  if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mA)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mW)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&mO)) : "memory");
-    for (int s = 0; s < GA_STAGES; ++s) {
-      mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 8);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
-
-  // producer and MMA loops run warp-uniform, one elected lane issues (operands stay in uniform registers; gemm_tc.cuh)
-  if (warp == 0) {
-    {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int m0 = (t / H) * RPT, h = t % H;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % GA_STAGES;
-          mbar_wait(&empty[s], ((it / GA_STAGES) & 1) ^ 1);
-          unsigned char* st = tiles + s * GA_STAGE_BYTES;
-          const int k0 = kb * 64;
-          if (elect_one()) {
-            mbar_arrive_expect_tx(&full[s], GA_STAGE_BYTES);
-            tma_load_2d(st, &mA, &full[s], k0, m0);
-            tma_load_2d(st + GA_A_BYTES, &mW, &full[s], k0, h * 64);
-            tma_load_2d(st + GA_A_BYTES + 8192, &mW, &full[s], k0, D + h * 64);
-            tma_load_2d(st + GA_A_BYTES + 16384, &mW, &full[s], k0, 2 * D + h * 64);
-          }
-          __syncwarp();
-        }
-      }
-    }
-  } else if (warp == 1) {
-    {
-      constexpr uint32_t idesc = umma_idesc(0, 128, GA_BN);
-      uint32_t it = 0, lt = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-        const uint32_t as = lt & 1;
-        mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tacc = tmem_base + as * 256;
-        for (int kb = 0; kb < nkb; ++kb, ++it) {
-          const int s = it % GA_STAGES;
-          mbar_wait(&full[s], (it / GA_STAGES) & 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a0 = smem_u32(tiles + s * GA_STAGE_BYTES);
-          const uint64_t dA = umma_desc(a0), dW = umma_desc(a0 + GA_A_BYTES);
-          if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) umma<KIND_F16>(tacc, dA + uint64_t(k * 2), dW + uint64_t(k * 2), idesc, (kb | k) != 0);
-            umma_commit(&empty[s]);
-          }
-          __syncwarp();
-        }
-        if (elect_one()) umma_commit(&tfull[as]);
-        __syncwarp();
-      }
-    }
-  } else {
-    const int ew = warp - 2;                 // 0..9; warps 8, 9 of the epilogue group only run attention
-    const int lg = warp & 3, half = ew >> 2;
-    const uint32_t sqkv = smem_u32(sQKV), so = smem_u32(sO);
-    const int g = lane >> 2, tq = lane & 3, m8 = lane >> 3, r8 = lane & 7;
-    uint32_t lt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-      const int mt = t / H, h = t % H, m0 = mt * RPT;
-      const uint32_t as = lt & 1;
-      const int row = lg * 32 + lane;
-      if (ew < 8) {
-      mbar_wait(&tfull[as], (lt >> 1) & 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + as * 256 + half * 96 + (uint32_t(lg * 32) << 16);
-      // ---- 1. accumulator -> (+bias) -> fp16 [126][192] tile ----
-#pragma unroll 1
-      for (int c = 0; c < 3; ++c) {
-        const int col0 = half * 96 + c * 32;                          // q: [0,64), k: [64,128), v: [128,192)
-        uint32_t v[32];
-        tmem_ld32(tacc + uint32_t(c * 32), v);
-        const float* bptr = p.bias + (col0 >> 6) * D + h * 64 + (col0 & 63);
-        float4 bb[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) bb[q] = __ldg(reinterpret_cast<const float4*>(bptr) + q);
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c == 2) {
-          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
-        }
-#pragma unroll
-        for (uint32_t q = 0; q < 4; ++q) {
-          if (row >= RPT) break;                                      // rows beyond the tile's frames belong to the next tile
-          const float4 b0 = bb[2 * q], b1 = bb[2 * q + 1];
-          sts128(sqkv + row * GA_QKV_STRIDE + col0 * 2 + q * 16,
-                 pack_half2(__uint_as_float(v[8 * q]) + b0.x, __uint_as_float(v[8 * q + 1]) + b0.y),
-                 pack_half2(__uint_as_float(v[8 * q + 2]) + b0.z, __uint_as_float(v[8 * q + 3]) + b0.w),
-                 pack_half2(__uint_as_float(v[8 * q + 4]) + b1.x, __uint_as_float(v[8 * q + 5]) + b1.y),
-                 pack_half2(__uint_as_float(v[8 * q + 6]) + b1.z, __uint_as_float(v[8 * q + 7]) + b1.w));
-        }
-      }
-      }
-      // the previous tile's O box must have left shared memory before anyone overwrites it
-      if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      asm volatile("bar.sync 1, 320;" ::: "memory");
-      // ---- 2. one warp per frame: softmax(q k^T * scale) v on mma.sync ----
-      for (int f = ew; f < FPT; f += 10) {
-        if (mt * FPT + f >= p.nframes) break;
-        const uint32_t fb = sqkv + (f * P) * GA_QKV_STRIDE;
-        float s[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-        {
-          const int qrow = min(r8 + (m8 & 1) * 8, P - 1), qcol = (m8 >> 1) * 8;
-          const int krow = min(r8 + (m8 >> 1) * 8, P - 1), kcol = (m8 & 1) * 8;
-          const uint32_t qa = fb + qrow * GA_QKV_STRIDE + qcol * 2;
-          const uint32_t ka = fb + krow * GA_QKV_STRIDE + (64 + kcol) * 2;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            uint32_t a[4], b[4];
-            ldsm_x4(a, qa + ks * 32);
-            ldsm_x4(b, ka + ks * 32);
-            mma_f16(s[0], a, b[0], b[1]);
-            mma_f16(s[1], a, b[2], b[3]);
-          }
-        }
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const bool ok = nt * 8 + 2 * tq + e < P;
-            s[nt][e] = ok ? s[nt][e] * p.scale : -INFINITY;
-            s[nt][2 + e] = ok ? s[nt][2 + e] * p.scale : -INFINITY;
-            mx0 = fmaxf(mx0, s[nt][e]);
-            mx1 = fmaxf(mx1, s[nt][2 + e]);
-          }
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-        mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-        mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 2; ++nt)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            s[nt][e] = expf(s[nt][e] - mx0);
-            s[nt][2 + e] = expf(s[nt][2 + e] - mx1);
-            s0 += s[nt][e];
-            s1 += s[nt][2 + e];
-          }
-        s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
-        s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 1);
-        s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
-        const float i0 = 1.f / s0, i1 = 1.f / s1;
-        uint32_t pa[4];
-        pa[0] = pack_half2(s[0][0] * i0, s[0][1] * i0);
-        pa[1] = pack_half2(s[0][2] * i1, s[0][3] * i1);
-        pa[2] = pack_half2(s[1][0] * i0, s[1][1] * i0);
-        pa[3] = pack_half2(s[1][2] * i1, s[1][3] * i1);
-        float o[8][4];
-#pragma unroll
-        for (int dt = 0; dt < 8; ++dt)
-#pragma unroll
-          for (int e = 0; e < 4; ++e) o[dt][e] = 0.f;
-        {
-          const int vrow = min(r8 + (m8 & 1) * 8, P - 1), vcol = (m8 >> 1) * 8;
-          const uint32_t va = fb + vrow * GA_QKV_STRIDE + (128 + vcol) * 2;
-#pragma unroll
-          for (int dp = 0; dp < 4; ++dp) {
-            uint32_t b[4];
-            ldsm_x4_t(b, va + dp * 32);
-            mma_f16(o[2 * dp], pa, b[0], b[1]);
-            mma_f16(o[2 * dp + 1], pa, b[2], b[3]);
-          }
-        }
-        // O rows into the 128B-swizzled store box: row r, 16-byte chunk dt, bytes 4*tq
-        const int ra = f * P + g, rb = f * P + g + 8;
-#pragma unroll
-        for (uint32_t dt = 0; dt < 8; ++dt) {
-          if (g < P) asm volatile("st.shared.b32 [%0], %1;" ::"r"(so + ra * 128 + ((dt ^ uint32_t(ra & 7)) << 4) + tq * 4), "r"(pack_half2(o[dt][0], o[dt][1])) : "memory");
-          if (g + 8 < P) asm volatile("st.shared.b32 [%0], %1;" ::"r"(so + rb * 128 + ((dt ^ uint32_t(rb & 7)) << 4) + tq * 4), "r"(pack_half2(o[dt][2], o[dt][3])) : "memory");
-        }
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      asm volatile("bar.sync 1, 320;" ::: "memory");
-      // ---- 3. the head's O columns of the tile's rows leave through one TMA store (row tail clipped by the TMA unit) ----
-      if (ew == 0 && lane == 0) {
-        tma_store_2d(&mO, sO, h * 64, m0);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      }
-    }
-    if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  }
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
-  }
-}
+constexpr int GA_QKV_ROWS = 126;                       // rows of the tile kept for the attention (9 frames x 14 tokens): 128 rows would
+                                                       // push the ring + the two tile buffers past the 227 KB of shared memory
 
 // ---- both attentions of the block with a PIPELINED epilogue ----------------------------------------------------------------
 // CROSS = false: the self-attention above.  CROSS = true: the cross-attention of the same block (modules.py:692-698): the
@@ -573,38 +330,21 @@ inline int gemm_attn_f16(Ctx& c, const __half* X, int ldx, int nframes, int P, i
               "gemm_attn: tensors must be 16-byte aligned");
   const int D = H * 64, FPT = 128 / P, RPT = FPT * P;
   const long long M = (long long)nframes * P;
-  CUtensorMap mA, mW, mO;
+  CUtensorMap mA, mW;
   QAT_TRY(tc::make_map(&mA, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, K, ldx, 128));
   QAT_TRY(tc::make_map(&mW, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3 * D, K, K, 64));
-  {
-    tc::EncodeTiledFn fn = tc::encode_fn();
-    if (!fn) QAT_FAIL(QAT_ECUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[2] = {(cuuint64_t)D, (cuuint64_t)M};
-    cuuint64_t strides[1] = {(cuuint64_t)ldo * 2};
-    cuuint32_t box[2] = {64, (cuuint32_t)RPT};
-    cuuint32_t es[2] = {1, 1};
-    CUresult r = fn(&mO, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, O, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) QAT_FAIL(QAT_ECUDA, "cuTensorMapEncodeTiled (attention output map) failed with code %d", (int)r);
-  }
   tc::GemmAttnP p;
   p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
-  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GA_SMEM));
   const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  const char* serial = getenv("QAT_PATCH_ATTN_SERIAL");       // A/B switch: 1 = the serial-epilogue kernel with the TMA-store box
-  if (!(serial && serial[0] == '1')) {
-    p.o = O;
-    p.ldo = ldo;
-    QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GxCfg<false>::SMEM));
-    tc::gemm_attn_pipe_kernel<false><<<grid, 384, tc::GxCfg<false>::SMEM, c.stream>>>(mA, mW, p);
-    return check_launch("gemm_attn_pipe_kernel<self>");
-  }
-  tc::gemm_attn_kernel<<<grid, 384, tc::GA_SMEM, c.stream>>>(mA, mW, mO, p);
-  return check_launch("gemm_attn_kernel");
+  p.o = O;
+  p.ldo = ldo;
+  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GxCfg<false>::SMEM));
+  tc::gemm_attn_pipe_kernel<false><<<grid, 384, tc::GxCfg<false>::SMEM, c.stream>>>(mA, mW, p);
+  return check_launch("gemm_attn_pipe_kernel<self>");
 }
 
 // O[nframes * 2, D] (fp16) = per-frame softmax(Q (X Wk^T + bk)^T / 8)(X Wv^T + bv) for the two projected query rows

@@ -160,14 +160,20 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+#ifdef QAT_PROFILE_BUILD
+#define QAT_DBG(p, bit) ((p).dbg & (bit))
+#else
+#define QAT_DBG(p, bit) 0
+#endif
+
 struct GemmP {
   int M, N, K;
   Epi epi;
   Act C;
   int pair_f16;    // 1: the (hi, lo) output pair is fp16 (Act::ph / pl, through the mChi / mClo maps) instead of bf16
   int tma_res;     // 1: the fp16 residual (epi.res_h) arrives through the mR tensor map into the warp's box (fp16-only output)
-  int dbg;         // profiling switches (QAT_GEMM_DBG): 1 = epilogue releases the accumulator without reading it,
-                   // 2 = MMA issuer skips the MMAs, 4 = epilogue skips its global stores
+  int dbg;         // QAT_PROFILE_BUILD only (per-tile cost model, tests/prof_gemm_k.py; compiled out of the product library):
+                   // 1 = epilogue releases the accumulator without reading it, 2 = MMA issuer skips the MMAs, 4 = no global stores
 };
 
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
@@ -325,7 +331,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < G::BK / G::UK; ++k) {
-              if (p.dbg & 2) break;
+              if (QAT_DBG(p, 2)) break;
               const uint64_t adv = uint64_t((k * G::UK * (KIND == KIND_TF32 ? 4 : 2)) >> 4);   // +32 bytes per MMA
               if (G::PLANES == 1) {
                 umma<KIND, CG>(tacc, dA0 + adv, dW0 + adv, idesc, (kb | k) != 0);
@@ -379,7 +385,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       const uint32_t tacc = tmem_base + as * BN + half * HALF_N + (uint32_t(lg * 32) << 16);
       const long long row = (long long)m0 + lg * 32 + lane;
       const bool row_ok = row < p.M;
-      if (p.dbg & 1) {
+      if (QAT_DBG(p, 1)) {
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         if (lane == 0) {
           if (CG == 2) mbar_arrive_cluster((as ? tempty_a1 : tempty_a0));
@@ -482,7 +488,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                    __float_as_uint(x[4 * q + 2]), __float_as_uint(x[4 * q + 3]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (elect_one() && !(p.dbg & 4)) {
+          if (elect_one() && !QAT_DBG(p, 4)) {
             tma_store_2d(&mCf, box, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -511,7 +517,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           }
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (elect_one() && !(p.dbg & 4)) {
+          if (elect_one() && !QAT_DBG(p, 4)) {
             tma_store_2d(&mChi, box, col0, crow);
             if (out_lo) tma_store_2d(&mClo, box + 2048, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -532,7 +538,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                    pack_half2(x[8 * q + 4], x[8 * q + 5]), pack_half2(x[8 * q + 6], x[8 * q + 7]));
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
-          if (elect_one() && !(p.dbg & 4)) {
+          if (elect_one() && !QAT_DBG(p, 4)) {
             tma_store_2d(&mCh, box + hb, col0, crow);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
@@ -642,8 +648,10 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
     QAT_TRY(make_store_map(&mR, epi.res_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, epi.ldr));
     p.tma_res = 1;
   }
-  const char* dbg = getenv("QAT_GEMM_DBG");
-  p.dbg = dbg ? atoi(dbg) : 0;
+  p.dbg = 0;
+#ifdef QAT_PROFILE_BUILD
+  if (const char* dbg = getenv("QAT_GEMM_DBG")) p.dbg = atoi(dbg);
+#endif
   // persistent units: CTAs, or CTA pairs walking 256-row pair tiles
   const long long ntiles = (long long)((N + BN - 1) / BN) * (((M + G::BM - 1) / G::BM + CG - 1) / CG);
   int dev = 0, sms = 148;
@@ -690,17 +698,15 @@ inline int check_common(long long M, int N, int K, long long lda, const Epi& epi
   return QAT_OK;
 }
 
-inline bool wide_tile(int N) {
-  const char* e = getenv("QAT_GEMM_BN");
-  if (e) return atoi(e) == 256;
+inline bool wide_tile(const Ctx& c, int N) {
+  if (c.opt.v[OPT_GEMM_BN] > 0) return c.opt.v[OPT_GEMM_BN] == 256;
   return N % 256 == 0;
 }
-// CTA pairs (cta_group::2) for the wide tile; QAT_GEMM_CG=1 / 2 is the A/B switch.  Measured on B200 (tests/prof_gemm.py):
+// CTA pairs (cta_group::2) for the wide tile; option gemm_cg = 1 / 2 is the A/B switch.  Measured on B200 (tests/prof_gemm.py):
 // bf16x3 +12 % (475 vs 425 nominal TFLOP/s at [15360,512]x[3584,512]^T), tf32 +4..10 %, f16 -3..7 % (its MMA time per tile is
 // close to its epilogue time, and a pair couples the two CTAs' epilogues to one accumulator hand-back), hence the defaults.
-inline bool pair_tile(long long M, bool dflt) {
-  const char* e = getenv("QAT_GEMM_CG");
-  if (e) return atoi(e) == 2;
+inline bool pair_tile(const Ctx& c, long long M, bool dflt) {
+  if (c.opt.v[OPT_GEMM_CG] > 0) return c.opt.v[OPT_GEMM_CG] == 2;
   return dflt && M > 128;
 }
 
@@ -711,8 +717,8 @@ inline int gemm_tc_tf32(Ctx& c, const float* A, int lda, long long M, const floa
   QAT_TRY(tc::check_common(M, N, K, lda, epi, C, 4));
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
   if (c.dry) return QAT_OK;
-  if (tc::wide_tile(N) && tc::pair_tile(M, true)) return tc::launch<tc::KIND_TF32, 256, 6, 2>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
-  if (tc::wide_tile(N)) return tc::launch<tc::KIND_TF32, 256, 4>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
+  if (tc::wide_tile(c, N) && tc::pair_tile(c, M, true)) return tc::launch<tc::KIND_TF32, 256, 6, 2>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
+  if (tc::wide_tile(c, N)) return tc::launch<tc::KIND_TF32, 256, 4>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
   return tc::launch<tc::KIND_TF32, 128, 6>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
 }
 
@@ -723,8 +729,8 @@ inline int gemm_tc_bf16x3(Ctx& c, const bf16* Ahi, const bf16* Alo, int lda, lon
   if (c.dry) return QAT_OK;
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(Ahi) | reinterpret_cast<uintptr_t>(Alo) | reinterpret_cast<uintptr_t>(Whi) |
                reinterpret_cast<uintptr_t>(Wlo)) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
-  if (tc::wide_tile(N) && tc::pair_tile(M, true)) return tc::launch<tc::KIND_BF16X3, 256, 3, 2>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
-  if (tc::wide_tile(N)) return tc::launch<tc::KIND_BF16X3, 256, 2>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
+  if (tc::wide_tile(c, N) && tc::pair_tile(c, M, true)) return tc::launch<tc::KIND_BF16X3, 256, 3, 2>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
+  if (tc::wide_tile(c, N)) return tc::launch<tc::KIND_BF16X3, 256, 2>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
   return tc::launch<tc::KIND_BF16X3, 128, 3>(c, Ahi, Alo, lda, M, Whi, Wlo, N, K, epi, C);
 }
 
@@ -733,8 +739,8 @@ inline int gemm_tc_f16(Ctx& c, const __half* A, int lda, long long M, const __ha
   QAT_TRY(tc::check_common(M, N, K, lda, epi, C, 2));
   if (c.dry) return QAT_OK;
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(W)) % 16 == 0, "gemm_tc: operands must be 16-byte aligned");
-  if (tc::wide_tile(N) && tc::pair_tile(M, false)) return tc::launch<tc::KIND_F16, 256, 6, 2>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
-  if (tc::wide_tile(N)) return tc::launch<tc::KIND_F16, 256, 4>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
+  if (tc::wide_tile(c, N) && tc::pair_tile(c, M, false)) return tc::launch<tc::KIND_F16, 256, 6, 2>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
+  if (tc::wide_tile(c, N)) return tc::launch<tc::KIND_F16, 256, 4>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
   return tc::launch<tc::KIND_F16, 128, 6>(c, A, nullptr, lda, M, W, nullptr, N, K, epi, C);
 }
 

@@ -3,6 +3,7 @@
 // No allocation, no synchronisation, no global mutable state.
 #include "attn_core.cuh"
 #include "attn_f16.cuh"
+#include "datapipe.cuh"
 #include "gauss.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
@@ -15,6 +16,24 @@ namespace qat {
 
 thread_local char g_err[512] = "";
 thread_local long long g_launches = 0;
+
+static const char* const kOptNames[OPT_COUNT] = {"gemm_cg", "gemm_bn", "attn_fp32_in", "patch_chunk", "patch_fp32_planes",
+                                                 "patch_no_fused_attn", "patch_no_fused_cross", "tome_match_rows",
+                                                 "moe_no_fused_reduce"};
+std::atomic<int> g_opt[OPT_COUNT];
+// defaults from the environment, read once at load time (QAT_GEMM_CG=1 etc.)
+static struct OptInit {
+  OptInit() {
+    for (int i = 0; i < OPT_COUNT; ++i) {
+      char env[64] = "QAT_";
+      size_t n = 4;
+      for (const char* s = kOptNames[i]; *s && n + 1 < sizeof(env); ++s) env[n++] = (*s >= 'a' && *s <= 'z') ? char(*s - 32) : *s;
+      env[n] = 0;
+      const char* e = getenv(env);
+      g_opt[i].store(e ? atoi(e) : 0, std::memory_order_relaxed);
+    }
+  }
+} g_opt_init;
 
 // rows [n0, n0+n) of one nn.Linear
 struct WView {
@@ -230,8 +249,7 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
   QAT_TRY(ensure_operand(c, Xw, BL, D, k_words));
   // S = in-projections of both modalities, rows [0,BT) audio, [BT,2BT) video; cols as in_src
   // bf16 mode: the in-projections leave as fp16 (hi, lo) plane pairs (same bytes as fp32), the form the attention cores eat
-  const bool pp = k_src == G_BF16X3 && k_words == G_BF16X3 && D % 8 == 0 &&
-                  !(getenv("QAT_ATTN_FP32_IN") && getenv("QAT_ATTN_FP32_IN")[0] == '1');
+  const bool pp = k_src == G_BF16X3 && k_words == G_BF16X3 && D % 8 == 0 && c.opt.v[OPT_ATTN_FP32_IN] != 1;
   Act S, KVw, O, X1, Hh, Y;
   if (pp) {
     QAT_TRY(act_alloc_pp(c, S, 2 * BT, 7 * D));
@@ -351,8 +369,7 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
   const int Cin = a->has_proj ? a->Cin : D;
   // frames per pass: 16 384 (B = 256, T = 60 is ONE pass: fewer launches and ragged last waves than two passes of 8 192, measured
   // 2 % of the step; 1.7 GB of workspace).  Smaller, L2-sized passes were measured slower still
-  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : 16384;
-  if (a->chunk_frames <= 0 && getenv("QAT_PATCH_CHUNK")) chunk = atoll(getenv("QAT_PATCH_CHUNK")) > 0 ? atoll(getenv("QAT_PATCH_CHUNK")) : chunk;
+  long long chunk = a->chunk_frames > 0 ? a->chunk_frames : (c.opt.v[OPT_PATCH_CHUNK] > 0 ? c.opt.v[OPT_PATCH_CHUNK] : 16384);
   if (chunk > BT) chunk = BT;
   const float scale = 0.125f;
   const WView Wp = wview(a->proj), Wsi = wview(a->slf_in), Wso = wview(a->slf_out), Wq = wview(a->crs_q), Wkv = wview(a->crs_kv);
@@ -360,8 +377,7 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
 
   // The whole block is off the router path (its outputs reach the logits only through the vt experts), so in bf16 mode
   // its remaining contractions run single-pass fp16 as well when the fp16 weights are supplied.
-  const bool sel16 = c.prec == QAT_PREC_BF16 && BT >= 512 && D % 64 == 0 &&
-                     !(getenv("QAT_PATCH_FP32_PLANES") && getenv("QAT_PATCH_FP32_PLANES")[0] == '1');
+  const bool sel16 = c.prec == QAT_PREC_BF16 && BT >= 512 && D % 64 == 0 && c.opt.v[OPT_PATCH_FP32_PLANES] != 1;
   // per-frame query rows [video; audio] -> q2 [BT, 2, D]  (modules.py:692: video first)
   Act Q2, O2, O3, Hm, Mo;
   {
@@ -386,7 +402,7 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
   // bf16 mode, P <= 16: activations between the kernels of a pass are single fp16 planes (half the bytes of
   // fp32, tf32-grade operands at twice the tf32 MMA rate), attention through mma.sync; DESIGN.md section 3.
   const bool f16_path = c.prec == QAT_PREC_BF16 && P <= 16 && H <= 8 && D % 64 == 0 && Wsi.h16 && Wso.h16 && Wkv.h16 &&
-                        !(getenv("QAT_PATCH_FP32_PLANES") && getenv("QAT_PATCH_FP32_PLANES")[0] == '1');
+                        c.opt.v[OPT_PATCH_FP32_PLANES] != 1;
   const size_t mark = c.mark();
   for (long long f0 = 0; f0 < BT; f0 += chunk) {
     const long long nf = (BT - f0 < chunk) ? BT - f0 : chunk;
@@ -423,8 +439,7 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
         }
       }
       QAT_TRY(act_alloc_h(c, Oa, rows, D));
-      const char* nofuse = getenv("QAT_PATCH_NO_FUSED_ATTN");      // A/B switch: in-proj GEMM + separate attention kernel
-      if (Wsi.bias && (128 / P) * P <= tc::GA_QKV_ROWS && !(nofuse && nofuse[0] == '1')) {
+      if (Wsi.bias && (128 / P) * P <= tc::GA_QKV_ROWS && c.opt.v[OPT_PATCH_NO_FUSED_ATTN] != 1) {
         // in-projection and the 14-token self-attention in one kernel: [q | k | v] never reaches HBM
         QAT_TRY(gemm_attn_f16(c, Pp.h, Pp.ld, (int)nf, P, H, D, Wsi.h16, Wsi.bias, scale, Oa.h, D));
       } else {
@@ -442,8 +457,7 @@ static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const 
         e.res_h = Pp.h; e.ldr = Pp.ld;
         QAT_TRY(gemm(c, G_F16, Oa, rows, Wso, e, P2));
       }
-      const char* nocross = getenv("QAT_PATCH_NO_FUSED_CROSS");    // A/B switch: K | V GEMM + separate cross-attention kernel
-      if (Q2.h && O2.h && !O2.f && !O2.hi && Wkv.bias && (128 / P) * P <= tc::GA_QKV_ROWS && !(nocross && nocross[0] == '1')) {
+      if (Q2.h && O2.h && !O2.f && !O2.hi && Wkv.bias && (128 / P) * P <= tc::GA_QKV_ROWS && c.opt.v[OPT_PATCH_NO_FUSED_CROSS] != 1) {
         // K | V projection and the two-query cross-attention in one kernel: [k | v] never reaches HBM
         QAT_TRY(gemm_attn_cross_f16(c, P2.h, P2.ld, (int)nf, P, H, D, Wkv.h16, Wkv.bias, scale, Q2.h + (size_t)f0 * 2 * D,
                                     O2.h + (size_t)f0 * 2 * D, D));
@@ -1034,6 +1048,10 @@ int qat_clip_text_fwd(const QatClipTextArgs* a) { return dispatch(a, a ? a->stre
 
 int qat_forward_fwd(const QatForwardArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_forward); }
 
+int qat_gather_rows(const QatGatherArgs* a) {
+  return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, [](const QatGatherArgs* g, Ctx& c) { return gather_rows(c, g); });
+}
+
 int qat_tome_clamp_r(int t, int r, int class_token) { return tome_clamp_r(t, r, class_token); }
 
 int qat_tome_chain_t_end(int t0, int n_steps, const int32_t* r_list, int class_token) {
@@ -1069,6 +1087,25 @@ size_t qat_workspace_bytes(int op, const void* args) {
     case QAT_OP_TOME_CHAIN: return dry_bytes(reinterpret_cast<const QatTomeChainArgs*>(args), QAT_PREC_FP32, run_tome_chain);
     default: return 0;
   }
+}
+
+int qat_set_option(const char* name, int value) {
+  if (!name) QAT_FAIL(QAT_EINVAL, "qat_set_option: name is NULL");
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptNames[i]) == 0) {
+      g_opt[i].store(value, std::memory_order_relaxed);
+      return QAT_OK;
+    }
+  QAT_FAIL(QAT_EINVAL, "qat_set_option: unknown option '%s'", name);
+}
+int qat_get_option(const char* name, int* value) {
+  if (!name || !value) QAT_FAIL(QAT_EINVAL, "qat_get_option: NULL argument");
+  for (int i = 0; i < OPT_COUNT; ++i)
+    if (strcmp(name, kOptNames[i]) == 0) {
+      *value = g_opt[i].load(std::memory_order_relaxed);
+      return QAT_OK;
+    }
+  QAT_FAIL(QAT_EINVAL, "qat_get_option: unknown option '%s'", name);
 }
 
 const char* qat_last_error(void) { return g_err; }

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <atomic>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -18,6 +19,27 @@ typedef __nv_bfloat16 bf16;
 // ------------------------------------------------------------------------------------------------
 extern thread_local char g_err[512];
 extern thread_local long long g_launches;
+
+// A/B switches (profiling aids; every default is the measured-faster path).  Process-wide, initialised ONCE from the environment
+// (QAT_<NAME>) when the library is loaded and changed afterwards only through qat_set_option(); each entry point snapshots
+// them into its Ctx, so the workspace dry run and the kernels of one call always see the same values and no getenv() runs on
+// the hot path.
+enum {
+  OPT_GEMM_CG = 0,            // 1 | 2: single-CTA / CTA-pair tiles for every tcgen05 kind (0 = per-kind default)
+  OPT_GEMM_BN,                // 128 | 256: tile width (0 = 256 when N % 256 == 0)
+  OPT_ATTN_FP32_IN,           // 1: fp32 instead of fp16 (hi, lo) plane-pair in-projections into the AVQ attention cores
+  OPT_PATCH_CHUNK,            // frames per PatchSelecter pass (0 = 16384)
+  OPT_PATCH_FP32_PLANES,      // 1: fp32 intermediates on the patch path
+  OPT_PATCH_NO_FUSED_ATTN,    // 1: in-projection GEMM + separate self-attention kernel
+  OPT_PATCH_NO_FUSED_CROSS,   // 1: K | V GEMM + separate cross-attention kernel
+  OPT_TOME_MATCH_ROWS,        // 1: the row-per-thread ToMe match kernel (the fallback of frames too long for the tiled one)
+  OPT_MOE_NO_FUSED_REDUCE,    // 1: expert first-layer GEMM writes the hidden tensor, separate gauss_reduce launches
+  OPT_COUNT
+};
+struct Options {
+  int v[OPT_COUNT];
+};
+extern std::atomic<int> g_opt[OPT_COUNT];
 
 #define QAT_FAIL(code, ...)                     \
   do {                                          \
@@ -232,6 +254,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   int prec = QAT_PREC_FP32;
   bool dry = false;
+  Options opt;          // snapshot of the A/B switches taken when the call entered the library
   char* base = nullptr;
   size_t cap = 0;
   size_t off = 0;
@@ -255,6 +278,7 @@ inline int ctx_init(Ctx& c, void* stream, int prec, void* ws, size_t ws_bytes, b
   c.dry = dry;
   c.base = reinterpret_cast<char*>(ws);
   c.cap = ws_bytes;
+  for (int i = 0; i < OPT_COUNT; ++i) c.opt.v[i] = g_opt[i].load(std::memory_order_relaxed);
   QAT_REQUIRE(prec == QAT_PREC_FP32 || prec == QAT_PREC_BF16, "unknown precision mode %d", prec);
   if (!dry) QAT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "workspace must be 256-byte aligned");
   return QAT_OK;

@@ -154,8 +154,15 @@ __global__ void __launch_bounds__(256) clip_embed_kernel(const int* __restrict__
   if (i >= rows * W4) return;
   const long long r = i / W4;
   const int c4 = (int)(i % W4);
-  int id = tokens[r];
-  id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+  const int id = tokens[r];
+  if (id < 0 || id >= vocab) {
+    // nn.Embedding raises on a bad id (a corrupt / mis-typed `quest` tensor).  The library cannot raise from the device without
+    // synchronising, so the row is poisoned instead: NaN propagates to that question's features and logits -- loud, never a
+    // plausible answer from a clamped id.  Host-side callers validate ids before the call (encoders.py).
+    const float q = __int_as_float(0x7fc00000);
+    reinterpret_cast<float4*>(x)[i] = make_float4(q, q, q, q);
+    return;
+  }
   const float4 a = __ldg(reinterpret_cast<const float4*>(tok_emb + (size_t)id * W4 * 4) + c4);
   const float4 b = __ldg(reinterpret_cast<const float4*>(pos_emb + (size_t)(r % L) * W4 * 4) + c4);
   reinterpret_cast<float4*>(x)[i] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);

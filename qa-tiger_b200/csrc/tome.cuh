@@ -554,8 +554,7 @@ inline int tome_match(Ctx& c, const float* metric, int N, int t, int C, int r, i
     const int seg_len = (((tb + nseg - 1) / nseg) + 7) / 8 * 8;
     nseg = (tb + seg_len - 1) / seg_len;
     const size_t smem_t = ((size_t)(ta + nseg * seg_len) * TM_LD + (size_t)2 * nseg * ta + (size_t)3 * ta) * 4 + 16;
-    const char* old = getenv("QAT_TOME_MATCH_ROWS");          // A/B switch: 1 = the row-per-thread kernel
-    if (rows > 0 && aw_n * nseg <= 20 && smem_t <= 220 * 1024 && !(old && old[0] == '1')) {
+    if (rows > 0 && aw_n * nseg <= 20 && smem_t <= 220 * 1024 && c.opt.v[OPT_TOME_MATCH_ROWS] != 1) {
       if (c.dry || N == 0) return QAT_OK;
       auto kern = R == 4 ? tome_match_tiled_kernel<64, 4> : (R == 3 ? tome_match_tiled_kernel<64, 3> : tome_match_tiled_kernel<64, 2>);
       if (smem_t > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));

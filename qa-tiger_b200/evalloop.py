@@ -96,8 +96,13 @@ def evaluate(forward_fn: Callable[[Dict[str, torch.Tensor]], torch.Tensor], data
     per = math.ceil(n / world)
     counters = torch.zeros(2 + 2 * N_QTYPES, dtype=torch.int64, device=device)
     preds = torch.full((per,), -1, dtype=torch.int64, device=device)
-    for (s, e) in local_batches(n, rank, world, batch_size):
-        b = dataset.batch(s, e, device)
+    # a dataset with `iter_batches` (datapipe.StreamingLoader) prefetches one batch ahead on its own streams; a plain one
+    # is asked for each local batch in turn
+    if hasattr(dataset, "iter_batches"):
+        batches = dataset.iter_batches(rank, world, batch_size, device)
+    else:
+        batches = ((s, e, dataset.batch(s, e, device)) for (s, e) in local_batches(n, rank, world, batch_size))
+    for s, e, b in batches:
         logits = forward_fn(b)
         p = logits.argmax(dim=1)
         preds[s - lo:e - lo] = p
@@ -160,6 +165,9 @@ def _main():
     ap.add_argument("--text", default="native", choices=["native", "fp32", "bf16x3"])
     ap.add_argument("--no-dedup", action="store_true")
     ap.add_argument("--no-memo", action="store_true", help="do not remember encoded questions across batches")
+    ap.add_argument("--stream", default="", choices=["", "fp16", "fp32"],
+                    help="evaluate from a PINNED HOST per-video feature store through datapipe.StreamingLoader (device cache, prefetch, "
+                         "tower on a side stream) instead of device-resident batches; the value is the patch dtype of the store")
     args = ap.parse_args()
     world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -181,20 +189,32 @@ def _main():
     model.quest_encoder.compute = args.text
     model.quest_encoder.dedup = not args.no_dedup
     model.quest_encoder.memo = not (args.no_memo or args.no_dedup)
-    ds = SyntheticAVQA(args.n, n_unique_questions=args.unique_questions)
-    t0 = time.perf_counter()
-    cache = {(s, e): ds.batch(s, e, dev) for (s, e) in local_batches(args.n, rank, world, args.batch)}
-    torch.cuda.synchronize()
-    t_gen = time.perf_counter() - t0
-
-    class Resident:
-        n = args.n
-
-        @staticmethod
-        def batch(s, e, device):
-            return cache[(s, e)]
-
     fwd = lambda b: model(b)["out"]
+    if args.stream:
+        from . import datapipe as dp
+        qs = dp.QuestionSet.synthetic_music_avqa(n=args.n, n_unique_questions=args.unique_questions)
+        lo, hi = shard_range(qs.n, rank, world)
+        t0 = time.perf_counter()
+        store = dp.FeatureStore.synthetic(qs.videos_of(lo, hi), dp.RowLayout(patch_dtype=torch.float16 if args.stream == "fp16" else torch.float32),
+                                          device=dev)
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        Resident = dp.StreamingLoader(store, qs, dev, args.batch, rank, world, encoder=model.quest_encoder)
+        cache = local_batches(args.n, rank, world, args.batch)
+    else:
+        ds = SyntheticAVQA(args.n, n_unique_questions=args.unique_questions)
+        t0 = time.perf_counter()
+        cache = {(s, e): ds.batch(s, e, dev) for (s, e) in local_batches(args.n, rank, world, args.batch)}
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+
+        class Resident:
+            n = args.n
+
+            @staticmethod
+            def batch(s, e, device):
+                return cache[(s, e)]
+
     evaluate(fwd, Resident, dev, args.batch, rank, world)          # warm-up pass (weight preparation, workspaces)
     torch.cuda.synchronize()
     if world > 1:
@@ -210,6 +230,8 @@ def _main():
         print(json.dumps({"workload": f"DP eval over {args.n} synthetic questions (configs[3]), per-GPU batch {args.batch}, "
                                       f"question pool {args.unique_questions or 'all distinct'}, text tower {args.text}"
                                       f"{'' if args.no_dedup else ' + dedup'}{' + cross-batch memo' if model.quest_encoder.memo else ''}",
+                          "input": (f"pinned host store ({args.stream} patches), datapipe.StreamingLoader, second pass (every video resident "
+                                    "in the device cache)") if args.stream else "device-resident batches",
                           "n_gpus": world, "questions": args.n, "wall_s": dt, "questions_per_s": args.n / dt,
                           "local_batches_rank0": len(cache), "generate_s_rank0": t_gen, "acc_vs_random_labels": res["acc"],
                           "memo_entries_rank0": len(getattr(model.quest_encoder, "_memo_state", {}).get("slots", {})) if model.quest_encoder.memo else 0,

@@ -122,8 +122,9 @@ class CLIP_TEncoder(nn.Module):
         self.native_precision = "bf16"   # follows QA_TIGER.set_precision
         self.dedup = False   # run the tower on unique token rows only (MUSIC-AVQA test: 33 unique questions)
         self.memo = False    # additionally remember encoded questions ACROSS calls (SURVEY 8f-N1 "memoise by token row"):
-                             # keyed by a 128-bit row hash kept on the host, outputs cached on the device; one small D2H
-                             # (the hashes) per call, the tower only ever runs on questions it has not seen yet
+                             # keyed by the exact token row (host dict), outputs cached on the device; the tower only ever
+                             # runs on questions it has not seen yet
+        self.memo_max_entries = 4096   # device cache cap (236 KB per question: ~1 GB); beyond it questions are not remembered
         self._try_load_local(model_name)
 
     def _try_load_local(self, name: str):
@@ -138,6 +139,14 @@ class CLIP_TEncoder(nn.Module):
             sd = torch.load(path, map_location="cpu")
         own = self.state_dict()
         self.load_state_dict({k: v.float() for k, v in sd.items() if k in own}, strict=False)
+
+    def _apply(self, fn, *args, **kwargs):
+        cabi.invalidate_prepared()          # prepared tower weights / memo follow the parameters (see _cabi.params_version)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        cabi.invalidate_prepared()
+        return super()._load_from_state_dict(*args, **kwargs)
 
     def freeze(self):
         for p in self.parameters():
@@ -203,15 +212,17 @@ class CLIP_TEncoder(nn.Module):
         eot = text.long().argmax(dim=-1)
         return x[torch.arange(x.shape[0], device=x.device), eot] @ self.text_projection, x
 
-    def forward(self, text: torch.Tensor):
+    def forward(self, text: torch.Tensor, text_host: torch.Tensor = None):
+        """`text_host` (optional, not in the reference signature): the same token ids on the host, when the caller still has
+        them -- the memo then keys on them without a device->host copy, and the ids are validated for free."""
         if text.is_cuda and self.compute in ("fp32", "tf32", "bf16x3"):
             prev = torch.backends.cuda.matmul.allow_tf32
             torch.backends.cuda.matmul.allow_tf32 = self.compute == "tf32"
             try:
-                return self._forward(text)
+                return self._forward(text, text_host)
             finally:
                 torch.backends.cuda.matmul.allow_tf32 = prev
-        return self._forward(text)
+        return self._forward(text, text_host)
 
     def _unique_rows(self, text: torch.Tensor):
         """(unique rows, inverse) of the token matrix.  On CUDA torch.unique(dim=0) costs ~13 ms at B=256 (measured,
@@ -235,18 +246,12 @@ class CLIP_TEncoder(nn.Module):
             return torch.unique(text, dim=0, return_inverse=True)
         return uniq, inv
 
-    def _row_hashes(self, text: torch.Tensor) -> torch.Tensor:
-        """[B, 2] int64: two independent multiplicative hashes of every token row (wrap mod 2^64)."""
-        L = text.shape[1]
-        key = ("memo", text.device, L)
-        mult = self.__dict__.setdefault("_hash_mult", {}).get(key)
-        if mult is None:
-            g = torch.Generator().manual_seed(0xC11F)
-            mult = (torch.randint(-(1 << 62), 1 << 62, (L, 2), generator=g, dtype=torch.int64) * 2 + 1).to(text.device)
-            self.__dict__["_hash_mult"][key] = mult
-        return (text.to(torch.int64).unsqueeze(-1) * mult).sum(dim=1)
-
-    def _forward_memo(self, text: torch.Tensor):
+    def _forward_memo(self, text: torch.Tensor, text_host: torch.Tensor = None):
+        """Cross-call memo keyed on the EXACT token row (its bytes), not on a hash: a hit can never return another question's
+        encoding.  `text_host` = the same token matrix on the host when the caller still has it (datapipe.py does): then the
+        call has no device->host sync at all; otherwise the tokens themselves (B x L int32, 79 KB at B = 256) are copied
+        back once.  The device cache holds at most `memo_max_entries` questions (236 KB each at L = 77, W = 768); questions
+        beyond the cap are encoded (deduplicated within the call) but not remembered."""
         B, L = text.shape
         W, E = self.transformer.width, self.text_projection.shape[1]
         ver = (self.compute, self.native_precision, str(text.device), L, cabi.params_version(self))
@@ -254,30 +259,52 @@ class CLIP_TEncoder(nn.Module):
         if st is None or st["ver"] != ver:
             st = dict(ver=ver, slots={}, q=torch.empty(64, E, device=text.device), w=torch.empty(64, L, W, device=text.device))
             self.__dict__["_memo_state"] = st
-        keys = [tuple(r) for r in self._row_hashes(text).cpu().tolist()]          # the one host sync of this call
-        slots, new_rows = st["slots"], []
+        rows = (text_host if text_host is not None else text.cpu()).to(torch.int32).contiguous().numpy()
+        if rows.shape != (B, L):
+            raise RuntimeError(f"CLIP_TEncoder: text_host shape {rows.shape} does not match text {(B, L)}")
+        if rows.size and (rows.min() < 0 or rows.max() >= self.vocab_size):       # nn.Embedding raises on a bad id; so do we
+            raise RuntimeError(f"CLIP_TEncoder: token id outside [0, {self.vocab_size}) (min {rows.min()}, max {rows.max()})")
+        keys = [rows[i].tobytes() for i in range(B)]
+        slots = st["slots"]
+        fresh = {}                                                                # unseen key -> first row that carries it
         for i, k in enumerate(keys):
-            if k not in slots:
-                slots[k] = len(slots)
-                new_rows.append(i)
-        if new_rows:
-            need = len(slots)
-            if need > st["q"].shape[0]:                                           # grow the device cache (doubling)
-                cap = max(need, 2 * st["q"].shape[0])
+            if k not in slots and k not in fresh:
+                fresh[k] = i
+        q_new = w_new = None
+        over = {}                                                                 # keys encoded now but not remembered (cap)
+        if fresh:
+            first = list(fresh.values())
+            q_new, w_new = self._tower(text[torch.tensor(first, device=text.device)])
+            n_old = len(slots)
+            n_store = max(0, min(len(first), int(self.memo_max_entries) - n_old))
+            if n_old + n_store > st["q"].shape[0]:                                # grow the device cache (doubling, capped)
+                cap = min(max(n_old + n_store, 2 * st["q"].shape[0]), max(int(self.memo_max_entries), n_old + n_store))
                 q2, w2 = torch.empty(cap, E, device=text.device), torch.empty(cap, L, W, device=text.device)
-                n_old = need - len(new_rows)
                 q2[:n_old], w2[:n_old] = st["q"][:n_old], st["w"][:n_old]
                 st["q"], st["w"] = q2, w2
-            rows = torch.tensor(new_rows, device=text.device)
-            q, w = self._tower(text[rows])
-            dst = torch.tensor([slots[keys[i]] for i in new_rows], device=text.device)
-            st["q"][dst], st["w"][dst] = q, w
-        idx = torch.tensor([slots[k] for k in keys], device=text.device)
-        return st["q"][idx], st["w"][idx]
+            for j, k in enumerate(fresh):
+                if j < n_store:
+                    slots[k] = n_old + j
+                else:
+                    over[k] = j
+            if n_store:
+                st["q"][n_old:n_old + n_store], st["w"][n_old:n_old + n_store] = q_new[:n_store], w_new[:n_store]
+        if not over:
+            idx = torch.tensor([slots[k] for k in keys], device=text.device)
+            return st["q"][idx], st["w"][idx]
+        idx = torch.tensor([slots.get(k, 0) for k in keys], device=text.device)
+        q, w = st["q"][idx], st["w"][idx]
+        rows_o = [i for i, k in enumerate(keys) if k in over]
+        src_o = torch.tensor([over[keys[i]] for i in rows_o], device=text.device)
+        dst_o = torch.tensor(rows_o, device=text.device)
+        q[dst_o], w[dst_o] = q_new[src_o], w_new[src_o]
+        return q, w
 
-    def _forward(self, text):
+    def _forward(self, text, text_host=None):
         if self.memo and text.is_cuda:
-            return self._forward_memo(text)
+            return self._forward_memo(text, text_host)
+        if text_host is not None and text_host.numel() and (int(text_host.min()) < 0 or int(text_host.max()) >= self.vocab_size):
+            raise RuntimeError(f"CLIP_TEncoder: token id outside [0, {self.vocab_size})")
         if self.dedup:
             uniq, inv = self._unique_rows(text)
             q, w = self._tower(uniq)

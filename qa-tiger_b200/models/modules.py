@@ -47,6 +47,17 @@ class _QatModule(nn.Module):
             raise RuntimeError(f"{type(self).__name__}: the B200 path is inference-only; call .eval() "
                                "(the reference applies dropout in train mode, this path has none)")
 
+    # derived weights are dropped whenever the parameters may have changed behind the (data_ptr, _version) key:
+    # .to() / .cuda() / .float() (-> _apply) and load_state_dict (-> _load_from_state_dict); `.data` writes need an
+    # explicit qa_tiger_b200.invalidate_prepared() (see _cabi.params_version)
+    def _apply(self, fn, *args, **kwargs):
+        cabi.invalidate_prepared()
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        cabi.invalidate_prepared()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def _prepared(self, prec: int):
         key = (prec, cabi.params_version(self))
         cache = self.__dict__.get("_qat_cache")
@@ -192,7 +203,7 @@ class QstGrounding(_QatModule):
         a.norm = w["norm"].c
         if head is None:
             return None
-        key = (head.weight.data_ptr(), head.weight._version, head.bias.data_ptr(), head.bias._version)
+        key = (cabi._prepared_epoch, head.weight.data_ptr(), head.weight._version, head.bias.data_ptr(), head.bias._version)
         cached = self.__dict__.get("_head_cache")
         if cached is None or cached[0] != key:
             cached = (key, cabi.Lin(head.weight, head.bias, cabi.PREC_FP32))

@@ -50,6 +50,14 @@ class QA_TIGER(nn.Module):
             if m.bias is not None:
                 nn.init.constant_(m.bias, 0)
 
+    def _apply(self, fn, *args, **kwargs):
+        cabi.invalidate_prepared()          # q_cat / head caches follow the parameters (see _cabi.params_version)
+        return super()._apply(fn, *args, **kwargs)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        cabi.invalidate_prepared()
+        return super()._load_from_state_dict(*args, **kwargs)
+
     def set_precision(self, name: str):
         """'fp32' | 'bf16' for every block of the hot path and for the native text tower (`quest_encoder.compute`
         selects torch / native for the tower itself)."""
@@ -70,6 +78,9 @@ class QA_TIGER(nn.Module):
             # the reference sets words=None here and then crashes at net.py:122; be explicit instead
             raise RuntimeError("QA_TIGER: `quest` must be CLIP token ids (int [B,77]); pre-computed float question "
                                "features go through forward_features(quest768, words768, ...)")
+        elif prefix == "" and reshaped_data.get("quest_feat") is not None:
+            # the input pipeline already ran the text tower for this batch on its own stream (datapipe.StreamingLoader)
+            quest, words = reshaped_data["quest_feat"]
         else:
             quest, words = self.quest_encoder(quest)
             quest = quest.squeeze(1)
@@ -84,7 +95,8 @@ class QA_TIGER(nn.Module):
         """[3D, D] = the query in-projections of at_aggregator, vt_aggregator and quest_grounding stacked (always fp32 FFMA:
         they are on the router path), cached on the parameter versions."""
         mods = (self.at_aggregator.qst_attn, self.vt_aggregator.qst_attn, self.quest_grounding.attn)
-        key = tuple((m.in_proj_weight.data_ptr(), m.in_proj_weight._version, m.in_proj_bias.data_ptr(), m.in_proj_bias._version) for m in mods)
+        key = (cabi._prepared_epoch,) + tuple((m.in_proj_weight.data_ptr(), m.in_proj_weight._version, m.in_proj_bias.data_ptr(),
+                                                m.in_proj_bias._version) for m in mods)
         cached = self.__dict__.get("_q_cat_cache")
         if cached is None or cached[0] != key:
             D = self.head.in_features

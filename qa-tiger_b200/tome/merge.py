@@ -169,3 +169,31 @@ def chain(x: torch.Tensor, schedule: Optional[List[int]] = None, class_token: bo
             steps.append((unm, src, dst))
             t -= rr
     return out, size[..., None], group, steps
+
+
+def frame_shard(n_frames: int, rank: int, world: int):
+    """contiguous shard [lo, hi) of the frame list owned by `rank` (ToMe shards by frame, no exchange)"""
+    per = -(-n_frames // max(world, 1))
+    lo = min(n_frames, rank * per)
+    return lo, min(n_frames, lo + per)
+
+
+def chain_frames(frames, n_frames: int, rank: int = 0, world: int = 1, chunk: int = 592, schedule: Optional[List[int]] = None,
+                 class_token: bool = True, want_group: bool = False):
+    """The extractor's loop (scripts/extract_ToMe/extract_tome14.py:153-170: one frame at a time through the 23-step schedule)
+    over this rank's shard of `n_frames` frames, `chunk` frames per `chain()` call (a multiple of the SM count keeps the
+    one-frame-per-CTA match kernel in whole waves).  `frames`: a [n_frames, t0, C] CUDA tensor, or a callable
+    (lo, hi) -> [hi-lo, t0, C] producing the frames of a chunk (x0 of configs[2] is 36 GB: callers may stream it).
+    Returns (x_out [n_local, t_end, C], size [n_local, t_end, 1], group [n_local, t0] | None) in frame order."""
+    lo, hi = frame_shard(n_frames, rank, world)
+    outs, sizes, groups = [], [], []
+    for c0 in range(lo, hi, chunk):
+        c1 = min(hi, c0 + chunk)
+        x = frames(c0, c1) if callable(frames) else frames[c0:c1]
+        o, sz, g, _ = chain(x, schedule, class_token, trace=False, want_group=want_group)
+        outs.append(o)
+        sizes.append(sz)
+        groups.append(g)
+    if not outs:
+        return None, None, None
+    return torch.cat(outs), torch.cat(sizes), (torch.cat(groups) if want_group else None)

@@ -1,5 +1,6 @@
 """Profiling aid (not a test): per-tile cost model of the tcgen05 GEMM -- sweep K at fixed M, N and fit
-cycles/tile = a + b*K; QAT_GEMM_DBG switches isolate epilogue / MMA / store costs."""
+cycles/tile = a + b*K; QAT_GEMM_DBG switches isolate epilogue / MMA / store costs
+(they exist only in a profile build of the library: NVCC_EXTRA="-DQAT_PROFILE_BUILD" python qa-tiger_b200/build.py --force)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch

@@ -38,7 +38,7 @@ def test_struct_layout_matches_c(tmp_path):
              "QatGroundArgs": _cabi.GroundArgs, "QatTomeMatchArgs": _cabi.TomeMatchArgs,
              "QatTomeMergeArgs": _cabi.TomeMergeArgs, "QatTomeChainArgs": _cabi.TomeChainArgs,
              "QatClipLayerW": _cabi.ClipLayerW, "QatClipTextArgs": _cabi.ClipTextArgs, "QatAttnArgs": _cabi.AttnArgs,
-             "QatForwardArgs": _cabi.ForwardArgs}
+             "QatForwardArgs": _cabi.ForwardArgs, "QatGatherArgs": _cabi.GatherArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "qat.h"', 'int main(void){']
     for cname, ct in pairs.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -54,6 +54,24 @@ def test_struct_layout_matches_c(tmp_path):
         assert int(out[cname]) == C.sizeof(ct), cname
         for f, _ in ct._fields_:
             assert int(out[f"{cname}.{f}"]) == getattr(ct, f).offset, f"{cname}.{f}"
+
+
+def test_options_are_set_through_the_abi_not_the_environment(monkeypatch):
+    """A/B switches: explicit setter, snapshot per call; a leaked environment variable after load changes nothing, and the
+    product library has no GEMM debug mode (QAT_GEMM_DBG is compiled out: no symbol, no getenv on the hot path)."""
+    from qa_tiger_b200 import _cabi
+    lib = _cabi.lib()
+    assert _cabi.get_option("gemm_cg") == 0
+    monkeypatch.setenv("QAT_GEMM_CG", "1")
+    assert _cabi.get_option("gemm_cg") == 0
+    with _cabi.option("gemm_cg", 2):
+        assert _cabi.get_option("gemm_cg") == 2
+    assert _cabi.get_option("gemm_cg") == 0
+    with pytest.raises(RuntimeError, match="unknown option"):
+        _cabi.set_option("gemm_dbg", 1)
+    blob = open(_cabi.LIB_PATH, "rb").read()
+    assert b"QAT_GEMM_DBG" not in blob
+    assert lib.qat_abi_version() == 2
 
 
 def test_workspace_sizing_runs_without_gpu():

@@ -146,3 +146,75 @@ def test_state_dict_is_reference_compatible():
     assert keys == set(sd.keys()) and len(keys) == 286
     for k, v in model.state_dict().items():
         assert tuple(v.shape) == tuple(sd[k].shape), k
+
+
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_stress_config_at_its_own_batch(prec):
+    """BASELINE configs[4] at its per-GPU batch: B = 128, T = 120, E = K = 14 against the reference golden (logits + ranks)."""
+    g = golden("fwd_stress_b128")
+    B, T, E, K, wseed, bseed = FWD_CASES["fwd_stress_b128"]
+    sd = synth.make_state_dict(wseed, num_experts=E)
+    model = build_model(sd, E, K, prec)
+    for agg in (model.at_aggregator, model.vt_aggregator):
+        agg.keep_aux = True
+    batch = synth.make_batch(bseed, B, T)
+    data = {k: v.to(dev()) for k, v in batch.items()}
+    with torch.no_grad():
+        out = model(data)["out"]
+    for agg, nm in ((model.at_aggregator, "at_aggregator"), (model.vt_aggregator, "vt_aggregator")):
+        assert agg.last_aux[0].cpu().tolist() == g[nm + ".topk_inds"].astype(np.int64).tolist()
+    assert relerr(out, g["out"]) < TOL[prec]
+    assert out.argmax(1).cpu().tolist() == g["argmax"].tolist()
+
+
+def test_two_threads_two_streams_are_reentrant():
+    """nn.DataParallel (trainutils.py:107-108) drives one Python thread per replica through the same library: two threads,
+    each with its own stream, model replica and batch, run concurrently and must reproduce their single-threaded logits."""
+    import threading
+    sd = synth.make_state_dict(713, num_experts=7)
+    models = [build_model(sd, 7, 7, "bf16") for _ in range(2)]
+    batches = [{k: v.to(dev()) for k, v in synth.make_batch(40 + i, 5 + i, 60).items()} for i in range(2)]
+    with torch.no_grad():
+        want = [m(b)["out"].clone() for m, b in zip(models, batches)]
+    torch.cuda.synchronize()
+    got, errs = [None, None], []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s), torch.no_grad():
+                for _ in range(6):
+                    o = models[i](batches[i])["out"]
+                s.synchronize()
+            got[i] = o
+        except Exception as e:   # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i in range(2):
+        assert torch.equal(got[i], want[i])
+
+
+def test_data_writes_need_invalidate_prepared():
+    """ADVICE: derived weights are cached on (data_ptr, _version); load_state_dict / .to() invalidate them automatically,
+    writes through `.data` need qa_tiger_b200._cabi.invalidate_prepared()."""
+    from qa_tiger_b200 import _cabi
+    sd = synth.make_state_dict(713, num_experts=7)
+    model = build_model(sd, 7, 7, "bf16")
+    data = {k: v.to(dev()) for k, v in synth.make_batch(8, 4, 60).items()}
+    with torch.no_grad():
+        a = model(data)["out"].clone()
+        sd2 = {k: (v * 1.01 if k.startswith("crs_attn.linear1") else v) for k, v in sd.items()}
+        model.load_state_dict(sd2)                       # same storage, no _version bump on the module side needed
+        b = model(data)["out"].clone()
+        assert relerr(b, a) > 1e-5
+        model.crs_attn.linear1.weight.data.copy_(sd["crs_attn.linear1.weight"])
+        model.crs_attn.linear1.bias.data.copy_(sd["crs_attn.linear1.bias"])
+        _cabi.invalidate_prepared()
+        c = model(data)["out"]
+    assert torch.equal(c, a)

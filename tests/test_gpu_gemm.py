@@ -33,10 +33,24 @@ def test_gemm_kinds(kind, tol, M, N, K):
     assert torch.equal(hi, got2.to(torch.bfloat16))
 
 
-@pytest.mark.parametrize("bn", ["128", "256"])
-def test_gemm_tile_widths(bn, monkeypatch):
+@pytest.fixture
+def opt():
+    """set A/B options of the library for one test, restore them afterwards"""
     from qa_tiger_b200 import _cabi
-    monkeypatch.setenv("QAT_GEMM_BN", bn)
+    prev = {}
+
+    def _set(name, value):
+        prev.setdefault(name, _cabi.get_option(name))
+        _cabi.set_option(name, value)
+    yield _set
+    for k, v in prev.items():
+        _cabi.set_option(k, v)
+
+
+@pytest.mark.parametrize("bn", [128, 256])
+def test_gemm_tile_widths(bn, opt):
+    from qa_tiger_b200 import _cabi
+    opt("gemm_bn", bn)
     g = torch.Generator(device="cuda").manual_seed(1)
     a = torch.randn(777, 512, device=dev(), generator=g)
     w = torch.randn(1024, 512, device=dev(), generator=g) * 512 ** -0.5
@@ -88,13 +102,13 @@ def test_gemm_tf32_to_f16_plane(M, N, K):
     assert torch.equal(got, full.half())
 
 
-@pytest.mark.parametrize("cg", ["1", "2"])
+@pytest.mark.parametrize("cg", [1, 2])
 @pytest.mark.parametrize("M", [129, 777, 1024, 40 * 128 + 5])
-def test_gemm_cta_pairs(cg, M, monkeypatch):
+def test_gemm_cta_pairs(cg, M, opt):
     """cta_group::2 (256-row pair tiles, W rows split across the pair) against single-CTA tiles: every kind, odd and even
     numbers of 128-row tiles (a tail pair is half empty), bias / ReLU / residual epilogues, plane outputs."""
     from qa_tiger_b200 import _cabi
-    monkeypatch.setenv("QAT_GEMM_CG", cg)
+    opt("gemm_cg", cg)
     N, K = 768, 320
     g = torch.Generator(device="cuda").manual_seed(M)
     a = torch.randn(M, K, device=dev(), generator=g)
