@@ -342,14 +342,17 @@ class StreamingLoader:
                 runs.append([slot, row, 1])
         cs = self.copy_stream
         with torch.cuda.stream(cs):
-            if evicted and self._gather_done is not None:
-                cs.wait_event(self._gather_done)          # an overwritten slot may still be read by the last issued gather
-            for slot, row, cnt in runs:
-                self.cache.rows[slot:slot + cnt].copy_(self.store.rows[row:row + cnt], non_blocking=True)
+            # the small per-question vectors first (their own event: the text tower only needs the tokens), then the videos
             self._slots_dev[k][:n].copy_(sh[:n], non_blocking=True)
             self._tok_dev[k][:n].copy_(q.tokens[s:e], non_blocking=True)
             self._lab_dev[k][:n].copy_(q.label[s:e], non_blocking=True)
             self._qt_dev[k][:n].copy_(q.qtype[s:e], non_blocking=True)
+            vec_copied = torch.cuda.Event()
+            vec_copied.record(cs)
+            if evicted and self._gather_done is not None:
+                cs.wait_event(self._gather_done)          # an overwritten slot may still be read by the last issued gather
+            for slot, row, cnt in runs:
+                self.cache.rows[slot:slot + cnt].copy_(self.store.rows[row:row + cnt], non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(cs)
         self._copied[k] = copied
@@ -359,7 +362,7 @@ class StreamingLoader:
         if self.encoder is not None:
             ts = self.tower_stream
             with torch.cuda.stream(ts):
-                ts.wait_event(copied)
+                ts.wait_event(vec_copied)
                 feat = self.encoder(self._tok_dev[k][:n], text_host=q.tokens[s:e])
                 towered = torch.cuda.Event()
                 towered.record(ts)

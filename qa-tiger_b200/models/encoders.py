@@ -246,6 +246,14 @@ class CLIP_TEncoder(nn.Module):
             return torch.unique(text, dim=0, return_inverse=True)
         return uniq, inv
 
+    @staticmethod
+    def _index(values, device) -> torch.Tensor:
+        """an index vector on `device` WITHOUT a synchronous pageable copy: `torch.tensor(list, device='cuda')` makes the host
+        wait for everything queued on the current stream (the streaming loader's tower stream waits on a host->device copy
+        there, and the host stalling on it serialises the copy with the previous batch's compute)"""
+        t = torch.tensor(values, dtype=torch.int64)
+        return t.pin_memory().to(device, non_blocking=True) if device.type == "cuda" else t
+
     def _forward_memo(self, text: torch.Tensor, text_host: torch.Tensor = None):
         """Cross-call memo keyed on the EXACT token row (its bytes), not on a hash: a hit can never return another question's
         encoding.  `text_host` = the same token matrix on the host when the caller still has it (datapipe.py does): then the
@@ -274,7 +282,7 @@ class CLIP_TEncoder(nn.Module):
         over = {}                                                                 # keys encoded now but not remembered (cap)
         if fresh:
             first = list(fresh.values())
-            q_new, w_new = self._tower(text[torch.tensor(first, device=text.device)])
+            q_new, w_new = self._tower(text[self._index(first, text.device)])
             n_old = len(slots)
             n_store = max(0, min(len(first), int(self.memo_max_entries) - n_old))
             if n_old + n_store > st["q"].shape[0]:                                # grow the device cache (doubling, capped)
@@ -290,13 +298,13 @@ class CLIP_TEncoder(nn.Module):
             if n_store:
                 st["q"][n_old:n_old + n_store], st["w"][n_old:n_old + n_store] = q_new[:n_store], w_new[:n_store]
         if not over:
-            idx = torch.tensor([slots[k] for k in keys], device=text.device)
+            idx = self._index([slots[k] for k in keys], text.device)
             return st["q"][idx], st["w"][idx]
-        idx = torch.tensor([slots.get(k, 0) for k in keys], device=text.device)
+        idx = self._index([slots.get(k, 0) for k in keys], text.device)
         q, w = st["q"][idx], st["w"][idx]
         rows_o = [i for i, k in enumerate(keys) if k in over]
-        src_o = torch.tensor([over[keys[i]] for i in rows_o], device=text.device)
-        dst_o = torch.tensor(rows_o, device=text.device)
+        src_o = self._index([over[keys[i]] for i in rows_o], text.device)
+        dst_o = self._index(rows_o, text.device)
         q[dst_o], w[dst_o] = q_new[src_o], w_new[src_o]
         return q, w
 
