@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QAT_ABI_VERSION 2
+#define QAT_ABI_VERSION 3
 
 enum {
   QAT_OK = 0,
@@ -108,6 +108,13 @@ typedef struct {
   void* c_lo;
   void* c_f16;         /* fp16 plane; when it is the only output the tile leaves through a TMA store */
   int32_t ldc;
+  /* reduce epilogue (QAT_GEMM_BF16X3 only; M4 of SURVEY 8a folded into the expert first-layer GEMM, modules.py:473-534): rows of
+   * A are (sample, t) pairs, coef_T rows per sample; instead of act(A W^T + b) the call writes, per sample s and column n,
+   *   c[s, n] = sum_t coef[(s*coef_T + t) % coef_mod, n / coef_Ch] * act(...)[s*coef_T + t, n]       (c is [M / coef_T, ldc])
+   * 32 <= coef_T <= 128, M % coef_T == 0, coef_Ch % 32 == 0, w.n % 256 == 0; coef = NULL: the plain epilogue above */
+  const float* coef;   /* [coef_mod, coef_E] */
+  int32_t coef_E, coef_T, coef_Ch;
+  int64_t coef_mod;
 } QatGemmArgs;
 int qat_gemm(const QatGemmArgs* a);
 

@@ -13,6 +13,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libqat_b200.so")
 
+ABI_VERSION = 3
 PREC_FP32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
 OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT, OP_FORWARD = range(10)
@@ -40,7 +41,8 @@ class GemmArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("M", C.c_int32), ("stream", C.c_void_p), ("a", C.c_void_p), ("a_hi", C.c_void_p),
                 ("a_lo", C.c_void_p), ("a_f16", C.c_void_p), ("lda", C.c_int32), ("w", LinearW), ("relu", C.c_int32),
                 ("res", C.c_void_p), ("res_f16", C.c_void_p), ("ldr", C.c_int32), ("c", C.c_void_p), ("c_hi", C.c_void_p),
-                ("c_lo", C.c_void_p), ("c_f16", C.c_void_p), ("ldc", C.c_int32)]
+                ("c_lo", C.c_void_p), ("c_f16", C.c_void_p), ("ldc", C.c_int32),
+                ("coef", C.c_void_p), ("coef_E", C.c_int32), ("coef_T", C.c_int32), ("coef_Ch", C.c_int32), ("coef_mod", C.c_int64)]
 
 
 class AvqArgs(C.Structure):
@@ -196,7 +198,7 @@ def lib():
                 for name, (res, args) in EXPORTS.items():
                     fn = getattr(l, name)
                     fn.restype, fn.argtypes = res, args
-                if l.qat_abi_version() != 2:
+                if l.qat_abi_version() != ABI_VERSION:
                     raise RuntimeError("libqat_b200.so ABI version mismatch")
                 _lib = l
     return _lib
@@ -339,6 +341,25 @@ def gemm(kind: int, a: torch.Tensor, lin: "Lin", relu: bool = False, res: Option
     with torch.cuda.device(dev):
         check(lib().qat_gemm(C.byref(g)), "qat_gemm")
     return (c, planes) if out_planes else c
+
+
+def gemm_reduce(a: torch.Tensor, lin: "Lin", coef: torch.Tensor, T: int, Ch: int, relu: bool = True, a_planes=None) -> torch.Tensor:
+    """The expert first-layer GEMM with M4 in its epilogue (bf16x3 kind): a [S*T, K] rows = (sample, t), coef [R, E] with row
+    (s*T + t) % R -> out [S, N] = sum_t coef[., n // Ch] * act(a W^T + b)   (parity tests / roofline timing)."""
+    M, K = a.shape
+    N = lin.w.shape[0]
+    dev = a.device
+    g = GemmArgs()
+    g.kind, g.M, g.stream, g.lda, g.w, g.relu, g.ldc = GEMM_BF16X3, M, stream_ptr(dev), a.stride(0), lin.c, int(relu), N
+    hi, lo = a_planes if a_planes is not None else split_planes(a)
+    g.a_hi, g.a_lo = hi.data_ptr(), lo.data_ptr()
+    coef = coef.contiguous().float()
+    g.coef, g.coef_E, g.coef_T, g.coef_Ch, g.coef_mod = coef.data_ptr(), coef.shape[1], T, Ch, coef.shape[0]
+    c = torch.empty(M // T, N, device=dev, dtype=torch.float32)
+    g.c = c.data_ptr()
+    with torch.cuda.device(dev):
+        check(lib().qat_gemm(C.byref(g)), "qat_gemm")
+    return c
 
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False, need_weights: bool = False):

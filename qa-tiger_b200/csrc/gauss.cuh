@@ -69,12 +69,111 @@ __device__ __forceinline__ void fma_vec<uint4, 8>(float (&acc)[8], const uint4& 
   }
 }
 
+// shared-memory arrays of the router / Gaussian prologue
+struct GaussSm {
+  float* coef;          // [T][E]
+  float* G;             // [K][T]
+  float* p;             // [K] gate of rank i (renormalised)
+  float* c;             // [K] centre
+  float* w;             // [K] width
+  int* idx;             // [K] expert of rank i (own sample)
+  unsigned char* perm;  // [T][K] expert of rank i of sample (b*T+t) % B
+};
+
+// M2 + M3 for sample b, shared by the streaming kernel below and by moe_coef_kernel (the GEMM-epilogue form of M4):
+//   phase 0  rank lists.  One thread per (row t, expert e) -- and per (own sample, e): the rank of e is the number of experts
+//            that beat it (higher softmax probability, lower index on ties = torch.topk's order), so no thread walks a
+//            top-K selection loop over a locally indexed array (that serial form cost ~10 us per launch)
+//   phase 1  Gaussian masks, one warp per selected expert, peak-normalised over t
+//   phase 2  coef[t][j] = sum_{i: perm_t[i] = j} p[i] G[i][t]
+// Ends with a __syncthreads(): every array of `s` is complete.
+template <int NT>
+__device__ __forceinline__ void gauss_prologue(const GaussP& p, int b, const GaussSm& s) {
+  const int T = p.T, E = p.E, K = p.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rl_ld = p.rl_ld ? p.rl_ld : E;
+  for (int item = tid; item < (T + 1) * E; item += NT) {
+    const int t = item / E, e = item - t * E;
+    const bool own = (t == T);
+    const int o = own ? b : (int)(((long long)b * T + t) % p.B);
+    const float* l = p.rl + (long long)o * rl_ld;
+    float mx = -INFINITY;
+    for (int j = 0; j < E; ++j) mx = fmaxf(mx, __ldg(l + j));
+    float sum = 0.f;
+    for (int j = 0; j < E; ++j) sum += expf(__ldg(l + j) - mx);
+    const float pe = expf(__ldg(l + e) - mx) / sum;
+    int rank = 0;
+    for (int j = 0; j < E; ++j) {
+      const float pj = expf(__ldg(l + j) - mx) / sum;
+      rank += (pj > pe || (pj == pe && j < e)) ? 1 : 0;
+    }
+    if (rank < K) {
+      if (own) {
+        s.idx[rank] = e;
+        s.p[rank] = pe;
+      } else {
+        s.perm[t * K + rank] = (unsigned char)e;
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // renormalise the K gates (sum in rank order, as modules.py:570) and derive centre / width of the selected experts
+    float psum = 0.f;
+    for (int i = 0; i < K; ++i) psum += s.p[i];
+    __syncwarp();
+    if (lane < K) {
+      const int e = s.idx[lane];
+      s.p[lane] = s.p[lane] / psum;
+      const float margin = 1.0f / (float)(E * 2);
+      const long long gro = (long long)b * (p.gr_ld ? p.gr_ld : 2 * E);
+      const float g0 = __ldg(p.gr + gro + 2 * e);
+      const float g1 = __ldg(p.gr + gro + 2 * e + 1);
+      const float centre = linspace_at(margin, 1.f - margin, E, e) + tanhf(g0) * margin;
+      const float width = 1.f / (1.f + expf(-g1));
+      s.c[lane] = fminf(fmaxf(centre, 0.f), 1.f);
+      s.w[lane] = fmaxf(width, 0.09f) / p.sigma;
+    }
+  }
+  __syncthreads();
+  for (int i = warp; i < K; i += NT / 32) {
+    const float c = s.c[i], w = s.w[i];
+    const float pref = 0.3989422804014327f / w;
+    const float den = 2.f * (w * w);
+    float mx = -INFINITY;
+    for (int t = lane; t < T; t += 32) {
+      float d = linspace_at(0.f, 1.f, T, t) - c;
+      float g = pref * expf(-(d * d) / den);
+      s.G[i * T + t] = g;
+      mx = fmaxf(mx, g);
+    }
+    mx = warp_max(mx);
+    for (int t = lane; t < T; t += 32) s.G[i * T + t] = s.G[i * T + t] / mx;
+  }
+  __syncthreads();
+  for (int t = tid; t < T; t += NT) {
+    for (int e = 0; e < E; ++e) s.coef[t * E + e] = 0.f;
+    for (int i = 0; i < K; ++i) s.coef[t * E + s.perm[t * K + i]] += s.p[i] * s.G[i * T + t];
+  }
+  __syncthreads();
+}
+
+// optional rank / gate / mask outputs of sample b (after gauss_prologue)
+template <int NT>
+__device__ __forceinline__ void gauss_write_aux(const GaussP& p, int b, const GaussSm& s) {
+  const int tid = threadIdx.x, K = p.K, T = p.T;
+  if (p.topk_inds && tid < K) p.topk_inds[(long long)b * K + tid] = s.idx[tid];
+  if (p.topk_probs && tid < K) p.topk_probs[(long long)b * K + tid] = s.p[tid];
+  if (p.gauss_weight)
+    for (int f = tid; f < K * T; f += NT) p.gauss_weight[(long long)b * K * T + f] = s.G[f];
+}
+
 // VecT = float4 (fp32 X) or uint4 (bf16 X); SLOTS = vectors per thread per time step.
 template <typename VecT, int VEC, int SLOTS, int NT, bool CLUSTER>
 __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.T, E = p.E, K = p.K, C = p.C;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x;
   const int b = blockIdx.x;
   const int rank = CLUSTER ? blockIdx.y : 0;
   const int nrank = CLUSTER ? gridDim.y : 1;
@@ -87,13 +186,15 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
   VecT* s_ring = reinterpret_cast<VecT*>(smem_raw);                                   // [ring][nvec]
   uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ring * row_bytes); // [ring]
   float* s_part = reinterpret_cast<float*>(s_full + ring);       // [nvec*VEC] partial sums (DSMEM-visible)
-  float* s_coef = s_part + (size_t)nvec * VEC;                    // [T][E]
-  float* s_G = s_coef + T * E;                                    // [K][T]
-  float* s_p = s_G + K * T;                                       // [K]
-  float* s_c = s_p + K;                                           // [K]
-  float* s_w = s_c + K;                                           // [K]
-  int* s_idx = reinterpret_cast<int*>(s_w + K);                   // [K]
-  unsigned char* s_perm = reinterpret_cast<unsigned char*>(s_idx + K);  // [T][K]
+  GaussSm sm;
+  sm.coef = s_part + (size_t)nvec * VEC;                          // [T][E]
+  sm.G = sm.coef + T * E;                                         // [K][T]
+  sm.p = sm.G + K * T;                                            // [K]
+  sm.c = sm.p + K;                                                // [K]
+  sm.w = sm.c + K;                                                // [K]
+  sm.idx = reinterpret_cast<int*>(sm.w + K);                      // [K]
+  sm.perm = reinterpret_cast<unsigned char*>(sm.idx + K);         // [T][K]
+  float* s_coef = sm.coef;
 
   // ---- start streaming before anything else: arm the ring and issue the first `ring` row copies ----
   const int t0 = (int)((long long)T * rank / nrank), t1 = (int)((long long)T * (rank + 1) / nrank);
@@ -109,83 +210,9 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
     }
   }
 
-  // ---- phase 0: rank lists.  Thread t ranks sample (b*T+t)%B; the last thread ranks sample b. ----
-  for (int t = tid; t < T + 1; t += NT) {
-    const bool own = (t == T);
-    const int o = own ? b : (int)(((long long)b * T + t) % p.B);
-    float pr[GAUSS_MAX_E];
-    float mx = -INFINITY;
-    for (int e = 0; e < E; ++e) {
-      pr[e] = __ldg(p.rl + (long long)o * (p.rl_ld ? p.rl_ld : E) + e);
-      mx = fmaxf(mx, pr[e]);
-    }
-    float sum = 0.f;
-    for (int e = 0; e < E; ++e) {
-      pr[e] = expf(pr[e] - mx);
-      sum += pr[e];
-    }
-    for (int e = 0; e < E; ++e) pr[e] = pr[e] / sum;
-    float psum = 0.f;
-    for (int i = 0; i < K; ++i) {
-      int best = 0;
-      float bv = -1.f;
-      for (int e = 0; e < E; ++e)
-        if (pr[e] > bv) { bv = pr[e]; best = e; }   // strict > keeps the lowest index on ties
-      pr[best] = -2.f;
-      if (own) {
-        s_idx[i] = best;
-        s_p[i] = bv;
-        psum += bv;
-      } else {
-        s_perm[t * K + i] = (unsigned char)best;
-      }
-    }
-    if (own) {
-      const float margin = 1.0f / (float)(E * 2);
-      for (int i = 0; i < K; ++i) {
-        const int e = s_idx[i];
-        s_p[i] = s_p[i] / psum;
-        const long long gro = (long long)b * (p.gr_ld ? p.gr_ld : 2 * E);
-        float g0 = __ldg(p.gr + gro + 2 * e);
-        float g1 = __ldg(p.gr + gro + 2 * e + 1);
-        float centre = linspace_at(margin, 1.f - margin, E, e) + tanhf(g0) * margin;
-        float width = 1.f / (1.f + expf(-g1));
-        s_c[i] = fminf(fmaxf(centre, 0.f), 1.f);
-        s_w[i] = fmaxf(width, 0.09f) / p.sigma;
-      }
-    }
-  }
-  __syncthreads();
-
-  // ---- phase 1: Gaussian masks, one warp per selected expert, peak-normalised over t ----------
-  for (int i = warp; i < K; i += NT / 32) {
-    const float c = s_c[i], w = s_w[i];
-    const float pref = 0.3989422804014327f / w;
-    const float den = 2.f * (w * w);
-    float mx = -INFINITY;
-    for (int t = lane; t < T; t += 32) {
-      float d = linspace_at(0.f, 1.f, T, t) - c;
-      float g = pref * expf(-(d * d) / den);
-      s_G[i * T + t] = g;
-      mx = fmaxf(mx, g);
-    }
-    mx = warp_max(mx);
-    for (int t = lane; t < T; t += 32) s_G[i * T + t] = s_G[i * T + t] / mx;
-  }
-  __syncthreads();
-
-  // ---- phase 2: coef[t][j] -------------------------------------------------------------------
-  for (int t = tid; t < T; t += NT) {
-    for (int e = 0; e < E; ++e) s_coef[t * E + e] = 0.f;
-    for (int i = 0; i < K; ++i) s_coef[t * E + s_perm[t * K + i]] += s_p[i] * s_G[i * T + t];
-  }
-  if (rank == 0) {
-    if (p.topk_inds && tid < K) p.topk_inds[(long long)b * K + tid] = s_idx[tid];
-    if (p.topk_probs && tid < K) p.topk_probs[(long long)b * K + tid] = s_p[tid];
-    if (p.gauss_weight)
-      for (int f = tid; f < K * T; f += NT) p.gauss_weight[(long long)b * K * T + f] = s_G[f];
-  }
-  __syncthreads();
+  // ---- router / Gaussian prologue (HBM is already streaming) ----------------------------------
+  gauss_prologue<NT>(p, b, sm);
+  if (rank == 0) gauss_write_aux<NT>(p, b, sm);
 
   // ---- main loop: consume ring stages in order, refill each stage as soon as the CTA is done with it ----
   float acc[SLOTS][VEC];
@@ -273,6 +300,54 @@ __global__ void __launch_bounds__(NT) gauss_reduce_kernel(GaussP p) {
     }
   }
   if (CLUSTER) cg::this_cluster().sync();   // keep every CTA's smem alive until all ranks have read it
+}
+
+// The GEMM-epilogue form of M4: the expert first-layer GEMM multiplies its relu'd tile by coef[b,t,e] and sums
+// over the rows of a sample in its epilogue (gemm_tc.cuh, EPI = 4), so the hidden activations [T,B,E,C/2] never reach HBM.  This
+// kernel provides what that epilogue needs: coef[b*T + t][e] for every row of the batch, the bias column block
+// hb[b, E*Ch + e] = sum_t coef[b,t,e] (e < 64, zero beyond E) of the second-layer contraction -- in `nrep` row blocks of hb,
+// B rows apart (the two vt branches share one router) -- and the optional rank / gate / mask outputs.  One CTA per sample.
+struct MoeCoefP {
+  GaussP g;          // rl / gr / B / T / E / K / sigma / aux outputs (x, out unused)
+  float* coef;       // [B*T, E]
+  float* hb;         // [nrep*B, ldh]
+  int ldh, col0, nrep;
+};
+
+constexpr int MOE_COEF_NT = 128;
+
+__global__ void __launch_bounds__(MOE_COEF_NT) moe_coef_kernel(MoeCoefP q) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const GaussP& p = q.g;
+  const int T = p.T, E = p.E, K = p.K, tid = threadIdx.x, b = blockIdx.x;
+  GaussSm sm;
+  sm.coef = reinterpret_cast<float*>(smem_raw);
+  sm.G = sm.coef + T * E;
+  sm.p = sm.G + K * T;
+  sm.c = sm.p + K;
+  sm.w = sm.c + K;
+  sm.idx = reinterpret_cast<int*>(sm.w + K);
+  sm.perm = reinterpret_cast<unsigned char*>(sm.idx + K);
+  gauss_prologue<MOE_COEF_NT>(p, b, sm);
+  gauss_write_aux<MOE_COEF_NT>(p, b, sm);
+  for (int f = tid; f < T * E; f += MOE_COEF_NT) q.coef[(long long)b * T * E + f] = sm.coef[f];
+  for (int e = tid; e < 64; e += MOE_COEF_NT) {
+    float sum = 0.f;
+    if (e < E)
+      for (int t = 0; t < T; ++t) sum += sm.coef[t * E + e];
+    for (int r = 0; r < q.nrep; ++r) q.hb[((long long)r * p.B + b) * q.ldh + q.col0 + e] = sum;
+  }
+}
+
+inline int moe_coef(Ctx& c, const MoeCoefP& q) {
+  const GaussP& p = q.g;
+  QAT_REQUIRE(p.E >= 1 && p.E <= GAUSS_MAX_E && p.K >= 1 && p.K <= p.E && p.T >= 1 && p.T <= 4096 && p.B >= 1, "moe_coef: bad shape");
+  if (c.dry) return QAT_OK;
+  const size_t smem = ((size_t)p.T * p.E + (size_t)p.K * p.T + 3 * (size_t)p.K) * 4 + (size_t)p.K * 4 + (size_t)p.T * p.K + 16;
+  QAT_REQUIRE(smem <= 200 * 1024, "moe_coef: T*E too large for one CTA");
+  if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(moe_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  moe_coef_kernel<<<p.B, MOE_COEF_NT, smem, c.stream>>>(q);
+  return check_launch("moe_coef_kernel");
 }
 
 inline size_t gauss_smem_bytes(const GaussP& p, size_t row_bytes) {

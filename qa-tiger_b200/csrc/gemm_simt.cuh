@@ -12,6 +12,13 @@ struct Epi {
   const float* res = nullptr;   // [M, ldr] added after the activation
   int ldr = 0;
   const __half* res_h = nullptr;  // the same residual as an fp16 plane (tensor-core GEMMs only; res wins if both are set)
+  // tcgen05 kinds only -- the "reduce" epilogue (M4 of SURVEY 8a folded into the expert first-layer GEMM): rows are (sample, t)
+  // pairs, T rows per sample; instead of storing act(A W^T + b) the epilogue writes, per sample s and column n,
+  //   C.f[s, n] = sum_t coef[(s*T + t) % coef_mod, n / coef_Ch] * act(...)[s*T + t, n]
+  // i.e. the Gaussian-weighted temporal reduction of expert n / coef_Ch (coef from moe_coef_kernel)
+  const float* coef = nullptr;    // [coef_mod, coef_E]
+  int coef_E = 0, coef_T = 0, coef_Ch = 0;
+  long long coef_mod = 0;
 };
 
 __device__ __forceinline__ float epi_act(float x, int mode) {

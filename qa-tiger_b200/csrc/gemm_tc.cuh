@@ -166,8 +166,26 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
 #define QAT_DBG(p, bit) 0
 #endif
 
+// column sums over the 32 lanes of a warp: lane L holds x[0..31] (one row, 32 columns); returns, in lane j, sum_L x_L[j].
+// Recursive halving: at distance o a lane keeps the half of its columns that matches its lane bit and hands the other half to
+// its partner -- 31 shuffles for 32 x 32 values, fixed summation tree (bit-reproducible), no shared memory.
+__device__ __forceinline__ float warp_colsum32(float (&x)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = up ? x[i] : x[i + o];
+      const float keep = up ? x[i + o] : x[i];
+      x[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return x[0];
+}
+
 struct GemmP {
   int M, N, K;
+  int tile_rows;   // rows of A a CTA's tile advances by: 128, or (128 / T) * T with the reduce epilogue (whole samples per tile)
   Epi epi;
   Act C;
   int pair_f16;    // 1: the (hi, lo) output pair is fp16 (Act::ph / pl, through the mChi / mClo maps) instead of bf16
@@ -235,7 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nkb = (p.K + G::BK - 1) / G::BK;
   const int tiles_n = (p.N + BN - 1) / BN;
-  const int tiles_m = ((p.M + G::BM - 1) / G::BM + CG - 1) / CG;             // pair tiles when CG == 2 (a tail pair may be half empty)
+  const int tiles_m = ((p.M + p.tile_rows - 1) / p.tile_rows + CG - 1) / CG;  // pair tiles when CG == 2 (a tail pair may be half empty)
   const int ntiles = tiles_n * tiles_m;
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
   const int unit0 = blockIdx.x / CG, nunits = gridDim.x / CG;                 // persistent walk, one unit = one CTA (pair)
@@ -279,7 +297,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     {
       uint32_t it = 0;                                   // running k-block counter across tiles
       for (int t = unit0; t < ntiles; t += nunits) {
-        const int m0 = ((t / tiles_n) * CG + (int)crank) * G::BM, n0 = (t % tiles_n) * BN + (int)crank * G::BN_CTA;
+        const int m0 = ((t / tiles_n) * CG + (int)crank) * p.tile_rows, n0 = (t % tiles_n) * BN + (int)crank * G::BN_CTA;
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (it / STAGES) & 1;
@@ -378,7 +396,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     const uint32_t tempty_a0 = CG == 2 ? mapa_rank(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]);
     const uint32_t tempty_a1 = CG == 2 ? mapa_rank(smem_u32(&tempty[1]), 0) : smem_u32(&tempty[1]);
     for (int t = unit0; t < ntiles; t += nunits, ++lt) {
-      const int m0 = ((t / tiles_n) * CG + (int)crank) * G::BM, n0 = (t % tiles_n) * BN;
+      const int m0 = ((t / tiles_n) * CG + (int)crank) * p.tile_rows, n0 = (t % tiles_n) * BN;
       const uint32_t as = lt & 1;
       mbar_wait(&tfull[as], (lt >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -390,6 +408,110 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         if (lane == 0) {
           if (CG == 2) mbar_arrive_cluster((as ? tempty_a1 : tempty_a0));
           else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((as ? tempty_a1 : tempty_a0)) : "memory");
+        }
+        continue;
+      }
+      if (EPI == 4) {
+        // ---- reduce epilogue: Gaussian-weighted temporal reduction of the tile's samples (Epi::coef) ----------------------
+        // The tile holds tile_rows / T whole samples.  A warp's 32 rows touch at most two of them (T >= 32): rows [0, split)
+        // belong to the first, the rest to the next.  Per 32-column chunk every lane scales its row by coef[row, expert] and the
+        // warp sums columns over its rows with warp_colsum32 (twice when it straddles two samples); the per-warp partial sums
+        // (lane = column) are parked in the warp's box, double-buffered over tiles, and after ONE named barrier per tile the
+        // 256 epilogue threads add the partials of the four row quarters in order and store sample x column sums -- no
+        // atomics, bit-reproducible.
+        const int TT = p.epi.coef_T, TR = p.tile_rows;
+        const int r_in = lg * 32 + lane;
+        const bool rvalid = r_in < TR && row_ok;
+        const int samp0 = (lg * 32) / TT;
+        const int split = (samp0 + 1) * TT - lg * 32;                 // >= 1
+        const bool two = split < 32 && lg * 32 + split < TR;           // warp-uniform
+        const bool inA = lane < split;
+        const float* crow = p.epi.coef + (rvalid ? (row % p.epi.coef_mod) : 0) * p.epi.coef_E;
+        float ps0[NCH], ps1[NCH];
+        uint32_t v[32];
+        if (n0 + half * HALF_N < p.N) tmem_ld32(tacc, v);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = n0 + half * HALF_N + c * 32;
+          const bool live = col0 < p.N;                       // warp-uniform
+          float cf = 0.f;
+          float4 bb[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            bb[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (live && p.epi.bias && col0 + 4 * q < p.N) bb[q] = __ldg(reinterpret_cast<const float4*>(p.epi.bias + col0 + 4 * q));
+          }
+          if (live && rvalid) cf = __ldg(crow + col0 / p.epi.coef_Ch);
+          if (live) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          float x[32];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            x[4 * q] = __uint_as_float(v[4 * q]) + bb[q].x;
+            x[4 * q + 1] = __uint_as_float(v[4 * q + 1]) + bb[q].y;
+            x[4 * q + 2] = __uint_as_float(v[4 * q + 2]) + bb[q].z;
+            x[4 * q + 3] = __uint_as_float(v[4 * q + 3]) + bb[q].w;
+          }
+          if (c + 1 < NCH && col0 + 32 < p.N) tmem_ld32(tacc + uint32_t((c + 1) * 32), v);
+          if (c == NCH - 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) {
+              if (CG == 2) mbar_arrive_cluster((as ? tempty_a1 : tempty_a0));
+              else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((as ? tempty_a1 : tempty_a0)) : "memory");
+            }
+          }
+          ps0[c] = 0.f;
+          ps1[c] = 0.f;
+          if (!live) continue;
+          // rows beyond the tile's samples (or beyond M) contribute exact zeros, whatever their accumulator holds
+          if (p.epi.relu == 1) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = rvalid ? fmaxf(x[e], 0.f) * cf : 0.f;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) x[e] = rvalid ? epi_act(x[e], p.epi.relu) * cf : 0.f;
+          }
+          if (two) {
+            float y[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+              y[e] = inA ? 0.f : x[e];
+              x[e] = inA ? x[e] : 0.f;
+            }
+            ps0[c] = warp_colsum32(x, lane);
+            ps1[c] = warp_colsum32(y, lane);
+          } else {
+            ps0[c] = warp_colsum32(x, lane);
+          }
+        }
+        float* pb = reinterpret_cast<float*>(box + (lt & 1) * 1024);
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          pb[c * 32 + lane] = ps0[c];
+          pb[(NCH + c) * 32 + lane] = ps1[c];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");            // the eight epilogue warps
+        {
+          const int q = ew * 32 + lane;                             // column of the tile this thread combines
+          const int hq = q / HALF_N, cq = (q % HALF_N) / 32, jq = q % 32;
+          const int nsamp = TR / TT;
+          for (int s = 0; s < nsamp; ++s) {
+            float sum = 0.f;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {                           // row quarters in order
+              const int f = (g * 32) / TT;
+              const int sp = (f + 1) * TT - g * 32;
+              int slot = -1;
+              if (s == f) slot = 0;
+              else if (s == f + 1 && sp < 32 && g * 32 + sp < TR) slot = 1;
+              if (slot >= 0) {
+                const int ewg = hq * 4 + ((g + 2) & 3);             // the warp of column half hq that owns TMEM lane quarter g
+                const float* ob = reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(epi_smem) + ewg * 4096 + (lt & 1) * 1024);
+                sum += ob[(slot * NCH + cq) * 32 + jq];
+              }
+            }
+            const long long srow = (long long)m0 / TT + s;
+            if (srow * TT < p.M && n0 + q < p.N) p.C.f[srow * p.C.ld + n0 + q] = sum;
+          }
         }
         continue;
       }
@@ -626,10 +748,11 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
     mW1 = mW0;
   }
   QAT_REQUIRE(C.f || C.hi || C.h || C.ph, "gemm_tc: no output plane");
+  const Act Cstore = epi.coef ? Act() : C;      // the reduce epilogue stores through the LSU ([samples, N], not [M, N])
   QAT_REQUIRE(!C.lo || C.hi, "gemm_tc: a lo plane needs its hi plane");
   QAT_REQUIRE((C.ph != nullptr) == (C.pl != nullptr) && !(C.ph && C.hi), "gemm_tc: the fp16 pair needs both planes and excludes the bf16 pair");
   mCf = mChi = mClo = mCh = mA0;
-  if (C.f) QAT_TRY(make_store_map(&mCf, C.f, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, M, N, C.ld));
+  if (Cstore.f) QAT_TRY(make_store_map(&mCf, C.f, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, M, N, C.ld));
   if (C.hi) QAT_TRY(make_store_map(&mChi, C.hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
   if (C.lo) QAT_TRY(make_store_map(&mClo, C.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
   if (C.h) QAT_TRY(make_store_map(&mCh, C.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
@@ -640,6 +763,13 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   GemmP p;
   p.pair_f16 = C.ph ? 1 : 0;
   p.M = (int)M; p.N = N; p.K = K; p.epi = epi; p.C = C;
+  p.tile_rows = G::BM;
+  if (epi.coef) {
+    QAT_REQUIRE(BN == 256 && C.f && !C.hi && !C.h && !C.ph && !epi.res && !epi.res_h, "gemm_tc: the reduce epilogue writes one fp32 plane from 256-wide tiles");
+    QAT_REQUIRE(epi.coef_T >= 32 && epi.coef_T <= 128 && M % epi.coef_T == 0 && epi.coef_Ch % 32 == 0 && epi.coef_E >= 1 && epi.coef_mod >= 1,
+                "gemm_tc: reduce epilogue needs 32 <= T <= 128, M %% T == 0 and Ch %% 32 == 0 (T=%d Ch=%d)", epi.coef_T, epi.coef_Ch);
+    p.tile_rows = (G::BM / epi.coef_T) * epi.coef_T;
+  }
   // fp16 residual next to an fp16-only output: through the TMA unit as well (lane-per-row LSU loads of a row-strided
   // residual cost 32 L1 wavefronts per instruction and made the PatchSelecter out-proj epilogue-bound)
   mR = mA0;
@@ -653,7 +783,7 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   if (const char* dbg = getenv("QAT_GEMM_DBG")) p.dbg = atoi(dbg);
 #endif
   // persistent units: CTAs, or CTA pairs walking 256-row pair tiles
-  const long long ntiles = (long long)((N + BN - 1) / BN) * (((M + G::BM - 1) / G::BM + CG - 1) / CG);
+  const long long ntiles = (long long)((N + BN - 1) / BN) * (((M + p.tile_rows - 1) / p.tile_rows + CG - 1) / CG);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -681,7 +811,11 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
     cfg.numAttrs = CG == 2 ? 1 : 0;                                                                           \
     QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, mA0, mA1, mW0, mW1, mCf, mChi, mClo, mCh, mR, p));                \
   } while (0)
-  if (mode == 1) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 ? 0 : 1));
+  if (epi.coef) {
+    // instantiated for the kind / tile the expert GEMM uses (bf16x3, 256-wide tiles, single CTA or CTA pair)
+    if (KIND == KIND_BF16X3 && BN == 256) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 && BN == 256 ? 4 : 0));
+    else QAT_FAIL(QAT_EINVAL, "gemm_tc: the reduce epilogue is built for the bf16x3 kind with 256-wide tiles");
+  } else if (mode == 1) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 ? 0 : 1));
   else if (mode == 2) QAT_GEMM_LAUNCH(2);
   else if (mode == 3) QAT_GEMM_LAUNCH((KIND == KIND_BF16X3 ? 3 : 0));
   else QAT_GEMM_LAUNCH(0);

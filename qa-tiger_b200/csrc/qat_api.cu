@@ -200,6 +200,10 @@ static int run_gemm(const QatGemmArgs* a, Ctx& c) {
   e.res_h = reinterpret_cast<const __half*>(a->res_f16);
   e.ldr = a->ldr;
   QAT_REQUIRE(a->kind != G_SIMT || !e.res_h, "gemm: the SIMT engine takes fp32 residuals only");
+  if (a->coef) {
+    QAT_REQUIRE(a->kind == G_BF16X3, "gemm: the reduce epilogue is built for the bf16x3 kind");
+    e.coef = a->coef; e.coef_E = a->coef_E; e.coef_T = a->coef_T; e.coef_Ch = a->coef_Ch; e.coef_mod = a->coef_mod;
+  }
   return gemm(c, (GemmKind)a->kind, A, a->M, wview(a->w), e, C);
 }
 
@@ -604,6 +608,56 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
   QAT_TRY(gemm(c, G_SIMT, TW, B, Wrg, Epi(), RG));
   // RG rows are [router(E) | gauss(2E)] with ld 3E: the reduce kernel reads both through a row pitch
 
+  // M4 in the expert GEMM's epilogue: the first-layer GEMM scales its relu'd tile by coef[b,t,e] and sums over
+  // the rows of a sample before anything is stored, so the hidden activations [rows, E*Ch] (3 x 110 MB written + read back per
+  // 256-question batch) never reach HBM and the gauss_reduce launches disappear.  bf16 mode, 32 <= T <= 128, 256-wide tiles.
+  const bool fused_reduce = k_w1 == G_BF16X3 && T >= 32 && T <= 128 && Ch % 32 == 0 && (E * Ch) % 256 == 0 && c.opt.v[OPT_MOE_NO_FUSED_REDUCE] != 1 &&
+                            c.opt.v[OPT_GEMM_BN] != 128;
+  if (fused_reduce) {
+    const int nb = two ? 2 : 1;
+    const bool stacked = two && xe_a && xe_v && xe_stacked;
+    Act Hb, Ob;
+    float* coef = reinterpret_cast<float*>(c.alloc((size_t)BT * E * 4));
+    if (!c.dry && !coef) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+    QAT_TRY(act_alloc(c, Hb, (long long)nb * B, KE, true, false));
+    MoeCoefP q;
+    q.g = GaussP();
+    q.g.x = nullptr; q.g.st = 0; q.g.sb = 0;
+    q.g.rl = RG.f; q.g.gr = RG.f + E; q.g.rl_ld = 3 * E; q.g.gr_ld = 3 * E; q.g.B = B; q.g.T = T; q.g.E = E; q.g.K = K; q.g.C = Ch; q.g.sigma = a->sigma;
+    q.g.per_expert = 1; q.g.ring = 0;
+    q.g.topk_inds = reinterpret_cast<long long*>(a->topk_inds); q.g.topk_probs = a->topk_probs; q.g.gauss_weight = a->gauss_weight;
+    q.coef = coef; q.hb = Hb.f; q.ldh = KE; q.col0 = E * Ch; q.nrep = nb;
+    QAT_TRY(moe_coef(c, q));
+    Epi e;
+    e.relu = 1;
+    e.coef = coef; e.coef_E = E; e.coef_T = T; e.coef_Ch = Ch; e.coef_mod = BT;
+    if (stacked) {
+      QAT_TRY(gemm(c, k_w1, *xe_a, 2 * BT, W1, e, Hb));
+    } else {
+      for (int br = 0; br < nb; ++br) {
+        const size_t mark = c.mark();
+        Act Xe = Xd;
+        if (two && xe_a && xe_v) {
+          Xe = br == 0 ? *xe_a : *xe_v;
+        } else if (two) {
+          QAT_TRY(act_alloc(c, Xe, BT, D, false, true));
+          QAT_TRY(add_rows(c, Xd.f, Xd.ld, br == 0 ? sub_a : sub_v, D, Xe, BT, D));     // :587,597
+        }
+        QAT_TRY(gemm(c, k_w1, Xe, BT, W1, e, Hb.rows((long long)br * B)));
+        c.release(mark);
+      }
+    }
+    QAT_TRY(act_alloc(c, Ob, (long long)nb * B, D, true, false));
+    {
+      Epi e2;
+      WView w2 = W2;
+      w2.bias = nullptr;
+      QAT_TRY(gemm(c, G_SIMT, Hb, (long long)nb * B, w2, e2, Ob));
+    }
+    QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm_a, act_of(out_a, D), B, D));
+    if (two) QAT_TRY(ln(c, Ob.f + (size_t)B * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm_v, act_of(out_v, D), B, D));
+    return QAT_OK;
+  }
   if (two && xe_a && xe_v && xe_stacked) {
     Act Hd, Hb, Ob;
     QAT_TRY(act_alloc(c, Hd, 2 * BT, E * Ch, true, false));

@@ -131,3 +131,32 @@ def test_gemm_cta_pairs(cg, M, opt):
     rh = res.half()
     got3 = _cabi.gemm(_cabi.GEMM_F16, ah, lin, relu=True, res=rh)
     assert torch.equal(_cabi.gemm(_cabi.GEMM_F16, ah, lin, relu=True, res=rh, out_f16=True), got3.half())
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("S,T,E,rep", [(5, 60, 7, 1), (64, 60, 7, 2), (3, 120, 14, 1), (9, 32, 2, 1), (7, 100, 3, 1), (4, 128, 1, 1), (12, 50, 4, 2),
+                                       (257, 60, 7, 1)])
+def test_gemm_reduce_epilogue(cg, S, T, E, rep, opt):
+    """Expert first-layer GEMM with M4 in its epilogue (gemm_tc.cuh EPI = 4): out[s, n] = sum_t coef[row, n // Ch] relu(a W^T + b).
+    Samples of 32..128 rows (tiles of whole samples, warps straddling two samples, tail tiles / half-empty tail pairs),
+    the coefficient table shared by `rep` row blocks (the two vt branches), single CTAs and CTA pairs."""
+    from qa_tiger_b200 import _cabi
+    opt("gemm_cg", cg)
+    Ch, K = 256, 192
+    M, N = S * T, E * Ch
+    g = torch.Generator(device="cuda").manual_seed(S * 1000 + T)
+    a = torch.randn(M, K, device=dev(), generator=g)
+    w = torch.randn(N, K, device=dev(), generator=g) * K ** -0.5
+    b = torch.randn(N, device=dev(), generator=g)
+    assert S % rep == 0 or rep == 1
+    R = M // rep if S % rep == 0 else M
+    coef = torch.rand(R, E, device=dev(), generator=g)
+    lin = _cabi.Lin(w, b, _cabi.PREC_BF16)
+    got = _cabi.gemm_reduce(a, lin, coef, T, Ch)
+    h = torch.relu(a.double() @ w.double().t() + b.double())                    # [M, N]
+    cf = coef.double()[torch.arange(M, device=dev()) % R]                        # [M, E]
+    ref = (h.view(S, T, E, Ch) * cf.view(S, T, E, 1)).sum(1).reshape(S, N)
+    assert got.shape == (S, N)
+    assert relerr(got, ref) < 2e-5
+    # bit-reproducible: no atomics anywhere in the reduction
+    assert torch.equal(got, _cabi.gemm_reduce(a, lin, coef, T, Ch))

@@ -77,3 +77,31 @@ def test_tome_match_kernels_agree():
     for s1, s2 in zip(steps, steps2):
         for t1, t2 in zip(s1, s2):
             assert torch.equal(t1, t2)
+
+
+@pytest.mark.parametrize("B,T,E,K,two", [(40, 60, 7, 7, True), (40, 60, 7, 7, False), (12, 120, 14, 14, True), (37, 60, 10, 5, True)])
+def test_moe_fused_reduce_matches_the_streaming_kernel(B, T, E, K, two):
+    """TempMoE with M4 in the expert GEMM's epilogue (default) against first-layer GEMM + gauss_reduce_kernel launches: the same
+    coefficients and products, another summation order (fp32)."""
+    from qa_tiger_b200 import _cabi
+    from qa_tiger_b200.models import modules as M
+    sdm = synth.make_state_dict(720 + E, num_experts=E, text_tower=False)
+    pfx = "vt_aggregator" if two else "at_aggregator"
+    m = M.TempMoE(512, 8, topK=K, n_experts=E, vis_branch=two)
+    m.load_state_dict(sub_sd(sdm, pfx))
+    m = m.to(dev()).eval()
+    m.precision = "bf16"
+    m.keep_aux = True
+    g = torch.Generator().manual_seed(B + T)
+    q, d = torch.randn(B, 512, generator=g).to(dev()), torch.randn(B, T, 512, generator=g).to(dev())
+    sub = [torch.randn(B, T, 512, generator=g).to(dev()), torch.randn(B, T, 512, generator=g).to(dev())] if two else None
+    with torch.no_grad():
+        fused = m(q, d, sub)
+        aux_f = [t.clone() for t in m.last_aux]
+        with _cabi.option("moe_no_fused_reduce", 1):
+            plain = m(q, d, sub)
+        aux_p = m.last_aux
+    for x, y in zip(aux_f, aux_p):
+        assert torch.equal(x, y)
+    for x, y in zip(fused if two else [fused], plain if two else [plain]):
+        assert relerr(x, y) < 2e-6
