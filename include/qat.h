@@ -221,9 +221,14 @@ typedef struct {
   const float* sub_a;      /* optional sub_data[0] [B,T,D] */
   const float* sub_v;      /* optional sub_data[1] [B,T,D] */
   QatLinearW attn_q;       /* qst_attn.in_proj[0:D] */
-  QatLinearW attn_kv;      /* qst_attn.in_proj[D:3D] */
-  QatLinearW attn_out;
-  QatLinearW router_gauss; /* [3E, D] = cat(router.0, gauss_pred.0) */
+  QatLinearW attn_kv;      /* qst_attn.in_proj[D:3D] (fp32; only the K rows [0, D) are read, see attn_rg) */
+  QatLinearW attn_rg;      /* [3E, H*D] fp32 + bias [3E]: the value projection, the out-projection, router.0 and gauss_pred.0 of
+                              modules.py:562-578 composed on the host (one query row per sample: the projections commute with the
+                              attention, csrc/moe_front.cuh).  With Wrg = cat(router.0.weight, gauss_pred.0.weight) [3E, D],
+                              Wo / bo = qst_attn.out_proj, Wv / bv = qst_attn.in_proj[2D:3D], head h = rows / columns [64h, 64h+64):
+                                attn_rg.w[:, h*D:(h+1)*D] = (Wrg Wo)[:, 64h:64h+64] Wv[64h:64h+64, :]
+                                attn_rg.bias             = Wrg (Wo bv + bo) + cat(router.0.bias, gauss_pred.0.bias)
+                              (compute in fp64, round once to fp32; qa-tiger_b200/models/modules.py TempMoE._prepare) */
   QatLinearW w1_cat;       /* [E*D/2, D] = cat_e experts.e.0 */
   QatLinearW w2_ext;       /* [D, E*D/2 + 64]: cols e*D/2+c = experts.e.2.weight[:,c]; col E*D/2+e = experts.e.2.bias; 0 after */
   QatLayerNormW norm_a;    /* `norm` (single branch) or `anorm` */

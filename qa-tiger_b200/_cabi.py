@@ -80,7 +80,7 @@ class MoeArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("E", C.c_int32), ("K", C.c_int32),
                 ("prec", C.c_int32), ("sigma", C.c_float), ("stream", C.c_void_p),
                 ("qst", C.c_void_p), ("data", C.c_void_p), ("sub_a", C.c_void_p), ("sub_v", C.c_void_p),
-                ("attn_q", LinearW), ("attn_kv", LinearW), ("attn_out", LinearW), ("router_gauss", LinearW),
+                ("attn_q", LinearW), ("attn_kv", LinearW), ("attn_rg", LinearW),
                 ("w1_cat", LinearW), ("w2_ext", LinearW), ("norm_a", LayerNormW), ("norm_v", LayerNormW),
                 ("out_a", C.c_void_p), ("out_v", C.c_void_p),
                 ("topk_inds", C.c_void_p), ("topk_probs", C.c_void_p), ("gauss_weight", C.c_void_p),

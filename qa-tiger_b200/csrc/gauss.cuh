@@ -313,11 +313,15 @@ struct MoeCoefP {
   float* hb;         // [nrep*B, ldh]
   int ldh, col0, nrep;
 };
+struct MoeCoefPack {
+  MoeCoefP m[2];     // blockIdx.y selects the module (at_aggregator / vt_aggregator share a launch)
+};
 
 constexpr int MOE_COEF_NT = 128;
 
-__global__ void __launch_bounds__(MOE_COEF_NT) moe_coef_kernel(MoeCoefP q) {
+__global__ void __launch_bounds__(MOE_COEF_NT) moe_coef_kernel(MoeCoefPack pk) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  const MoeCoefP& q = pk.m[blockIdx.y];
   const GaussP& p = q.g;
   const int T = p.T, E = p.E, K = p.K, tid = threadIdx.x, b = blockIdx.x;
   GaussSm sm;
@@ -339,14 +343,18 @@ __global__ void __launch_bounds__(MOE_COEF_NT) moe_coef_kernel(MoeCoefP q) {
   }
 }
 
-inline int moe_coef(Ctx& c, const MoeCoefP& q) {
-  const GaussP& p = q.g;
+// n modules (1 or 2) with the same B / T / E / K in one launch
+inline int moe_coef(Ctx& c, const MoeCoefPack& pk, int n) {
+  const GaussP& p = pk.m[0].g;
+  QAT_REQUIRE(n >= 1 && n <= 2, "moe_coef: 1 or 2 modules per launch");
   QAT_REQUIRE(p.E >= 1 && p.E <= GAUSS_MAX_E && p.K >= 1 && p.K <= p.E && p.T >= 1 && p.T <= 4096 && p.B >= 1, "moe_coef: bad shape");
+  for (int m = 1; m < n; ++m)
+    QAT_REQUIRE(pk.m[m].g.B == p.B && pk.m[m].g.T == p.T && pk.m[m].g.E == p.E && pk.m[m].g.K == p.K, "moe_coef: modules of one launch must share B / T / E / K");
   if (c.dry) return QAT_OK;
   const size_t smem = ((size_t)p.T * p.E + (size_t)p.K * p.T + 3 * (size_t)p.K) * 4 + (size_t)p.K * 4 + (size_t)p.T * p.K + 16;
   QAT_REQUIRE(smem <= 200 * 1024, "moe_coef: T*E too large for one CTA");
   if (smem > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(moe_coef_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  moe_coef_kernel<<<p.B, MOE_COEF_NT, smem, c.stream>>>(q);
+  moe_coef_kernel<<<dim3(p.B, n), MOE_COEF_NT, smem, c.stream>>>(pk);
   return check_launch("moe_coef_kernel");
 }
 

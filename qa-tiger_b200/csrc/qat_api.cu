@@ -8,6 +8,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_attn.cuh"
+#include "moe_front.cuh"
 #include "qat_common.cuh"
 #include "rowops.cuh"
 #include "tome.cuh"
@@ -558,79 +559,125 @@ static int run_gauss(const QatGaussArgs* a, Ctx& c) {
 // =================================================================================================
 // M1-M4 (+LN)  TempMoE
 // =================================================================================================
-// xe_a / xe_v (optional, qat_forward_fwd): the expert inputs data + sub_data[i] already formed by the producer of sub_data
-// (sub_a / sub_v are then only markers for "two branches" and are not read); xe_stacked: xe_v's rows follow xe_a's in memory, so
-// the two branches, which share every weight, run their expert GEMMs as single launches over 2*BT (2*B) rows
-static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst, Act Xd, const float* sub_a, const float* sub_v, float* out_a,
-                    float* out_v, const float* qpre = nullptr, int ldq = 0, const Act* xe_a = nullptr, const Act* xe_v = nullptr,
-                    bool xe_stacked = false) {
-  const int D = a->D, H = a->H, E = a->E, K = a->K;
-  QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
-  QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
-  QAT_REQUIRE((sub_a == nullptr) == (sub_v == nullptr), "temp_moe: sub_data needs both tensors or none");
-  const int Ch = D / 2, KE = E * Ch + 64;
-  QAT_TRY(check_w(a->attn_q, D, D, "moe.attn_q", c.prec));
-  QAT_TRY(check_w(a->attn_kv, 2 * D, D, "moe.attn_kv", c.prec));
-  QAT_TRY(check_w(a->attn_out, D, D, "moe.attn_out", c.prec));
-  QAT_TRY(check_w(a->router_gauss, 3 * E, D, "moe.router_gauss", c.prec));
-  QAT_TRY(check_w(a->w1_cat, E * Ch, D, "moe.w1_cat", c.prec));
-  QAT_TRY(check_w(a->w2_ext, D, KE, "moe.w2_ext", c.prec));
+// One TempMoE module inside a front / back pair.  xe_a / xe_v (optional, qat_forward_fwd): the expert inputs data + sub_data[i]
+// already formed by the producer of sub_data (sub_a / sub_v are then only markers for "two branches" and are not read);
+// xe_stacked: xe_v's rows follow xe_a's in memory, so the two branches, which share every weight, run their expert GEMM as a
+// single launch over 2*BT rows.
+struct MoeMod {
+  const QatMoeArgs* a = nullptr;
+  const float* qst = nullptr;      // [B, D] projected question (input of attn_q) ...
+  const float* qpre = nullptr;     // ... or attn_q(qst) computed by the caller, row pitch ldq
+  int ldq = 0;
+  Act Xd;                          // data [B*T, D]: fp32 view + whatever planes its producer emitted
+  const float* sub_a = nullptr;
+  const float* sub_v = nullptr;
+  const Act* xe_a = nullptr;
+  const Act* xe_v = nullptr;
+  bool xe_stacked = false;
+  float* out_a = nullptr;
+  float* out_v = nullptr;
+  // set by moe_front
+  Act RG;                          // [B, 3E] router logits | gauss_pred
+  bool fused = false;              // M4 runs in the expert GEMM's epilogue
+  float* coef = nullptr;           // [B*T, E]   (fused)
+  Act Hb;                          // [nbranch*B, E*Ch + 64]  (fused: bias-column block already written)
+};
+
+// temp_w -> router | gauss_pred for up to two modules per launch sequence (moe_front.cuh), then the per-row coefficients of
+// the modules whose M4 runs in the GEMM epilogue
+static int moe_front(Ctx& c, MoeMod* mods, int n, int B, int T) {
+  QAT_REQUIRE(n >= 1 && n <= MF_MAX, "temp_moe: 1 or 2 modules per front end");
   const long long BT = (long long)B * T;
-  const bool two = sub_a != nullptr;
-  QAT_REQUIRE(c.dry || (out_a && (!two || out_v)), "temp_moe: output pointer missing");
-  const WView Wq = wview(a->attn_q), Wkv = wview(a->attn_kv), Wo = wview(a->attn_out), Wrg = wview(a->router_gauss);
-  const WView W1 = wview(a->w1_cat), W2 = wview(a->w2_ext);
-  const GemmKind k_kv = pick_kind(c, BT, 2 * D, D, false, Wkv), k_w1 = pick_kind(c, BT, E * Ch, D, false, W1);
-
-  // temp_w = qst_attn(q = qst, kv = data)   (:562) -- the rank-critical chain: K/V at bf16x3 or fp32, rest fp32
-  Act KV, Q, Oq, TW, RG;
-  QAT_TRY(ensure_operand(c, Xd, BT, D, k_kv));
-  if (!two) QAT_TRY(ensure_operand(c, Xd, BT, D, k_w1));
-  QAT_TRY(act_alloc(c, KV, BT, 2 * D, true, false));
-  QAT_TRY(gemm(c, k_kv, Xd, BT, Wkv, Epi(), KV));
-  if (qpre) {
-    Q = act_of(qpre, ldq);
-  } else {
-    QAT_TRY(act_alloc(c, Q, B, D, true, false));
-    QAT_TRY(gemm(c, G_SIMT, act_of(qst, D), B, Wq, Epi(), Q));
+  MoeFrontP fp;
+  fp.n = n; fp.B = B; fp.T = T; fp.scale = 0.125f;
+  for (int m = 0; m < n; ++m) {
+    MoeMod& M = mods[m];
+    const QatMoeArgs* a = M.a;
+    const int D = a->D, H = a->H, E = a->E, K = a->K;
+    QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
+    QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
+    QAT_REQUIRE((M.sub_a == nullptr) == (M.sub_v == nullptr), "temp_moe: sub_data needs both tensors or none");
+    QAT_REQUIRE(m == 0 || (a->D == mods[0].a->D && a->H == mods[0].a->H && a->E == mods[0].a->E && a->K == mods[0].a->K),
+                "temp_moe: modules of one front end must share D / H / E / K");
+    const int Ch = D / 2, KE = E * Ch + 64;
+    QAT_TRY(check_w(a->attn_q, D, D, "moe.attn_q", c.prec));
+    QAT_TRY(check_w(a->attn_kv, 2 * D, D, "moe.attn_kv", c.prec));
+    QAT_TRY(check_w(a->attn_rg, 3 * E, H * D, "moe.attn_rg", c.prec));
+    QAT_REQUIRE(c.dry || a->attn_rg.bias, "moe.attn_rg: the composed bias is missing");
+    QAT_TRY(check_w(a->w1_cat, E * Ch, D, "moe.w1_cat", c.prec));
+    QAT_TRY(check_w(a->w2_ext, D, KE, "moe.w2_ext", c.prec));
+    QAT_REQUIRE(c.dry || (M.out_a && (!M.sub_a || M.out_v)), "temp_moe: output pointer missing");
+    QAT_REQUIRE(c.dry || M.Xd.f, "temp_moe: data needs its fp32 view");
+    QAT_REQUIRE(M.Xd.ld == D, "temp_moe: data must be dense [B*T, D]");
+    Act Q, U;
+    if (M.qpre) {
+      Q = act_of(M.qpre, M.ldq);
+    } else {
+      QAT_TRY(act_alloc(c, Q, B, D, true, false));
+      QAT_TRY(gemm(c, G_SIMT, act_of(M.qst, D), B, wview(a->attn_q), Epi(), Q));
+    }
+    QAT_TRY(act_alloc(c, U, B, H * D, true, false));
+    QAT_TRY(act_alloc(c, M.RG, B, 3 * E, true, false));
+    fp.D = D; fp.H = H; fp.E3 = 3 * E;
+    fp.q[m] = Q.f; fp.ldq[m] = Q.ld; fp.wk[m] = a->attn_kv.w; fp.x[m] = M.Xd.f;
+    fp.wrg[m] = a->attn_rg.w; fp.brg[m] = a->attn_rg.bias; fp.u[m] = U.f; fp.rg[m] = M.RG.f;
   }
-  QAT_TRY(act_alloc(c, Oq, B, D, true, false));
-  AttnP p;
-  p.nseq = B; p.H = H; p.Lq = 1; p.Lk = T; p.scale = 0.125f;
-  p.q = Q.f; p.q_sn = Q.ld; p.q_si = Q.ld;
-  p.k = KV.f; p.v = KV.f + D; p.k_sn = (long long)T * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B;
-  p.o = Oq; p.o_rn = 1; p.o_ri = 1; p.attw = nullptr;
-  QAT_TRY(attention(c, p));
-  QAT_TRY(act_alloc(c, TW, B, D, true, false));
-  QAT_TRY(gemm(c, G_SIMT, Oq, B, Wo, Epi(), TW));
-  // router logits [B,E] | gauss_pred [B,2E] in one fp32 contraction (:565,573)
-  QAT_TRY(act_alloc(c, RG, B, 3 * E, true, false));
-  QAT_TRY(gemm(c, G_SIMT, TW, B, Wrg, Epi(), RG));
-  // RG rows are [router(E) | gauss(2E)] with ld 3E: the reduce kernel reads both through a row pitch
-
+  QAT_TRY(moe_front_launch(c, fp));
   // M4 in the expert GEMM's epilogue: the first-layer GEMM scales its relu'd tile by coef[b,t,e] and sums over
   // the rows of a sample before anything is stored, so the hidden activations [rows, E*Ch] (3 x 110 MB written + read back per
   // 256-question batch) never reach HBM and the gauss_reduce launches disappear.  bf16 mode, 32 <= T <= 128, 256-wide tiles.
-  const bool fused_reduce = k_w1 == G_BF16X3 && T >= 32 && T <= 128 && Ch % 32 == 0 && (E * Ch) % 256 == 0 && c.opt.v[OPT_MOE_NO_FUSED_REDUCE] != 1 &&
-                            c.opt.v[OPT_GEMM_BN] != 128;
-  if (fused_reduce) {
+  MoeCoefPack pk;
+  int nf = 0;
+  for (int m = 0; m < n; ++m) {
+    MoeMod& M = mods[m];
+    const QatMoeArgs* a = M.a;
+    const int D = a->D, E = a->E, Ch = D / 2, KE = E * Ch + 64;
+    const bool two = M.sub_a != nullptr;
+    const GemmKind k_w1 = pick_kind(c, BT, E * Ch, D, false, wview(a->w1_cat));
+    M.fused = k_w1 == G_BF16X3 && T >= 32 && T <= 128 && Ch % 32 == 0 && (E * Ch) % 256 == 0 && c.opt.v[OPT_MOE_NO_FUSED_REDUCE] != 1 &&
+              c.opt.v[OPT_GEMM_BN] != 128;
+    if (!M.fused) continue;
     const int nb = two ? 2 : 1;
-    const bool stacked = two && xe_a && xe_v && xe_stacked;
-    Act Hb, Ob;
-    float* coef = reinterpret_cast<float*>(c.alloc((size_t)BT * E * 4));
-    if (!c.dry && !coef) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
-    QAT_TRY(act_alloc(c, Hb, (long long)nb * B, KE, true, false));
-    MoeCoefP q;
+    M.coef = reinterpret_cast<float*>(c.alloc((size_t)BT * E * 4));
+    if (!c.dry && !M.coef) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+    QAT_TRY(act_alloc(c, M.Hb, (long long)nb * B, KE, true, false));
+    MoeCoefP& q = pk.m[nf++];
     q.g = GaussP();
     q.g.x = nullptr; q.g.st = 0; q.g.sb = 0;
-    q.g.rl = RG.f; q.g.gr = RG.f + E; q.g.rl_ld = 3 * E; q.g.gr_ld = 3 * E; q.g.B = B; q.g.T = T; q.g.E = E; q.g.K = K; q.g.C = Ch; q.g.sigma = a->sigma;
-    q.g.per_expert = 1; q.g.ring = 0;
+    q.g.rl = M.RG.f; q.g.gr = M.RG.f + E; q.g.rl_ld = 3 * E; q.g.gr_ld = 3 * E; q.g.B = B; q.g.T = T; q.g.E = E; q.g.K = a->K; q.g.C = Ch;
+    q.g.sigma = a->sigma; q.g.per_expert = 1; q.g.ring = 0;
     q.g.topk_inds = reinterpret_cast<long long*>(a->topk_inds); q.g.topk_probs = a->topk_probs; q.g.gauss_weight = a->gauss_weight;
-    q.coef = coef; q.hb = Hb.f; q.ldh = KE; q.col0 = E * Ch; q.nrep = nb;
-    QAT_TRY(moe_coef(c, q));
+    q.coef = M.coef; q.hb = M.Hb.f; q.ldh = KE; q.col0 = E * Ch; q.nrep = nb;
+  }
+  if (nf) QAT_TRY(moe_coef(c, pk, nf));
+  return QAT_OK;
+}
+
+// experts -> M4 -> second-layer contraction -> LayerNorm of one module (modules.py:585-612)
+static int moe_back(Ctx& c, MoeMod& M, int B, int T) {
+  const QatMoeArgs* a = M.a;
+  const int D = a->D, E = a->E, K = a->K;
+  const int Ch = D / 2, KE = E * Ch + 64;
+  const long long BT = (long long)B * T;
+  const bool two = M.sub_a != nullptr;
+  const WView W1 = wview(a->w1_cat), W2 = wview(a->w2_ext);
+  const GemmKind k_w1 = pick_kind(c, BT, E * Ch, D, false, W1);
+  const Act* xe_a = M.xe_a;
+  const Act* xe_v = M.xe_v;
+  const float* sub_a = M.sub_a;
+  const float* sub_v = M.sub_v;
+  float* out_a = M.out_a;
+  float* out_v = M.out_v;
+  const Act& RG = M.RG;
+  Act Xd = M.Xd;
+  if (!two) QAT_TRY(ensure_operand(c, Xd, BT, D, k_w1));
+  if (M.fused) {
+    const int nb = two ? 2 : 1;
+    const bool stacked = two && xe_a && xe_v && M.xe_stacked;
+    Act Hb = M.Hb, Ob;
     Epi e;
     e.relu = 1;
-    e.coef = coef; e.coef_E = E; e.coef_T = T; e.coef_Ch = Ch; e.coef_mod = BT;
+    e.coef = M.coef; e.coef_E = E; e.coef_T = T; e.coef_Ch = Ch; e.coef_mod = BT;
     if (stacked) {
       QAT_TRY(gemm(c, k_w1, *xe_a, 2 * BT, W1, e, Hb));
     } else {
@@ -658,36 +705,7 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
     if (two) QAT_TRY(ln(c, Ob.f + (size_t)B * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm_v, act_of(out_v, D), B, D));
     return QAT_OK;
   }
-  if (two && xe_a && xe_v && xe_stacked) {
-    Act Hd, Hb, Ob;
-    QAT_TRY(act_alloc(c, Hd, 2 * BT, E * Ch, true, false));
-    {
-      Epi e;
-      e.relu = 1;
-      QAT_TRY(gemm(c, k_w1, *xe_a, 2 * BT, W1, e, Hd));
-    }
-    QAT_TRY(act_alloc(c, Hb, 2ll * B, KE, true, false));
-    for (int br = 0; br < 2; ++br) {
-      GaussP g;
-      g.x = Hd.f + (size_t)br * BT * E * Ch; g.st = (long long)E * Ch; g.sb = (long long)T * E * Ch;
-      g.rl = RG.f; g.gr = RG.f + E; g.rl_ld = 3 * E; g.gr_ld = 3 * E; g.B = B; g.T = T; g.E = E; g.K = K; g.C = Ch; g.sigma = a->sigma;
-      g.per_expert = 1; g.out = Hb.rows((long long)br * B);
-      g.topk_inds = br == 0 ? reinterpret_cast<long long*>(a->topk_inds) : nullptr;
-      g.topk_probs = br == 0 ? a->topk_probs : nullptr;
-      g.gauss_weight = br == 0 ? a->gauss_weight : nullptr;
-      QAT_TRY(gauss_reduce(c, g, QAT_DT_F32, 0));
-    }
-    QAT_TRY(act_alloc(c, Ob, 2ll * B, D, true, false));
-    {
-      Epi e;
-      WView w2 = W2;
-      w2.bias = nullptr;
-      QAT_TRY(gemm(c, G_SIMT, Hb, 2ll * B, w2, e, Ob));
-    }
-    QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm_a, act_of(out_a, D), B, D));
-    QAT_TRY(ln(c, Ob.f + (size_t)B * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm_v, act_of(out_v, D), B, D));
-    return QAT_OK;
-  }
+  // fp32 mode (and shapes outside the fused epilogue): first-layer GEMM writes the hidden activations, the streaming kernel reduces them
   const int nbranch = two ? 2 : 1;
   for (int br = 0; br < nbranch; ++br) {
     const size_t mark = c.mark();
@@ -729,6 +747,14 @@ static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst,
     c.release(mark);
   }
   return QAT_OK;
+}
+
+static int moe_core(const QatMoeArgs* a, int B, int T, Ctx& c, const float* qst, Act Xd, const float* sub_a, const float* sub_v, float* out_a,
+                    float* out_v) {
+  MoeMod M;
+  M.a = a; M.qst = qst; M.Xd = Xd; M.sub_a = sub_a; M.sub_v = sub_v; M.out_a = out_a; M.out_v = out_v;
+  QAT_TRY(moe_front(c, &M, 1, B, T));
+  return moe_back(c, M, B, T);
 }
 
 static int run_moe(const QatMoeArgs* a, Ctx& c) {
@@ -879,9 +905,21 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
   c.release(mark);
   QAT_TRY(patch_core(&a->patch_sel, B, T, P, c, a->patch, Ax, Vx, Ap, Vp, Vx.f, Vx.ld));
   c.release(mark);
-  QAT_TRY(moe_core(&a->at, B, T, c, Q0.f, Ax, nullptr, nullptr, a_global, nullptr, q_at, ldq));
-  c.release(mark);
-  QAT_TRY(moe_core(&a->vt, B, T, c, Q0.f, Vx, Vx.f, Vx.f, ap_global, vp_global, q_vt, ldq, &Ap, &Vp, true));
+  {
+    // both TempMoE modules share one front end (question attention -> router | gauss_pred -> coefficients: three launches)
+    MoeMod mm[2];
+    mm[0].a = &a->at; mm[0].qst = Q0.f; mm[0].qpre = q_at; mm[0].ldq = ldq; mm[0].Xd = Ax; mm[0].out_a = a_global;
+    mm[1].a = &a->vt; mm[1].qst = Q0.f; mm[1].qpre = q_vt; mm[1].ldq = ldq; mm[1].Xd = Vx; mm[1].sub_a = Vx.f; mm[1].sub_v = Vx.f;
+    mm[1].xe_a = &Ap; mm[1].xe_v = &Vp; mm[1].xe_stacked = true; mm[1].out_a = ap_global; mm[1].out_v = vp_global;
+    if (a->at.E == a->vt.E && a->at.K == a->vt.K) {
+      QAT_TRY(moe_front(c, mm, 2, B, T));
+    } else {
+      QAT_TRY(moe_front(c, &mm[0], 1, B, T));
+      QAT_TRY(moe_front(c, &mm[1], 1, B, T));
+    }
+    QAT_TRY(moe_back(c, mm[0], B, T));
+    QAT_TRY(moe_back(c, mm[1], B, T));
+  }
   c.release(mark);
   QAT_TRY(ground_core(&a->ground, B, c, Q0.f, ap_global, vp_global, fusion1, false, nullptr, q_gr, ldq));
   c.release(mark);

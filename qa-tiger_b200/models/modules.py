@@ -275,8 +275,16 @@ class TempMoE(_QatModule):
         D, E = self.d_model, self.n_experts
         Ch = D // 2
         at = self.qst_attn
-        rg_w = torch.cat([self.router[0].weight, self.gauss_pred[0].weight], 0)
-        rg_b = torch.cat([self.router[0].bias, self.gauss_pred[0].bias], 0)
+        # [router | gauss_pred] o out_proj o value projection, composed in fp64 (one query row per sample: the projections commute
+        # with the attention, csrc/moe_front.cuh): attn_rg.w[:, h*D:(h+1)*D] = (Wrg Wo)[:, head h] Wv[head h, :]
+        H, hd = self.nhead, D // self.nhead
+        rg_w = torch.cat([self.router[0].weight, self.gauss_pred[0].weight], 0).double()
+        rg_b = torch.cat([self.router[0].bias, self.gauss_pred[0].bias], 0).double()
+        wo, bo = at.out_proj.weight.double(), at.out_proj.bias.double()
+        wv, bv = at.in_proj_weight[2 * D:].double(), at.in_proj_bias[2 * D:].double()
+        rgo = rg_w @ wo                                                                 # [3E, D]
+        arg_w = torch.cat([rgo[:, h * hd:(h + 1) * hd] @ wv[h * hd:(h + 1) * hd] for h in range(H)], 1).float()   # [3E, H*D]
+        arg_b = (rg_w @ (wo @ bv + bo) + rg_b).float()
         w1 = torch.cat([e[0].weight for e in self.experts], 0)
         b1 = torch.cat([e[0].bias for e in self.experts], 0)
         w2 = torch.zeros(D, E * Ch + 64, device=w1.device, dtype=torch.float32)
@@ -285,9 +293,8 @@ class TempMoE(_QatModule):
             w2[:, E * Ch + i] = e[2].bias
         d = dict(
             attn_q=cabi.Lin(at.in_proj_weight[:D], at.in_proj_bias[:D], prec),
-            attn_kv=cabi.Lin(at.in_proj_weight[D:], at.in_proj_bias[D:], prec),
-            attn_out=cabi.Lin(at.out_proj.weight, at.out_proj.bias, prec),
-            router_gauss=cabi.Lin(rg_w, rg_b, cabi.PREC_FP32),
+            attn_kv=cabi.Lin(at.in_proj_weight[D:], at.in_proj_bias[D:], cabi.PREC_FP32),
+            attn_rg=cabi.Lin(arg_w, arg_b, cabi.PREC_FP32),
             w1_cat=cabi.Lin(w1, b1, prec),
             w2_ext=cabi.Lin(w2, None, prec))
         if self.vis_branch:
@@ -299,8 +306,7 @@ class TempMoE(_QatModule):
     def fill_weights(self, a, prec: int):
         w = self._prepared(prec)
         a.D, a.H, a.E, a.K, a.sigma = self.d_model, self.nhead, self.n_experts, self.topK, float(self.sigma)
-        a.attn_q, a.attn_kv, a.attn_out, a.router_gauss, a.w1_cat, a.w2_ext = (
-            w[k].c for k in ("attn_q", "attn_kv", "attn_out", "router_gauss", "w1_cat", "w2_ext"))
+        a.attn_q, a.attn_kv, a.attn_rg, a.w1_cat, a.w2_ext = (w[k].c for k in ("attn_q", "attn_kv", "attn_rg", "w1_cat", "w2_ext"))
         a.norm_a, a.norm_v = w["norm_a"].c, w["norm_v"].c
 
     def attach_aux(self, a, B: int, T: int, dev):
