@@ -11,7 +11,7 @@ from typing import Dict, Optional, Tuple
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libqat_b200.so")
+LIB_PATH = os.environ.get("QAT_LIB") or os.path.join(HERE, "csrc", "libqat_b200.so")   # QAT_LIB: A/B builds while profiling
 
 ABI_VERSION = 3
 PREC_FP32, PREC_BF16 = 0, 1
