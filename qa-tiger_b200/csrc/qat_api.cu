@@ -167,6 +167,7 @@ static int ln(Ctx& c, const float* x0, long long ld0, const float* x1, long long
 // P1  Projection
 // =================================================================================================
 static int linear_core(Ctx& c, const QatLinearW& w, Act X, long long rows, int relu, Act Y) {
+  StageRange nvtx_(c, "qat.projection");
   QAT_REQUIRE(rows >= 0 && w.n > 0 && w.k > 0, "linear: bad shape");
   QAT_TRY(check_w(w, w.n, w.k, "linear.w", c.prec));
   WView W = wview(w);
@@ -236,6 +237,7 @@ static int run_attention(const QatAttnArgs* a, Ctx& c) {
 // plane they point at (fp32 always; inside qat_forward_fwd also the planes the next blocks read)
 static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Act Xv, Act Xw, Act out_a, Act out_v, float* attw_audio,
                     float* attw_video) {
+  StageRange nvtx_(c, "qat.avq_cross_attn");
   const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && H >= 1 && D == H * 64, "avq: need D == H*64 (D=%d H=%d)", D, H);
   QAT_REQUIRE(T <= 128 && L <= 128, "avq: sequence lengths T=%d L=%d must be <= 128", T, L);
@@ -358,6 +360,7 @@ static int run_avq(const QatAvqArgs* a, Ctx& c) {
 // of the vt TempMoE (modules.py:587,597), whose only consumer they are
 static int patch_core(const QatPatchArgs* a, int B, int T, int P, Ctx& c, const float* patch, Act Xaud, Act Xvid, Act out_a, Act out_v,
                       const float* post = nullptr, long long ldp = 0) {
+  StageRange nvtx_(c, "qat.patch_selecter");
   const int D = a->D, H = a->H;
   const __half* patch_h = reinterpret_cast<const __half*>(a->patch_f16);
   QAT_REQUIRE(c.dry || patch || patch_h, "patch_select: patch tensor missing");
@@ -542,6 +545,7 @@ static int run_patch(const QatPatchArgs* a, Ctx& c) {
 // M2-M4 standalone
 // =================================================================================================
 static int run_gauss(const QatGaussArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.gauss_reduce");
   QAT_REQUIRE(a->experts && a->router_logits && a->gauss_raw && a->out, "gauss_reduce: NULL tensor");
   GaussP p;
   p.x = a->experts; p.st = a->stride_t; p.sb = a->stride_b;
@@ -586,6 +590,7 @@ struct MoeMod {
 // temp_w -> router | gauss_pred for up to two modules per launch sequence (moe_front.cuh), then the per-row coefficients of
 // the modules whose M4 runs in the GEMM epilogue
 static int moe_front(Ctx& c, MoeMod* mods, int n, int B, int T) {
+  StageRange nvtx_(c, "qat.temp_moe.front");
   QAT_REQUIRE(n >= 1 && n <= MF_MAX, "temp_moe: 1 or 2 modules per front end");
   const long long BT = (long long)B * T;
   MoeFrontP fp;
@@ -655,6 +660,7 @@ static int moe_front(Ctx& c, MoeMod* mods, int n, int B, int T) {
 
 // experts -> M4 -> second-layer contraction -> LayerNorm of one module (modules.py:585-612)
 static int moe_back(Ctx& c, MoeMod& M, int B, int T) {
+  StageRange nvtx_(c, "qat.temp_moe.experts");
   const QatMoeArgs* a = M.a;
   const int D = a->D, E = a->E, K = a->K;
   const int Ch = D / 2, KE = E * Ch + 64;
@@ -769,6 +775,7 @@ static int run_moe(const QatMoeArgs* a, Ctx& c) {
 // query projections of every block that attends from the question into one contraction)
 static int ground_core(const QatGroundArgs* a, int B, Ctx& c, const float* qst, const float* d0, const float* d1, float* out, bool with_head,
                        float* logits, const float* qpre = nullptr, int ldq = 0) {
+  StageRange nvtx_(c, "qat.qst_grounding");
   const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && D == H * 64, "qst_grounding: need D==H*64");
   QAT_TRY(check_w(a->attn_q, D, D, "ground.attn_q", c.prec));
@@ -839,6 +846,7 @@ static int run_ground(const QatGroundArgs* a, Ctx& c) {
 // with the storage planes their consumers read (no conversion passes at module boundaries, one launch sequence).
 // =================================================================================================
 static int run_forward(const QatForwardArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.forward");
   const int B = a->B, T = a->T, L = a->L, P = a->P, D = a->avq.D;
   QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && P >= 1, "forward: bad shape");
   QAT_REQUIRE(c.dry || (a->quest && a->words && a->audio && a->video && (a->patch || a->patch_sel.patch_f16) && a->logits), "forward: NULL tensor");
@@ -932,6 +940,7 @@ static int run_forward(const QatForwardArgs* a, Ctx& c) {
 // N1  CLIP text tower (frozen), encoders.py:30-37 / clip_base.py:186-254
 // =================================================================================================
 static int run_clip_text(const QatClipTextArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.clip_text");
   const int B = a->B, L = a->L, W = a->W, H = a->H, E = a->E;
   QAT_REQUIRE(B >= 1 && L >= 1 && L <= 128 && H >= 1 && W == H * 64 && E >= 1, "clip_text: need W == H*64 and L <= 128 (W=%d H=%d L=%d)", W, H, L);
   QAT_REQUIRE(a->n_layers >= 0 && (a->n_layers == 0 || a->layers), "clip_text: layer weights missing");
@@ -1015,6 +1024,7 @@ static int run_clip_text(const QatClipTextArgs* a, Ctx& c) {
 // T1-T3, T0
 // =================================================================================================
 static int run_tome_match(const QatTomeMatchArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.tome.match");
   const int r = tome_clamp_r(a->t, a->r, a->class_token);
   QAT_REQUIRE(r > 0, "tome_match: nothing to merge (r clamps to 0 for t=%d)", a->t);
   QAT_REQUIRE(a->metric && a->unm_idx && a->src_idx && a->dst_idx, "tome_match: NULL tensor");
@@ -1022,12 +1032,14 @@ static int run_tome_match(const QatTomeMatchArgs* a, Ctx& c) {
 }
 
 static int run_tome_merge(const QatTomeMergeArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.tome.merge");
   QAT_REQUIRE(a->x && a->unm_idx && a->src_idx && a->dst_idx && a->x_out, "tome_merge: NULL tensor");
   return tome_merge(c, a->x, a->size, a->N, a->t, a->C, a->r, a->mode, a->unm_idx, a->src_idx, a->dst_idx, a->x_out,
                     a->size_out, a->group, a->T0);
 }
 
 static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.tome.chain");
   const int N = a->N, C = a->C;
   QAT_REQUIRE(a->n_steps >= 0 && (a->n_steps == 0 || a->r_list), "tome_chain: r_list missing");
   QAT_REQUIRE(C % 64 == 0, "tome_chain: C=%d must be a multiple of 64 (stand-in metric)", C);

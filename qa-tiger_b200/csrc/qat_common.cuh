@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <atomic>
 #include <stdint.h>
 #include <stdio.h>
@@ -270,6 +271,20 @@ struct Ctx {
   }
   size_t mark() const { return off; }
   void release(size_t m) { off = m; }
+};
+
+// NVTX range per fused stage ("NVTX ranges per fused stage"): visible on an nsys / ncu --nvtx timeline, a no-op
+// without a tool attached (header-only nvtx3: the injection library is looked up once).  Not opened by the sizing dry run.
+struct StageRange {
+  bool on;
+  StageRange(const Ctx& c, const char* name) : on(!c.dry) {
+    if (on) nvtxRangePushA(name);
+  }
+  ~StageRange() {
+    if (on) nvtxRangePop();
+  }
+  StageRange(const StageRange&) = delete;
+  StageRange& operator=(const StageRange&) = delete;
 };
 
 inline int ctx_init(Ctx& c, void* stream, int prec, void* ws, size_t ws_bytes, bool dry) {
