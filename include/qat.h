@@ -138,6 +138,9 @@ typedef struct {
   int64_t o_rn, o_ri;
   int32_t ldo;
   float* attw;             /* F32 only: optional [nseq, Lq, Lk] head-averaged weights, zero-initialised by the caller */
+  const float* kbias;      /* F32 only, optional [k_mod, Lk]: added to every score of key j AFTER the scaling (ToMe's proportional
+                              attention, log(size): tome/patch/timm.py:94-95).  Sequences with Lk > 128 or a bias run on the
+                              long-sequence (online-softmax) core: no causal mask, no attw */
 } QatAttnArgs;
 int qat_attention_fwd(const QatAttnArgs* a);
 
@@ -374,6 +377,44 @@ typedef struct {
 } QatClipTextArgs;
 int qat_clip_text_fwd(const QatClipTextArgs* a);
 
+/* ---- N4: one ToMe-patched ViT block = ToMeBlock.forward, tome/patch/timm.py:35-65, with ToMeAttention.forward
+ *      :68-108 inside:  x += proj(softmax(q k^T * hd^-0.5 + log(size)) v)   (proportional attention :94-95; q, k, v = qkv(norm1 x))
+ *                       metric = k.mean(heads) :107  ->  bipartite_soft_matching(metric, r) -> merge_wavg (+ source group ids)
+ *                       x += fc2(GELU(fc1(norm2 x))).
+ *      So T1 runs on the REAL metric form, not the stand-in of qat_tome_chain.  Parameter names are timm's (norm1, attn.qkv,
+ *      attn.proj, norm2, mlp.fc1, mlp.fc2). ---- */
+typedef struct {
+  int32_t N, t, C, H;        /* frames, tokens per frame, width C = H*64, heads */
+  int32_t r;                 /* tokens to merge after the attention (clamped as merge.py:43-44); 0 = none */
+  int32_t class_token;       /* token 0 is the class token (protected) */
+  int32_t prop_attn;         /* 1: add log(size) to the scores (needs `size`; size = NULL means all ones: no bias) */
+  int32_t prec;
+  float eps;                 /* LayerNorm eps (timm ViT: 1e-6) */
+  void* stream;
+  const float* x;            /* [N,t,C] */
+  const float* size;         /* [N,t] token sizes, or NULL */
+  QatLayerNormW norm1, norm2;
+  QatLinearW qkv;            /* [3C, C] */
+  QatLinearW proj;           /* [C, C] */
+  QatLinearW fc1;            /* [4C, C] (any hidden width) */
+  QatLinearW fc2;            /* [C, 4C] */
+  float* x_out;              /* [N,t-r',C], r' = the clamped r (qat_tome_clamp_r) */
+  float* size_out;           /* [N,t-r'] */
+  float* metric;             /* optional [N,t,64] */
+  int32_t* unm_idx;          /* optional merge indices of this block, as qat_tome_match (all three or none) */
+  int32_t* src_idx;
+  int32_t* dst_idx;
+  int32_t* group;            /* optional in/out [N,T0]: merged-token position of every original token (merge_source :228-241) */
+  int32_t T0;
+  void* workspace;
+  size_t workspace_bytes;
+} QatTomeBlockArgs;
+int qat_tome_block_fwd(const QatTomeBlockArgs* a);
+/* ToMeAttention.forward alone (timm.py:75-108) on the same struct: x = norm1 output is NOT applied here -- `x` is the attention's
+ * input as the caller passes it (the reference calls attn(norm1(x), size)); x_out [N,t,C] = proj(attention) without residual,
+ * metric [N,t,64] = k.mean(heads) (required).  norm1 is applied iff norm1.gamma != NULL; r, norm2, fc1, fc2, size_out are ignored. */
+int qat_tome_attention_fwd(const QatTomeBlockArgs* a);
+
 /* ---- N3: batch assembly from a device-resident per-video feature cache.  dataset.py:132-159 loads the three
  *      feature files of a question's video per QUESTION and trainutils.py:223-236 copies every batch to the device; with the
  *      cache (qa_tiger_b200/datapipe.py) a video crosses the host link once and a batch is gathered in HBM:
@@ -395,7 +436,8 @@ int qat_gather_rows(const QatGatherArgs* a);
 
 /* ---- bookkeeping ---------------------------------------------------------------------------- */
 enum { QAT_OP_LINEAR = 0, QAT_OP_AVQ = 1, QAT_OP_PATCH = 2, QAT_OP_MOE = 3, QAT_OP_GROUND = 4,
-       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7, QAT_OP_CLIP_TEXT = 8, QAT_OP_FORWARD = 9 };
+       QAT_OP_TOME_MATCH = 5, QAT_OP_TOME_MERGE = 6, QAT_OP_TOME_CHAIN = 7, QAT_OP_CLIP_TEXT = 8, QAT_OP_FORWARD = 9,
+       QAT_OP_TOME_BLOCK = 10, QAT_OP_TOME_ATTENTION = 11 };
 /* Pass the same args struct the op will be called with (pointers may be NULL). */
 size_t qat_workspace_bytes(int op, const void* args);
 const char* qat_last_error(void);

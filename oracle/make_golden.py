@@ -209,9 +209,60 @@ def gen_tome():
     print("tome ok", k, "steps")
 
 
+def load_reference_tome_patch():
+    """The REAL tome/patch/timm.py, imported by file path with `timm.models.vision_transformer` stubbed (oracle/timm_stub.py:
+    timm is not installed here) and `src.tome` registered as a bare package (its __init__ pulls in PIL-based visualisation)."""
+    from oracle import timm_stub
+    timm_stub.install()
+    sys.path.insert(0, REF)
+    if "src.tome" not in sys.modules:
+        src = sys.modules.get("src") or types.ModuleType("src")
+        src.__path__ = [os.path.join(REF, "src")]
+        sys.modules["src"] = src
+        t = types.ModuleType("src.tome")
+        t.__path__ = [os.path.join(REF, "src", "tome")]
+        sys.modules["src.tome"] = t
+    spec = importlib.util.spec_from_file_location("ref_tome_timm", os.path.join(REF, "src/tome/patch/timm.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod, timm_stub
+
+
+def gen_tome_block():
+    """two ToMe-patched ViT-L blocks (dim 1024, 16 heads) of the real reference on 2 frames of 197 tokens, r = 25
+    each (the second block therefore sees size != 1: proportional attention), trace_source on; plus a 577-token single block."""
+    mod, stub = load_reference_tome_patch()
+    sd = synth.make_vit_blocks(717, 2)
+    d = {}
+    for nm, (N, t, rs) in {"b197": (2, 197, [25, 25]), "b577": (1, 577, [25])}.items():
+        blocks = []
+        info = {"r": list(rs), "size": None, "source": None, "trace_source": True, "prop_attn": True, "class_token": True, "distill_token": False}
+        for i in range(len(rs)):
+            b = stub.Block(1024, 16)
+            b.load_state_dict({k[len(f"blocks.{i}."):]: v for k, v in sd.items() if k.startswith(f"blocks.{i}.")})
+            b.__class__ = mod.ToMeBlock
+            b.attn.__class__ = mod.ToMeAttention
+            b._tome_info = info
+            blocks.append(b.eval())
+        g = torch.Generator().manual_seed(1000 + t)
+        x = torch.randn(N, t, 1024, generator=g)
+        d[f"{nm}.cfg"] = np.array([N, t, len(rs)] + list(rs))
+        with torch.no_grad():
+            for i, b in enumerate(blocks):
+                xa, metric = b.attn(b.norm1(x), info["size"])
+                d[f"{nm}.{i}.attn"], d[f"{nm}.{i}.metric"] = sub(xa), metric.numpy()
+                x = b(x)
+                d[f"{nm}.{i}.x"] = sub(x, 8192)
+                d[f"{nm}.{i}.size"] = info["size"].numpy()
+        d[f"{nm}.x_final"] = sub(x, 65536)
+        d[f"{nm}.group"] = info["source"].argmax(dim=1).numpy().astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "tome_block.npz"), **d)
+    print("tome_block", {k: v.shape for k, v in d.items() if k.endswith("x_final")})
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    which = sys.argv[1:] or list(FWD_CASES) + ["blocks", "tome"]
+    which = sys.argv[1:] or list(FWD_CASES) + ["blocks", "tome", "tome_block"]
     torch.set_num_threads(os.cpu_count())
     for w in which:
         if w in FWD_CASES:
@@ -220,5 +271,7 @@ if __name__ == "__main__":
             gen_blocks()
         elif w == "tome":
             gen_tome()
+        elif w == "tome_block":
+            gen_tome_block()
         else:
             raise SystemExit("unknown case " + w)

@@ -115,3 +115,19 @@ def make_batch(seed: int, B: int, T: int = 60, P: int = 14, audio_dim: int = 128
     out["label"] = torch.randint(0, 42, (B,), generator=g)
     out["qtype_label"] = torch.randint(0, 9, (B,), generator=g)
     return out
+
+
+def make_vit_blocks(seed: int = 717, n_blocks: int = 2, dim: int = 1024, hidden: int = 4096) -> Dict[str, torch.Tensor]:
+    """Seeded weights of `n_blocks` timm ViT blocks (names blocks.<i>.{norm1,attn.qkv,attn.proj,norm2,mlp.fc1,mlp.fc2}.*), for the
+    ToMe-patched block of SURVEY 8f-N4 (ViT-L/16: dim 1024, 16 heads, mlp 4096)."""
+    g = torch.Generator().manual_seed(seed)
+    sd: Dict[str, torch.Tensor] = {}
+    for i in range(n_blocks):
+        p = f"blocks.{i}"
+        _ln(sd, g, p + ".norm1", dim)
+        _lin(sd, g, p + ".attn.qkv", 3 * dim, dim, gain=1.0)
+        _lin(sd, g, p + ".attn.proj", dim, dim, gain=1.0)
+        _ln(sd, g, p + ".norm2", dim)
+        _lin(sd, g, p + ".mlp.fc1", hidden, dim)
+        _lin(sd, g, p + ".mlp.fc2", dim, hidden, gain=1.0)
+    return sd

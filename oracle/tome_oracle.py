@@ -137,3 +137,47 @@ def chain(x: Tensor, schedule: Optional[List[int]] = None, class_token: bool = T
     if size is None:
         size = torch.ones_like(x[..., 0, None])
     return x, size, group, steps
+
+
+# ---- the ToMe-patched ViT block (tome/patch/timm.py) ----------------------------------------------------------
+def tome_attention(sd, p: str, x: Tensor, size: Optional[Tensor], H: int):
+    """ToMeAttention.forward, timm.py:75-108: x is the attention input (norm1 already applied by the block).  Returns
+    (proj(attention) [N,t,C], metric = k.mean(heads) [N,t,C/H])."""
+    N, t, C = x.shape
+    hd = C // H
+    qkv = (x @ sd[p + ".qkv.weight"].t() + sd[p + ".qkv.bias"]).reshape(N, t, 3, H, hd).permute(2, 0, 3, 1, 4)   # :79-83
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * hd ** -0.5                                                              # :90
+    if size is not None:
+        attn = attn + size.log()[:, None, None, :, 0]                                                         # :94-95
+    attn = attn.softmax(dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(N, t, C)
+    o = o @ sd[p + ".proj.weight"].t() + sd[p + ".proj.bias"]                                                  # :100
+    return o, k.mean(1)                                                                                        # :107
+
+
+def _ln(x, w, b, eps):
+    mu = x.mean(-1, keepdim=True)
+    var = ((x - mu) ** 2).mean(-1, keepdim=True)
+    return (x - mu) / torch.sqrt(var + eps) * w + b
+
+
+def tome_block(sd, p: str, x: Tensor, size: Optional[Tensor], r: int, H: int, class_token: bool = True, prop_attn: bool = True,
+               eps: float = 1e-6, group: Optional[Tensor] = None):
+    """ToMeBlock.forward, timm.py:35-65.  `p` prefixes timm's block parameter names.  Returns
+    (x_out, size_out | None, metric, idx | None, group | None)."""
+    N, t, C = x.shape
+    xa, metric = tome_attention(sd, p + ".attn", _ln(x, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], eps), size if prop_attn else None, H)   # :39-40
+    x = x + xa                                                                                                 # :41
+    idx = None
+    if r > 0:
+        res = match(metric, r, class_token=class_token)                                                        # :48-53
+        if res is not None:
+            idx = res[:3]
+            if group is not None:
+                group = group_ids_update(group, t, idx)                                                        # :54-57 (as group ids)
+            x, size = merge_wavg(x, size, idx)                                                                 # :58
+    h = _ln(x, sd[p + ".norm2.weight"], sd[p + ".norm2.bias"], eps) @ sd[p + ".mlp.fc1.weight"].t() + sd[p + ".mlp.fc1.bias"]
+    h = torch.nn.functional.gelu(h)
+    x = x + (h @ sd[p + ".mlp.fc2.weight"].t() + sd[p + ".mlp.fc2.bias"])                                      # :62
+    return x, size, metric, idx, group

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("QAT_LIB") or os.path.join(HERE, "csrc", "libqat_b200.
 ABI_VERSION = 3
 PREC_FP32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
-OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT, OP_FORWARD = range(10)
+OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT, OP_FORWARD, OP_TOME_BLOCK, OP_TOME_ATTENTION = range(12)
 PREC_NAMES = {"fp32": PREC_FP32, "bf16": PREC_BF16}
 
 c_f32p = C.c_void_p  # all device pointers travel as void*
@@ -123,13 +123,23 @@ class TomeChainArgs(C.Structure):
                 ("idx_trace", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
+class TomeBlockArgs(C.Structure):
+    _fields_ = [("N", C.c_int32), ("t", C.c_int32), ("C", C.c_int32), ("H", C.c_int32), ("r", C.c_int32), ("class_token", C.c_int32),
+                ("prop_attn", C.c_int32), ("prec", C.c_int32), ("eps", C.c_float), ("stream", C.c_void_p),
+                ("x", C.c_void_p), ("size", C.c_void_p), ("norm1", LayerNormW), ("norm2", LayerNormW),
+                ("qkv", LinearW), ("proj", LinearW), ("fc1", LinearW), ("fc2", LinearW),
+                ("x_out", C.c_void_p), ("size_out", C.c_void_p), ("metric", C.c_void_p),
+                ("unm_idx", C.c_void_p), ("src_idx", C.c_void_p), ("dst_idx", C.c_void_p), ("group", C.c_void_p), ("T0", C.c_int32),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 class AttnArgs(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nseq", C.c_int32), ("H", C.c_int32), ("Lq", C.c_int32), ("Lk", C.c_int32),
                 ("scale", C.c_float), ("causal", C.c_int32), ("stream", C.c_void_p),
                 ("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p),
                 ("q_sn", C.c_int64), ("q_si", C.c_int64), ("k_sn", C.c_int64), ("k_si", C.c_int64),
                 ("k_shift", C.c_int32), ("k_mod", C.c_int32), ("o", C.c_void_p), ("o_f16", C.c_void_p),
-                ("o_rn", C.c_int64), ("o_ri", C.c_int64), ("ldo", C.c_int32), ("attw", C.c_void_p)]
+                ("o_rn", C.c_int64), ("o_ri", C.c_int64), ("ldo", C.c_int32), ("attw", C.c_void_p), ("kbias", C.c_void_p)]
 
 
 class ClipLayerW(C.Structure):
@@ -176,6 +186,8 @@ EXPORTS = {
     "qat_abi_version": (C.c_int, []),
     "qat_launch_count": (C.c_longlong, [C.c_int]),
     "qat_gather_rows": (C.c_int, [C.POINTER(GatherArgs)]),
+    "qat_tome_block_fwd": (C.c_int, [C.POINTER(TomeBlockArgs)]),
+    "qat_tome_attention_fwd": (C.c_int, [C.POINTER(TomeBlockArgs)]),
     "qat_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "qat_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
 }
@@ -362,7 +374,8 @@ def gemm_reduce(a: torch.Tensor, lin: "Lin", coef: torch.Tensor, T: int, Ch: int
     return c
 
 
-def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False, need_weights: bool = False):
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False, need_weights: bool = False,
+              key_bias: Optional[torch.Tensor] = None):
     """softmax(q k^T / 8) v on the library's attention cores (parity tests / roofline timing).
     fp32: q [N,Lq,H,64], k, v [N,Lk,H,64] (contiguous) -> o [N,Lq,H*64] (+ head-averaged weights [N,Lq,Lk]).
     fp16: q [N,Lq,H,64], k and v are the halves of ONE packed tensor kv [N,Lk,2,H,64] (pass kv as `k`, v=None) -> fp16 o."""
@@ -383,6 +396,9 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
     a.kind, a.Lk, a.q, a.k, a.v = 0, Lk, q.data_ptr(), k.data_ptr(), v.data_ptr()
     a.q_sn, a.q_si, a.k_sn, a.k_si, a.k_shift, a.k_mod = Lq * H * 64, H * 64, Lk * H * 64, H * 64, 0, N
     a.o, a.o_rn, a.o_ri, a.ldo, a.attw = o.data_ptr(), Lq, 1, H * 64, ptr(w)
+    if key_bias is not None:
+        require_cuda_f32(key_bias, "key_bias", (N, Lk))
+        a.kbias = key_bias.data_ptr()
     with torch.cuda.device(q.device):
         check(lib().qat_attention_fwd(C.byref(a)), "qat_attention_fwd")
     return (o, w) if need_weights else o

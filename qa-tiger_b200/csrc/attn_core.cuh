@@ -32,6 +32,9 @@ struct AttnP {
   const __half* kl = nullptr;
   const __half* vh = nullptr;
   const __half* vl = nullptr;
+  // optional additive per-key bias [n_kv_sequences, Lk] (ToMe's proportional attention: log(size), timm.py:94-95); long-sequence
+  // core only (attn_long.cuh)
+  const float* kbias = nullptr;
 };
 
 constexpr int HD = 64;

@@ -8,7 +8,7 @@ namespace qat {
 
 struct Epi {
   const float* bias = nullptr;  // [N]
-  int relu = 0;                 // 0 none, 1 ReLU, 2 QuickGELU x*sigmoid(1.702 x) (clip_base.py:162-164)
+  int relu = 0;                 // 0 none, 1 ReLU, 2 QuickGELU x*sigmoid(1.702 x) (clip_base.py:162-164), 3 exact GELU
   const float* res = nullptr;   // [M, ldr] added after the activation
   int ldr = 0;
   const __half* res_h = nullptr;  // the same residual as an fp16 plane (tensor-core GEMMs only; res wins if both are set)
@@ -24,6 +24,7 @@ struct Epi {
 __device__ __forceinline__ float epi_act(float x, int mode) {
   if (mode == 1) return fmaxf(x, 0.f);
   if (mode == 2) return x / (1.f + expf(-1.702f * x));
+  if (mode == 3) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));   // nn.GELU() (timm Mlp of the ToMe-patched ViT block)
   return x;
 }
 

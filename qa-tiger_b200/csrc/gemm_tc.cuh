@@ -580,9 +580,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         if (p.epi.relu == 1) {
 #pragma unroll
           for (int e = 0; e < 32; ++e) x[e] = fmaxf(x[e], 0.f);
-        } else if (p.epi.relu == 2) {
+        } else if (p.epi.relu != 0) {
 #pragma unroll
-          for (int e = 0; e < 32; ++e) x[e] = epi_act(x[e], 2);
+          for (int e = 0; e < 32; ++e) x[e] = epi_act(x[e], p.epi.relu);
         }
         if (p.tma_res) {
           mbar_wait(&rbar[ew], nres & 1);

@@ -3,6 +3,7 @@
 // No allocation, no synchronisation, no global mutable state.
 #include "attn_core.cuh"
 #include "attn_f16.cuh"
+#include "attn_long.cuh"
 #include "datapipe.cuh"
 #include "gauss.cuh"
 #include "gemm_simt.cuh"
@@ -154,11 +155,11 @@ static int planes_of(Ctx& c, const float* x, long long rows, int cols, bool want
 }
 
 static int ln(Ctx& c, const float* x0, long long ld0, const float* x1, long long ld1, const float* x2, long long ld2, float c01,
-              const QatLayerNormW& w, Act out, long long rows, int D, const float* post = nullptr, long long ldp = 0) {
+              const QatLayerNormW& w, Act out, long long rows, int D, const float* post = nullptr, long long ldp = 0, float eps = 1e-5f) {
   QAT_REQUIRE(w.gamma && w.beta, "layer_norm: affine parameters missing");
   LnP p;
   p.x0 = x0; p.ld0 = ld0; p.x1 = x1; p.ld1 = ld1; p.x2 = x2; p.ld2 = ld2;
-  p.c01 = c01; p.gamma = w.gamma; p.beta = w.beta; p.out = out; p.rows = rows; p.D = D; p.eps = 1e-5f;
+  p.c01 = c01; p.gamma = w.gamma; p.beta = w.beta; p.out = out; p.rows = rows; p.D = D; p.eps = eps;
   p.post = post; p.ldp = ldp;
   return layer_norm(c, p);
 }
@@ -222,12 +223,14 @@ static int run_attention(const QatAttnArgs* a, Ctx& c) {
   QAT_REQUIRE(a->kind == QAT_ATTN_F32, "attention: unknown kind %d", a->kind);
   QAT_REQUIRE(a->q && a->k && a->v && a->o && a->k_mod >= 1, "attention: NULL tensor or k_mod < 1");
   QAT_REQUIRE(!a->causal || a->Lk > 32 || a->Lq >= 32, "attention: the causal core serves Lk > 32 or Lq >= 32");
+  const bool long_core = a->Lk > 128 || a->kbias != nullptr;
   AttnP p;
   p.q = reinterpret_cast<const float*>(a->q); p.k = reinterpret_cast<const float*>(a->k); p.v = reinterpret_cast<const float*>(a->v);
   p.q_sn = a->q_sn; p.q_si = a->q_si; p.k_sn = a->k_sn; p.k_si = a->k_si; p.k_shift = a->k_shift; p.k_mod = a->k_mod;
   p.o = act_of(a->o, a->ldo); p.o_rn = a->o_rn; p.o_ri = a->o_ri; p.attw = a->attw;
   p.nseq = a->nseq; p.H = a->H; p.Lq = a->Lq; p.Lk = a->Lk; p.scale = a->scale; p.causal = a->causal;
-  return attention(c, p);
+  p.kbias = a->kbias;
+  return long_core ? attention_long(c, p) : attention(c, p);
 }
 
 // =================================================================================================
@@ -1109,6 +1112,128 @@ static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
   return QAT_OK;
 }
 
+// =================================================================================================
+// N4  one ToMe-patched ViT block (tome/patch/timm.py:35-108)
+// =================================================================================================
+__global__ void __launch_bounds__(256) log_rows_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = logf(x[i]);
+}
+
+// attn_only: ToMeAttention.forward alone (timm.py:75-108): x_out [N,t,C] = proj(attention), no residual; metric is required
+static int tome_block_core(const QatTomeBlockArgs* a, Ctx& c, bool attn_only) {
+  StageRange nvtx_(c, attn_only ? "qat.tome.attention" : "qat.tome.block");
+  const int N = a->N, t = a->t, C = a->C, H = a->H;
+  QAT_REQUIRE(N >= 1 && t >= 1 && H >= 1 && C == H * 64, "tome_block: need C == H*64 (C=%d H=%d)", C, H);
+  QAT_REQUIRE(c.dry || (a->x && a->x_out && (attn_only ? a->metric != nullptr : a->size_out != nullptr)), "tome_block: NULL tensor");
+  QAT_REQUIRE((a->unm_idx != nullptr) == (a->src_idx != nullptr) && (a->unm_idx != nullptr) == (a->dst_idx != nullptr),
+              "tome_block: pass all three index outputs or none");
+  QAT_TRY(check_w(a->qkv, 3 * C, C, "tome_block.qkv", c.prec));
+  QAT_TRY(check_w(a->proj, C, C, "tome_block.proj", c.prec));
+  QAT_REQUIRE(attn_only || (a->fc1.w && a->fc2.w && a->fc1.k == C && a->fc2.n == C && a->fc2.k == a->fc1.n),
+              "tome_block: mlp weights do not chain (fc1 [%d,%d], fc2 [%d,%d])", a->fc1.n, a->fc1.k, a->fc2.n, a->fc2.k);
+  const int r = (a->r > 0 && !attn_only) ? tome_clamp_r(t, a->r, a->class_token) : 0;
+  const long long rows = (long long)N * t, rows2 = (long long)N * (t - r);
+  const int Ch = a->fc1.n;
+  const float eps = a->eps > 0.f ? a->eps : 1e-6f;
+  const WView Wqkv = wview(a->qkv), Wp = wview(a->proj), W1 = wview(a->fc1), W2 = wview(a->fc2);
+  const GemmKind k_qkv = pick_kind(c, rows, 3 * C, C, false, Wqkv), k_p = pick_kind(c, rows, C, C, false, Wp);
+  const GemmKind k_1 = attn_only ? G_SIMT : pick_kind(c, rows2, Ch, C, false, W1), k_2 = attn_only ? G_SIMT : pick_kind(c, rows2, C, Ch, false, W2);
+  Act Y, QKV, O, X1, X2, Y2, Hh;
+  // x_attn, metric = attn(norm1(x), size)   (:40)
+  if (a->norm1.gamma || !attn_only) {
+    QAT_TRY(act_alloc_for(c, Y, rows, C, k_qkv));
+    QAT_TRY(ln(c, a->x, C, nullptr, 0, nullptr, 0, 1.f, a->norm1, Y, rows, C, nullptr, 0, eps));
+  } else {
+    Y = act_of(a->x, C);                       // ToMeAttention.forward gets norm1(x) from its caller
+    QAT_TRY(ensure_operand(c, Y, rows, C, k_qkv));
+  }
+  QAT_TRY(act_alloc(c, QKV, rows, 3 * C, true, false));
+  QAT_TRY(gemm(c, k_qkv, Y, rows, Wqkv, Epi(), QKV));
+  float* ls = nullptr;
+  if (a->prop_attn && a->size) {
+    ls = reinterpret_cast<float*>(c.alloc((size_t)rows * 4));
+    if (!c.dry && !ls) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+    if (!c.dry) {
+      log_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c.stream>>>(a->size, ls, rows);
+      QAT_TRY(check_launch("log_rows_kernel"));
+    }
+  }
+  QAT_TRY(act_alloc_for(c, O, rows, C, k_p));
+  {
+    AttnP p;
+    p.q = QKV.f; p.k = QKV.f + C; p.v = QKV.f + 2 * C;
+    p.q_sn = (long long)t * 3 * C; p.q_si = 3 * C; p.k_sn = p.q_sn; p.k_si = 3 * C; p.k_shift = 0; p.k_mod = N;
+    p.o = O; p.o_rn = t; p.o_ri = 1; p.attw = nullptr; p.kbias = ls;
+    p.nseq = N; p.H = H; p.Lq = t; p.Lk = t; p.scale = 0.125f; p.causal = 0;
+    QAT_TRY(attention_long(c, p));
+  }
+  // x = x + proj(x_attn)   (:41)
+  if (attn_only) {
+    QAT_TRY(gemm(c, k_p, O, rows, Wp, Epi(), act_of(a->x_out, C)));
+    return tome_metric(c, QKV.f + C, a->metric, rows, C, 3 * C);
+  }
+  QAT_TRY(act_alloc(c, X1, rows, C, true, false));
+  {
+    Epi e;
+    e.res = a->x; e.ldr = C;
+    QAT_TRY(gemm(c, k_p, O, rows, Wp, e, X1));
+  }
+  // metric = k.mean(heads)   (:107)
+  float* metric = a->metric;
+  if (!metric) {
+    metric = reinterpret_cast<float*>(c.alloc((size_t)rows * 64 * 4));
+    if (!c.dry && !metric) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+  }
+  QAT_TRY(tome_metric(c, QKV.f + C, metric, rows, C, 3 * C));
+  // merge (:45-58)
+  if (r > 0) {
+    const int ta = (t + 1) / 2, n_unm = ta - r;
+    int* unm = a->unm_idx;
+    int* src = a->src_idx;
+    int* dst = a->dst_idx;
+    if (!unm) {
+      unm = reinterpret_cast<int*>(c.alloc((size_t)N * (n_unm + 2 * r) * 4));
+      if (!c.dry && !unm) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
+      src = unm + (size_t)N * n_unm;
+      dst = src + (size_t)N * r;
+    }
+    QAT_TRY(tome_match(c, metric, N, t, 64, r, a->class_token, unm, src, dst));
+    QAT_TRY(act_alloc(c, X2, rows2, C, true, false));
+    if (tome_merge_wavg_supported(C)) {
+      QAT_TRY(tome_merge_wavg(c, X1.f, a->size, N, t, C, r, unm, src, dst, X2.f, a->size_out, nullptr, a->group, a->T0));
+    } else {
+      QAT_TRY(tome_merge(c, X1.f, a->size, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, X2.f, a->size_out, a->group, a->T0));
+    }
+  } else {
+    X2 = X1;
+    if (!c.dry) {
+      if (a->size) {
+        QAT_CUDA(cudaMemcpyAsync(a->size_out, a->size, (size_t)rows * 4, cudaMemcpyDeviceToDevice, c.stream));
+      } else {
+        ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c.stream>>>(a->size_out, rows);
+        QAT_TRY(check_launch("ones_kernel"));
+      }
+    }
+  }
+  // x = x + mlp(norm2(x))   (:62)
+  QAT_TRY(act_alloc_for(c, Y2, rows2, C, k_1));
+  QAT_TRY(ln(c, X2.f, C, nullptr, 0, nullptr, 0, 1.f, a->norm2, Y2, rows2, C, nullptr, 0, eps));
+  QAT_TRY(act_alloc_for(c, Hh, rows2, Ch, k_2));
+  {
+    Epi e;
+    e.relu = 3;
+    QAT_TRY(gemm(c, k_1, Y2, rows2, W1, e, Hh));
+    Epi e2;
+    e2.res = X2.f; e2.ldr = C;
+    QAT_TRY(gemm(c, k_2, Hh, rows2, W2, e2, act_of(a->x_out, C)));
+  }
+  return QAT_OK;
+}
+
+static int run_tome_block(const QatTomeBlockArgs* a, Ctx& c) { return tome_block_core(a, c, false); }
+static int run_tome_attention(const QatTomeBlockArgs* a, Ctx& c) { return tome_block_core(a, c, true); }
+
 template <typename Args, typename Fn>
 static int dispatch(const Args* a, void* stream, int prec, void* ws, size_t wsb, Fn fn) {
   if (!a) QAT_FAIL(QAT_EINVAL, "args is NULL");
@@ -1152,6 +1277,10 @@ int qat_clip_text_fwd(const QatClipTextArgs* a) { return dispatch(a, a ? a->stre
 
 int qat_forward_fwd(const QatForwardArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_forward); }
 
+int qat_tome_block_fwd(const QatTomeBlockArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_block); }
+
+int qat_tome_attention_fwd(const QatTomeBlockArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_tome_attention); }
+
 int qat_gather_rows(const QatGatherArgs* a) {
   return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, [](const QatGatherArgs* g, Ctx& c) { return gather_rows(c, g); });
 }
@@ -1189,6 +1318,8 @@ size_t qat_workspace_bytes(int op, const void* args) {
     case QAT_OP_TOME_MATCH: return 256;
     case QAT_OP_TOME_MERGE: return 256;
     case QAT_OP_TOME_CHAIN: return dry_bytes(reinterpret_cast<const QatTomeChainArgs*>(args), QAT_PREC_FP32, run_tome_chain);
+    case QAT_OP_TOME_ATTENTION: return dry_bytes(reinterpret_cast<const QatTomeBlockArgs*>(args), reinterpret_cast<const QatTomeBlockArgs*>(args)->prec, run_tome_attention);
+    case QAT_OP_TOME_BLOCK: return dry_bytes(reinterpret_cast<const QatTomeBlockArgs*>(args), reinterpret_cast<const QatTomeBlockArgs*>(args)->prec, run_tome_block);
     default: return 0;
   }
 }

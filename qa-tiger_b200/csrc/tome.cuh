@@ -510,13 +510,15 @@ __global__ void __launch_bounds__(256) tome_merge_wavg_kernel(const float* __res
 }
 
 // ---- stand-in metric: mean over the C/64 channel groups --------------------
-__global__ void __launch_bounds__(256) tome_metric_kernel(const float* __restrict__ x, float* __restrict__ metric, long long tokens, int C) {
+// With ldx = 3C and x pointing at the K third of a packed [tokens, 3C] qkv projection this is the REAL metric of the ToMe-patched
+// ViT, k.mean(heads) (timm.py:107): torch sums the heads left to right and divides by their number, exactly as below.
+__global__ void __launch_bounds__(256) tome_metric_kernel(const float* __restrict__ x, long long ldx, float* __restrict__ metric, long long tokens, int C) {
   const int G = C / 64;
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one float4 of one token's 64-vector
   if (i >= tokens * 16) return;
   const long long tok = i >> 4;
   const int c4 = (int)(i & 15);
-  const float4* xr = reinterpret_cast<const float4*>(x + tok * C) + c4;
+  const float4* xr = reinterpret_cast<const float4*>(x + tok * ldx) + c4;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int g = 0; g < G; ++g) {
     float4 v = __ldg(xr + g * 16);
@@ -609,11 +611,11 @@ inline int tome_merge_wavg(Ctx& c, const float* x, const float* size, int N, int
   return check_launch("tome_merge_wavg_kernel");
 }
 
-inline int tome_metric(Ctx& c, const float* x, float* metric, long long tokens, int C) {
-  QAT_REQUIRE(C % 64 == 0, "tome_metric: C=%d must be a multiple of 64", C);
+inline int tome_metric(Ctx& c, const float* x, float* metric, long long tokens, int C, long long ldx = 0) {
+  QAT_REQUIRE(C % 64 == 0 && ldx % 4 == 0, "tome_metric: C=%d must be a multiple of 64 (and the row pitch of 4)", C);
   if (c.dry || tokens == 0) return QAT_OK;
   long long th = tokens * 16;
-  tome_metric_kernel<<<(unsigned)((th + 255) / 256), 256, 0, c.stream>>>(x, metric, tokens, C);
+  tome_metric_kernel<<<(unsigned)((th + 255) / 256), 256, 0, c.stream>>>(x, ldx ? ldx : C, metric, tokens, C);
   return check_launch("tome_metric_kernel");
 }
 

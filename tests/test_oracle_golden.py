@@ -104,3 +104,26 @@ def test_tome_single_steps(nm):
         xo, so = TO.merge_wavg(x, None, res[:3], fast=fast)
         assert relerr(xo, g[nm + ".xo"]) < 1e-6
         assert torch.equal(so, torch.as_tensor(g[nm + ".so"]))
+
+
+@pytest.mark.parametrize("nm", ["b197", "b577"])
+def test_tome_vit_block_matches_reference(nm):
+    """the oracle's ToMeAttention / ToMeBlock restatement against the real tome/patch/timm.py (goldens minted with
+    timm stubbed, oracle/make_golden.py `tome_block`): attention output, metric = k.mean(heads), sizes, group ids, block output."""
+    g = np.load(os.path.join(GOLDEN, "tome_block.npz"))
+    N, t, nb = (int(v) for v in g[f"{nm}.cfg"][:3])
+    rs = [int(v) for v in g[f"{nm}.cfg"][3:]]
+    sd = synth.make_vit_blocks(717, 2)
+    x = torch.randn(N, t, 1024, generator=torch.Generator().manual_seed(1000 + t))
+    size, group = None, torch.arange(t)[None, :].expand(N, t).contiguous()
+    with torch.no_grad():
+        for i in range(nb):
+            p = f"blocks.{i}"
+            xa, metric = TO.tome_attention(sd, p + ".attn", TO._ln(x, sd[p + ".norm1.weight"], sd[p + ".norm1.bias"], 1e-6), size, 16)
+            assert relerr(sub(xa), g[f"{nm}.{i}.attn"]) < 2e-5
+            assert relerr(metric, g[f"{nm}.{i}.metric"]) < 1e-5
+            x, size, metric2, idx, group = TO.tome_block(sd, p, x, size, rs[i], 16, group=group)
+            assert relerr(sub(x, 8192), g[f"{nm}.{i}.x"]) < 2e-5
+            assert torch.equal(size, torch.as_tensor(g[f"{nm}.{i}.size"]))
+    assert relerr(sub(x, 65536), g[f"{nm}.x_final"]) < 2e-5
+    assert group.tolist() == g[f"{nm}.group"].astype(np.int64).tolist()
