@@ -33,7 +33,7 @@ def parse_r(num_layers: int, r: Union[List[int], Tuple[int, float], int]) -> Lis
         r, inflect = r
     min_val = int(r * (1.0 - inflect))
     max_val = 2 * r - min_val
-    step = (max_val - min_val) / (num_layers - 1)
+    step = (max_val - min_val) / max(num_layers - 1, 1)        # (the reference divides by zero for a single layer)
     return [int(min_val + step * i) for i in range(num_layers)]
 
 
