@@ -43,12 +43,18 @@ constexpr int GA_QKV_ROWS = 126;                       // rows of the tile kept 
 // drain -> barrier -> attention -> barrier epilogue it ran at 3.1 us per tile, with this one at 2.8 us -- an N = 128 tile moves
 // 256 KB of operands per 16.8 MFLOP (ncu: 14 TB/s of L2 -> SM traffic, tensor pipe 55 % active), so operand delivery is next.
 // Shared memory: STAGES x (A 16 KB + 8 KB per W box) + two [126][BN + 8] fp16 tiles.
-template <bool CROSS>
+// CG = 2: CTA pairs (cluster of two CTAs on one TPC, tcgen05.mma.cta_group::2, M = 256): the pair owns TWO row tiles of one head;
+// each CTA stages its own 128 A rows and HALF of the head's weight rows, the leader issues one MMA over both shared memories and
+// both TMEMs, and every CTA ends up with the accumulator of ITS row tile x all BN columns -- the drain / attention half of the
+// kernel is unchanged, while the weight traffic through L2 and shared memory halves (ncu on the single-CTA form: 12.5 - 14 TB/s
+// of L2 -> SM traffic, of which 60 % weight rows re-read by every row tile; tensor pipe 55 - 58 %).
+template <bool CROSS, int CG = 1>
 struct GxCfg {
-  static constexpr int NW = CROSS ? 2 : 3;                 // W boxes of 64 rows per stage: (q,) k, v of the head
+  static constexpr int NW = CROSS ? 2 : 3;                 // 64-row blocks of the head's weights: (q,) k, v
   static constexpr int BN = 64 * NW;
-  static constexpr int STAGES = CROSS ? 4 : 3;
-  static constexpr int STAGE_BYTES = GA_A_BYTES + NW * 8192;
+  static constexpr int WP = BN / 32 / CG;                  // 32-row weight pieces this CTA stages per k-block
+  static constexpr int STAGES = CG == 2 ? (CROSS ? 5 : 4) : (CROSS ? 4 : 3);
+  static constexpr int STAGE_BYTES = GA_A_BYTES + WP * 4096;
   static constexpr int STRIDE = (BN + 8) * 2;              // bytes per tile row: conflict-free ldmatrix / 16-byte stores
   static constexpr int TILE_BYTES = ((GA_QKV_ROWS * STRIDE + 1023) / 1024) * 1024;
   static constexpr int ACC_COLS = CROSS ? 128 : 256;       // TMEM columns per accumulator (two of them)
@@ -57,10 +63,10 @@ struct GxCfg {
   static_assert(SMEM <= 232448, "gemm_attn_pipe: shared-memory budget");
 };
 
-template <bool CROSS>
+template <bool CROSS, int CG>
 __global__ void __launch_bounds__(384, 1)
 gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_constant__ CUtensorMap mW, GemmAttnP p) {
-  typedef GxCfg<CROSS> G;
+  typedef GxCfg<CROSS, CG> G;
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   unsigned char* tiles = smem;
@@ -77,8 +83,10 @@ gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
   const int P = p.P, H = p.H, D = H * 64;
   const int FPT = 128 / P, RPT = FPT * P;                                 // frames / rows per tile
   const int nkb = p.K / 64;
-  const int tiles_m = (p.nframes + FPT - 1) / FPT;
+  const int tiles_m = ((p.nframes + FPT - 1) / FPT + CG - 1) / CG;         // (pairs of) row tiles; a tail pair may be half empty
   const int ntiles = tiles_m * H;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / CG, nunits = gridDim.x / CG;             // persistent walk, one unit = one CTA (pair)
   constexpr int KOFF = CROSS ? 0 : 64, VOFF = KOFF + 64;                  // tile columns of k and v (q: [0,64) in the self form)
 
   if (warp == 0 && lane == 0) {
@@ -90,7 +98,7 @@ gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], 4);          // the four drain warps
+      mbar_init(&tempty[a], 4 * CG);     // the four drain warps (of both CTAs of a pair)
       mbar_init(&kvfull[a], 4);          // the four drain warps
       mbar_init(&kvempty[a], 6);         // the six attention warps
     }
@@ -98,62 +106,91 @@ gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * G::ACC_COLS) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 2) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * G::ACC_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * G::ACC_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // the peer's barriers are initialised before anything signals them
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-      const int m0 = (t / H) * RPT, h = t % H;
+    for (int t = unit0; t < ntiles; t += nunits) {
+      const int m0 = ((t / H) * CG + (int)crank) * RPT, h = t % H;
       for (int kb = 0; kb < nkb; ++kb, ++it) {
         const int s = it % G::STAGES;
         mbar_wait(&empty[s], ((it / G::STAGES) & 1) ^ 1);
         unsigned char* st = tiles + s * G::STAGE_BYTES;
         const int k0 = kb * 64;
-        if (elect_one()) {
+        // weight pieces of 32 rows: piece pi of the head's [BN, K] block = rows (pi / 2) * D + h * 64 + (pi % 2) * 32 of W
+        // ((q,) k, v blocks are D rows apart); a CTA of a pair stages the pieces of its half of the BN columns
+        if (CG == 2) {
+          const uint32_t fb = mapa_rank(smem_u32(&full[s]), 0);           // both CTAs' bytes are counted on the leader's barrier
+          if (elect_one()) {
+            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * G::STAGE_BYTES);
+            tma_load_2d_pair(st, &mA, fb, k0, m0);
+#pragma unroll
+            for (int w = 0; w < G::WP; ++w) {
+              const int pi = (int)crank * G::WP + w;
+              tma_load_2d_pair(st + GA_A_BYTES + w * 4096, &mW, fb, k0, (pi >> 1) * D + h * 64 + (pi & 1) * 32);
+            }
+          }
+        } else if (elect_one()) {
           mbar_arrive_expect_tx(&full[s], G::STAGE_BYTES);
           tma_load_2d(st, &mA, &full[s], k0, m0);
 #pragma unroll
-          for (int w = 0; w < G::NW; ++w) tma_load_2d(st + GA_A_BYTES + w * 8192, &mW, &full[s], k0, w * D + h * 64);
+          for (int w = 0; w < G::WP; ++w) tma_load_2d(st + GA_A_BYTES + w * 4096, &mW, &full[s], k0, (w >> 1) * D + h * 64 + (w & 1) * 32);
         }
         __syncwarp();
       }
     }
   } else if (warp == 1) {
-    constexpr uint32_t idesc = umma_idesc(0, 128, G::BN);
-    uint32_t it = 0, lt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-      const uint32_t as = lt & 1;
-      mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tacc = tmem_base + as * G::ACC_COLS;
-      for (int kb = 0; kb < nkb; ++kb, ++it) {
-        const int s = it % G::STAGES;
-        mbar_wait(&full[s], (it / G::STAGES) & 1);
+    if (crank == 0) {                                                     // the leader issues for the pair
+      constexpr uint32_t idesc = umma_idesc(0, 128 * CG, G::BN);
+      uint32_t it = 0, lt = 0;
+      for (int t = unit0; t < ntiles; t += nunits, ++lt) {
+        const uint32_t as = lt & 1;
+        if (CG == 2) mbar_wait_cluster(&tempty[as], ((lt >> 1) & 1) ^ 1);
+        else mbar_wait(&tempty[as], ((lt >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = smem_u32(tiles + s * G::STAGE_BYTES);
-        const uint64_t dA = umma_desc(a0), dW = umma_desc(a0 + GA_A_BYTES);
-        if (elect_one()) {
+        const uint32_t tacc = tmem_base + as * G::ACC_COLS;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % G::STAGES;
+          mbar_wait(&full[s], (it / G::STAGES) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a0 = smem_u32(tiles + s * G::STAGE_BYTES);
+          const uint64_t dA = umma_desc(a0), dW = umma_desc(a0 + GA_A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) umma<KIND_F16>(tacc, dA + uint64_t(k * 2), dW + uint64_t(k * 2), idesc, (kb | k) != 0);
-          umma_commit(&empty[s]);
+            for (int k = 0; k < 4; ++k) umma<KIND_F16, CG>(tacc, dA + uint64_t(k * 2), dW + uint64_t(k * 2), idesc, (kb | k) != 0);
+            if (CG == 2) umma_commit_pair(&empty[s]);
+            else umma_commit(&empty[s]);
+          }
+          __syncwarp();
+        }
+        if (elect_one()) {
+          if (CG == 2) umma_commit_pair(&tfull[as]);
+          else umma_commit(&tfull[as]);
         }
         __syncwarp();
       }
-      if (elect_one()) umma_commit(&tfull[as]);
-      __syncwarp();
     }
   } else if (warp < 6) {
     // ===================== drain warps 2..5: accumulator -> (+bias) -> fp16 [126][(q |) k | v] tile =====================
     const int lg = warp & 3;
     const int row = lg * 32 + lane;
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
+    // accumulator hand-back: the leader's barrier (a remote arrival from the peer CTA)
+    const uint32_t tempty_a0 = CG == 2 ? mapa_rank(smem_u32(&tempty[0]), 0) : smem_u32(&tempty[0]);
+    const uint32_t tempty_a1 = CG == 2 ? mapa_rank(smem_u32(&tempty[1]), 0) : smem_u32(&tempty[1]);
+    for (int t = unit0; t < ntiles; t += nunits, ++lt) {
       const int h = t % H;
       const uint32_t as = lt & 1, ph = (lt >> 1) & 1;
       mbar_wait(&tfull[as], ph);
@@ -173,7 +210,10 @@ gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (c == G::BN / 32 - 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-          if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[as])) : "memory");
+          if (lane == 0) {
+            if (CG == 2) mbar_arrive_cluster(as ? tempty_a1 : tempty_a0);
+            else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(as ? tempty_a1 : tempty_a0) : "memory");
+          }
         }
 #pragma unroll
         for (uint32_t q = 0; q < 4; ++q) {
@@ -195,8 +235,8 @@ gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
     const int aw = warp - 6;
     const int g = lane >> 2, tq = lane & 3, m8 = lane >> 3, r8 = lane & 7;
     uint32_t lt = 0;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++lt) {
-      const int mt = t / H, h = t % H;
+    for (int t = unit0; t < ntiles; t += nunits, ++lt) {
+      const int mt = (t / H) * CG + (int)crank, h = t % H;
       const uint32_t as = lt & 1, ph = (lt >> 1) & 1;
       const uint32_t st = smem_u32(sT + as * G::TILE_BYTES);
       bool waited = false;
@@ -310,10 +350,39 @@ gemm_attn_pipe_kernel(const __grid_constant__ CUtensorMap mA, const __grid_const
     }
   }
   __syncthreads();
+  if (CG == 2) cluster_sync_all();        // no CTA of the pair leaves (or frees TMEM) while the other may still signal / be read
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * G::ACC_COLS) : "memory");
+    if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * G::ACC_COLS) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * G::ACC_COLS) : "memory");
   }
+}
+
+// launch: `cg` = 1 single CTAs, 2 = CTA pairs (cluster dimension 2)
+template <bool CROSS, int CG>
+inline int gemm_attn_pipe_launch(Ctx& c, const CUtensorMap& mA, const CUtensorMap& mW, const GemmAttnP& p, long long row_tiles) {
+  typedef GxCfg<CROSS, CG> G;
+  auto kern = gemm_attn_pipe_kernel<CROSS, CG>;
+  QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM));
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const long long ntiles = ((row_tiles + CG - 1) / CG) * p.H;
+  const long long units = sms / CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(ntiles < units ? ntiles : units) * CG);
+  cfg.blockDim = dim3(384);
+  cfg.dynamicSmemBytes = G::SMEM;
+  cfg.stream = c.stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = CG;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = CG == 2 ? 1 : 0;
+  QAT_CUDA(cudaLaunchKernelEx(&cfg, kern, mA, mW, p));
+  return check_launch(CROSS ? "gemm_attn_pipe_kernel<cross>" : "gemm_attn_pipe_kernel<self>");
 }
 
 }  // namespace tc
@@ -332,19 +401,14 @@ inline int gemm_attn_f16(Ctx& c, const __half* X, int ldx, int nframes, int P, i
   const long long M = (long long)nframes * P;
   CUtensorMap mA, mW;
   QAT_TRY(tc::make_map(&mA, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, K, ldx, 128));
-  QAT_TRY(tc::make_map(&mW, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3 * D, K, K, 64));
+  QAT_TRY(tc::make_map(&mW, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3 * D, K, K, 32));      // 32-row weight pieces
   tc::GemmAttnP p;
   p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
-  const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
   p.o = O;
   p.ldo = ldo;
-  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GxCfg<false>::SMEM));
-  tc::gemm_attn_pipe_kernel<false><<<grid, 384, tc::GxCfg<false>::SMEM, c.stream>>>(mA, mW, p);
-  return check_launch("gemm_attn_pipe_kernel<self>");
+  const long long row_tiles = (nframes + FPT - 1) / FPT;
+  if (row_tiles >= 2 && c.opt.v[OPT_GEMM_ATTN_CG] == 2) return tc::gemm_attn_pipe_launch<false, 2>(c, mA, mW, p, row_tiles);
+  return tc::gemm_attn_pipe_launch<false, 1>(c, mA, mW, p, row_tiles);
 }
 
 // O[nframes * 2, D] (fp16) = per-frame softmax(Q (X Wk^T + bk)^T / 8)(X Wv^T + bv) for the two projected query rows
@@ -362,18 +426,13 @@ inline int gemm_attn_cross_f16(Ctx& c, const __half* X, int ldx, int nframes, in
   const long long M = (long long)nframes * P;
   CUtensorMap mA, mW;
   QAT_TRY(tc::make_map(&mA, X, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, K, ldx, 128));
-  QAT_TRY(tc::make_map(&mW, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * D, K, K, 64));
+  QAT_TRY(tc::make_map(&mW, W, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2 * D, K, K, 32));      // 32-row weight pieces
   tc::GemmAttnP p;
   p.M = (int)M; p.nframes = nframes; p.P = P; p.H = H; p.K = K; p.bias = bias; p.scale = scale;
   p.q = Q; p.o = O; p.ldo = ldo;
-  const long long ntiles = (long long)((nframes + FPT - 1) / FPT) * H;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
-  QAT_CUDA(cudaFuncSetAttribute(tc::gemm_attn_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::GxCfg<true>::SMEM));
-  tc::gemm_attn_pipe_kernel<true><<<grid, 384, tc::GxCfg<true>::SMEM, c.stream>>>(mA, mW, p);
-  return check_launch("gemm_attn_pipe_kernel<cross>");
+  const long long row_tiles = (nframes + FPT - 1) / FPT;
+  if (row_tiles >= 2 && c.opt.v[OPT_GEMM_ATTN_CG] == 2) return tc::gemm_attn_pipe_launch<true, 2>(c, mA, mW, p, row_tiles);
+  return tc::gemm_attn_pipe_launch<true, 1>(c, mA, mW, p, row_tiles);
 }
 
 }  // namespace qat

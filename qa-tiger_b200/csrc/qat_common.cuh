@@ -35,6 +35,8 @@ enum {
   OPT_PATCH_NO_FUSED_CROSS,   // 1: K | V GEMM + separate cross-attention kernel
   OPT_TOME_MATCH_ROWS,        // 1: the row-per-thread ToMe match kernel (the fallback of frames too long for the tiled one)
   OPT_MOE_NO_FUSED_REDUCE,    // 1: expert first-layer GEMM writes the hidden tensor, separate gauss_reduce launches
+  OPT_GEMM_ATTN_CG,           // 2: CTA pairs (cta_group::2) in the fused PatchSelecter GEMM + attention kernels (default: single CTAs;
+                              //    pairs halve the weight traffic but measured 1 % slower: the kernels are not operand-delivery bound)
   OPT_COUNT
 };
 struct Options {

@@ -105,3 +105,19 @@ def test_moe_fused_reduce_matches_the_streaming_kernel(B, T, E, K, two):
         assert torch.equal(x, y)
     for x, y in zip(fused if two else [fused], plain if two else [plain]):
         assert relerr(x, y) < 2e-6
+
+
+def test_patch_selecter_cta_pairs_match_single_ctas(sd):
+    """Fused in-projection + attention kernels as CTA pairs (cta_group::2, option gemm_attn_cg = 2) against single-CTA tiles: the same products
+    and accumulation order per output element -> identical results; odd and even numbers of row tiles (a half-empty tail pair)."""
+    from qa_tiger_b200 import _cabi
+    m, proj = _patch_block(sd)
+    g = torch.Generator().manual_seed(9)
+    for B, T in ((12, 60), (1, 9), (3, 31), (2, 60)):         # 80, 1, 11 (odd), 14 row tiles of 9 frames
+        raw = torch.randn(B, T, 14, 1024, generator=g).to(dev())
+        a, v = torch.randn(B, T, 512, generator=g).to(dev()), torch.randn(B, T, 512, generator=g).to(dev())
+        with torch.no_grad():
+            da, dv = m(raw, a, v, proj=proj)
+            with _cabi.option("gemm_attn_cg", 2):
+                sa, sv = m(raw, a, v, proj=proj)
+        assert torch.equal(sa, da) and torch.equal(sv, dv), (B, T)
