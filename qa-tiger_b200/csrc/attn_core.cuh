@@ -349,6 +349,14 @@ __device__ __forceinline__ void mma3_f16(float (&d)[4], const uint32_t (&ah)[4],
 // The kernel is issue / latency bound (ncu: 2 460 warp instructions per warp, 51 % issue utilisation, tensor pipe 32 %), so
 // the softmax multiplies by one reciprocal per row instead of dividing every element, masks only the key tiles that reach
 // past the limit, and the output addresses are formed once per row.
+// 2^x on the SFU (ex2.approx.ftz: 2 ulp); the scores carry log2(e) in their scale, so softmax needs no further multiply -- the
+// accurate expf() was a quarter of this kernel's issue slots
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int NT16, bool PL>   // key tiles of 16: Lk <= 16*NT16
 __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
   extern __shared__ __align__(16) unsigned char smraw[];
@@ -422,6 +430,7 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
   const uint32_t koff = uint32_t((r8 + (m8 >> 1) * 8) * RSB + (m8 & 1) * 16);   // + np*16 rows, + ks*32 bytes
   const uint32_t voff = uint32_t((r8 + (m8 & 1) * 8) * RSB + (m8 >> 1) * 16);   // + kk*16 rows, + dp*32 bytes
   const float invH = 1.f / p.H;
+  const float scale2 = p.scale * 1.4426950408889634f;        // scores in units of log2: softmax = 2^(s - max) / sum
   // PL: every warp passes the staging barrier exactly once, inside its first pass (a warp without query rows still takes it)
   for (int r0 = warp * 16; r0 < Lq || !staged; r0 += 64) {
     // ---- Q fragments, rows r0+g / r0+g+8 ----
@@ -456,10 +465,10 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
         const float2 a1 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16));
         const float2 a2 = __ldg(reinterpret_cast<const float2*>(q0 + ks * 16 + 8));
         const float2 a3 = __ldg(reinterpret_cast<const float2*>(q1 + ks * 16 + 8));
-        split_half2(a0.x * p.scale, a0.y * p.scale, qh[ks][0], ql[ks][0]);
-        split_half2(a1.x * p.scale, a1.y * p.scale, qh[ks][1], ql[ks][1]);
-        split_half2(a2.x * p.scale, a2.y * p.scale, qh[ks][2], ql[ks][2]);
-        split_half2(a3.x * p.scale, a3.y * p.scale, qh[ks][3], ql[ks][3]);
+        split_half2(a0.x * scale2, a0.y * scale2, qh[ks][0], ql[ks][0]);
+        split_half2(a1.x * scale2, a1.y * scale2, qh[ks][1], ql[ks][1]);
+        split_half2(a2.x * scale2, a2.y * scale2, qh[ks][2], ql[ks][2]);
+        split_half2(a3.x * scale2, a3.y * scale2, qh[ks][3], ql[ks][3]);
       }
     }
     // ---- S = Q K^T ----
@@ -486,7 +495,7 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
 #pragma unroll
     for (int nt = 0; nt < 2 * NT16; ++nt) {
       if constexpr (PL) {
-        s[nt][0] *= p.scale; s[nt][1] *= p.scale; s[nt][2] *= p.scale; s[nt][3] *= p.scale;
+        s[nt][0] *= scale2; s[nt][1] *= scale2; s[nt][2] *= scale2; s[nt][3] *= scale2;
       }
       if (nt * 8 + 8 > lim_min) {
         const int c = nt * 8 + 2 * t;
@@ -505,10 +514,10 @@ __global__ void __launch_bounds__(128, 4) attn_mma16_kernel(AttnP p) {
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 2 * NT16; ++nt) {
-      s[nt][0] = expf(s[nt][0] - mx0);
-      s[nt][1] = expf(s[nt][1] - mx0);
-      s[nt][2] = expf(s[nt][2] - mx1);
-      s[nt][3] = expf(s[nt][3] - mx1);
+      s[nt][0] = ex2_fast(s[nt][0] - mx0);
+      s[nt][1] = ex2_fast(s[nt][1] - mx0);
+      s[nt][2] = ex2_fast(s[nt][2] - mx1);
+      s[nt][3] = ex2_fast(s[nt][3] - mx1);
       s0 += s[nt][0] + s[nt][1];
       s1 += s[nt][2] + s[nt][3];
     }
