@@ -8,7 +8,7 @@
 #include "gauss.cuh"
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
-#include "gemm_attn.cuh"
+#include "gemm_attn_ts.cuh"
 #include "moe_front.cuh"
 #include "qat_common.cuh"
 #include "rowops.cuh"
@@ -21,7 +21,7 @@ thread_local long long g_launches = 0;
 
 static const char* const kOptNames[OPT_COUNT] = {"gemm_cg", "gemm_bn", "attn_fp32_in", "patch_chunk", "patch_fp32_planes",
                                                  "patch_no_fused_attn", "patch_no_fused_cross", "tome_match_rows",
-                                                 "moe_no_fused_reduce", "gemm_attn_cg"};
+                                                 "moe_no_fused_reduce", "gemm_attn_no_ts", "gemm_attn_ts_flags"};
 std::atomic<int> g_opt[OPT_COUNT];
 // defaults from the environment, read once at load time (QAT_GEMM_CG=1 etc.)
 static struct OptInit {

@@ -35,8 +35,9 @@ enum {
   OPT_PATCH_NO_FUSED_CROSS,   // 1: K | V GEMM + separate cross-attention kernel
   OPT_TOME_MATCH_ROWS,        // 1: the row-per-thread ToMe match kernel (the fallback of frames too long for the tiled one)
   OPT_MOE_NO_FUSED_REDUCE,    // 1: expert first-layer GEMM writes the hidden tensor, separate gauss_reduce launches
-  OPT_GEMM_ATTN_CG,           // 2: CTA pairs (cta_group::2) in the fused PatchSelecter GEMM + attention kernels (default: single CTAs;
-                              //    pairs halve the weight traffic but measured 1 % slower: the kernels are not operand-delivery bound)
+  OPT_GEMM_ATTN_NO_TS,        // 1: the fused PatchSelecter kernels with both operands from shared memory (gemm_attn.cuh) instead of the
+                              //    A-resident form (A operand in tensor memory, gemm_attn_ts.cuh)
+  OPT_GEMM_ATTN_TS_FLAGS,     // per-stage cost-model bits of the A-resident kernels (GemmAttnP::flags); read by a -DQAT_PROFILE_BUILD library only
   OPT_COUNT
 };
 struct Options {
