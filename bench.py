@@ -50,6 +50,7 @@ def parse():
                     help="BASELINE configs[2] instead of configs[1]: ToMe 577->14 merge chain over 60 x 256 = 15 360 frames, chunked, "
                          "frame-sharded over the ranks; prints frames/s and the stepwise-traffic roofline")
     ap.add_argument("--tome-frames", type=int, default=15360)
+    ap.add_argument("--tome-streams", type=int, default=2, help="side streams the chunks of the ToMe chain alternate over (1 = serial chunks)")
     ap.add_argument("--stress", action="store_true",
                     help="BASELINE configs[4] shape instead of configs[1]: T=120, E=K=14, 128 questions per GPU (combine with --hot-only)")
     a = ap.parse_args()
@@ -277,7 +278,7 @@ def run_tome(args):
     if rank == 0:
         sampler.start()
     for _ in range(max(1, args.warmup)):
-        tm.chain_frames(x, hi - lo, chunk=chunk)
+        tm.chain_frames(x, hi - lo, chunk=chunk, streams=args.tome_streams)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -287,7 +288,7 @@ def run_tome(args):
     sampler.armed = True
     e0.record()
     for _ in range(args.steps):
-        xo, so, _ = tm.chain_frames(x, hi - lo, chunk=chunk)
+        xo, so, _ = tm.chain_frames(x, hi - lo, chunk=chunk, streams=args.tome_streams)
     e1.record()
     torch.cuda.synchronize()
     sampler.armed = False
@@ -352,7 +353,7 @@ def run_tome(args):
                 "data": "synthetic",
                 "config": {"workload": f"ToMe bipartite soft matching 577->14 (configs[2]): {n_frames} frames = 60 x 256, 23 merge steps "
                                        "(r = 25 x 22, then 13), class token, stand-in metric x.view(N,t,16,64).mean(2) (SURVEY 8d), "
-                                       "bit-exact indices", "frames_per_rank": hi - lo, "chunk_frames": chunk,
+                                       "bit-exact indices", "frames_per_rank": hi - lo, "chunk_frames": chunk, "chunk_streams": args.tome_streams,
                            "parallelism": f"frame-sharded dp{world}, no collective", "l2": "1.4 GB of tokens per chunk exceeds L2"},
                 "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,

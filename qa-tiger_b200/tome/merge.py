@@ -178,22 +178,52 @@ def frame_shard(n_frames: int, rank: int, world: int):
     return lo, min(n_frames, lo + per)
 
 
+_side_streams = {}
+
+
+def _streams_for(dev: torch.device, n: int):
+    key = dev.index if dev.index is not None else torch.cuda.current_device()
+    pool = _side_streams.setdefault(key, [])
+    while len(pool) < n:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:n]
+
+
 def chain_frames(frames, n_frames: int, rank: int = 0, world: int = 1, chunk: int = 592, schedule: Optional[List[int]] = None,
-                 class_token: bool = True, want_group: bool = False):
+                 class_token: bool = True, want_group: bool = False, streams: int = 2):
     """The extractor's loop (scripts/extract_ToMe/extract_tome14.py:153-170: one frame at a time through the 23-step schedule)
     over this rank's shard of `n_frames` frames, `chunk` frames per `chain()` call (a multiple of the SM count keeps the
     one-frame-per-CTA match kernel in whole waves).  `frames`: a [n_frames, t0, C] CUDA tensor, or a callable
     (lo, hi) -> [hi-lo, t0, C] producing the frames of a chunk (x0 of configs[2] is 36 GB: callers may stream it).
+    `streams` > 1: consecutive chunks run on that many side streams (each with its own workspace), so the FFMA-bound match
+    kernels of one chunk overlap the HBM-bound merge kernels of another; the chunks are independent, results are unchanged.
     Returns (x_out [n_local, t_end, C], size [n_local, t_end, 1], group [n_local, t0] | None) in frame order."""
     lo, hi = frame_shard(n_frames, rank, world)
     outs, sizes, groups = [], [], []
-    for c0 in range(lo, hi, chunk):
+    starts = list(range(lo, hi, chunk))
+    dev = frames.device if isinstance(frames, torch.Tensor) else torch.device("cuda", torch.cuda.current_device())
+    side = _streams_for(dev, streams) if streams > 1 and len(starts) > 1 else None
+    if side is not None:
+        cur = torch.cuda.current_stream(dev)
+        for st in side:
+            st.wait_stream(cur)                     # the frames (and anything else queued so far) are ready
+    for i, c0 in enumerate(starts):
         c1 = min(hi, c0 + chunk)
-        x = frames(c0, c1) if callable(frames) else frames[c0:c1]
-        o, sz, g, _ = chain(x, schedule, class_token, trace=False, want_group=want_group)
+        if side is None:
+            x = frames(c0, c1) if callable(frames) else frames[c0:c1]
+            o, sz, g, _ = chain(x, schedule, class_token, trace=False, want_group=want_group)
+        else:
+            with torch.cuda.stream(side[i % len(side)]):
+                x = frames(c0, c1) if callable(frames) else frames[c0:c1]
+                o, sz, g, _ = chain(x, schedule, class_token, trace=False, want_group=want_group)
         outs.append(o)
         sizes.append(sz)
         groups.append(g)
+    if side is not None:
+        for st in side:
+            cur.wait_stream(st)                     # outputs are consumed on the caller's stream
+        for t_ in outs + sizes + [g for g in groups if g is not None]:
+            t_.record_stream(cur)
     if not outs:
         return None, None, None
     return torch.cat(outs), torch.cat(sizes), (torch.cat(groups) if want_group else None)

@@ -94,3 +94,17 @@ def test_r_zero_and_errors():
         tm.bipartite_soft_matching(torch.randn(1, 8, 64, device=dev()), 2, distill_token=True)
     with pytest.raises(RuntimeError, match="C="):
         tm.bipartite_soft_matching(torch.randn(1, 8, 48, device=dev()), 2)
+
+
+def test_chain_frames_side_streams_match_serial_chunks():
+    """chain_frames over several chunks on two side streams (match kernels of one chunk overlapping merge kernels of another) returns
+    exactly what the serial chunk loop returns: the chunks are independent."""
+    from qa_tiger_b200.tome import merge as tm
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(23, 577, 1024, generator=g).cuda()
+    a = tm.chain_frames(x, 23, chunk=5, want_group=True, streams=1)
+    b = tm.chain_frames(x, 23, chunk=5, want_group=True, streams=2)
+    c = tm.chain_frames(lambda lo, hi: x[lo:hi].clone(), 23, chunk=5, want_group=True, streams=3)
+    torch.cuda.synchronize()
+    for u, v, w in zip(a, b, c):
+        assert torch.equal(u, v) and torch.equal(u, w)
