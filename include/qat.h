@@ -445,7 +445,7 @@ int qat_abi_version(void);
 /* number of kernel launches issued by this thread since the last reset (bench.py's gpu_launches) */
 long long qat_launch_count(int reset);
 /* A/B switches (profiling aids; defaults are the measured-faster paths): "gemm_cg", "gemm_bn", "attn_fp32_in", "patch_chunk",
- * "patch_fp32_planes", "patch_no_fused_attn", "patch_no_fused_cross", "tome_match_rows", "moe_no_fused_reduce", "gemm_attn_no_ts", "gemm_attn_ts_flags" (the last one only acts in a -DQAT_PROFILE_BUILD library).  Process-wide;
+ * "patch_fp32_planes", "patch_no_fused_attn", "patch_no_fused_cross", "tome_match_rows", "moe_no_fused_reduce", "gemm_attn_no_ts", "moe_w2_simt", "gemm_attn_ts_flags" (the last one only acts in a -DQAT_PROFILE_BUILD library).  Process-wide;
  * initialised once from the environment (QAT_<UPPER-CASE NAME>) when the library is loaded, never read from the environment
  * again; every entry point snapshots them on entry, so sizing and execution of one call agree.  Set them between calls. */
 int qat_set_option(const char* name, int value);

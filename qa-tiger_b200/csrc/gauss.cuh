@@ -311,6 +311,8 @@ struct MoeCoefP {
   GaussP g;          // rl / gr / B / T / E / K / sigma / aux outputs (x, out unused)
   float* coef;       // [B*T, E]
   float* hb;         // [nrep*B, ldh]
+  bf16* hbh = nullptr;   // the same block as bf16 (hi, lo) planes (optional: the split-K tensor-core second layer reads those)
+  bf16* hbl = nullptr;
   int ldh, col0, nrep;
 };
 struct MoeCoefPack {
@@ -339,7 +341,16 @@ __global__ void __launch_bounds__(MOE_COEF_NT) moe_coef_kernel(MoeCoefPack pk) {
     float sum = 0.f;
     if (e < E)
       for (int t = 0; t < T; ++t) sum += sm.coef[t * E + e];
-    for (int r = 0; r < q.nrep; ++r) q.hb[((long long)r * p.B + b) * q.ldh + q.col0 + e] = sum;
+    bf16 sh, sl;
+    split_bf16(sum, sh, sl);
+    for (int r = 0; r < q.nrep; ++r) {
+      const long long o = ((long long)r * p.B + b) * q.ldh + q.col0 + e;
+      q.hb[o] = sum;
+      if (q.hbh) {
+        q.hbh[o] = sh;
+        q.hbl[o] = sl;
+      }
+    }
   }
 }
 

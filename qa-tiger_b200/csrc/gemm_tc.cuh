@@ -510,7 +510,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
               }
             }
             const long long srow = (long long)m0 / TT + s;
-            if (srow * TT < p.M && n0 + q < p.N) p.C.f[srow * p.C.ld + n0 + q] = sum;
+            if (srow * TT < p.M && n0 + q < p.N) {
+              p.C.f[srow * p.C.ld + n0 + q] = sum;
+              if (p.C.hi) {                                         // planes for a tensor-core consumer of the reduced tile
+                bf16 sh, sl;
+                split_bf16(sum, sh, sl);
+                p.C.hi[srow * p.C.ld + n0 + q] = sh;
+                p.C.lo[srow * p.C.ld + n0 + q] = sl;
+              }
+            }
           }
         }
         continue;
@@ -753,8 +761,8 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   QAT_REQUIRE((C.ph != nullptr) == (C.pl != nullptr) && !(C.ph && C.hi), "gemm_tc: the fp16 pair needs both planes and excludes the bf16 pair");
   mCf = mChi = mClo = mCh = mA0;
   if (Cstore.f) QAT_TRY(make_store_map(&mCf, C.f, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, M, N, C.ld));
-  if (C.hi) QAT_TRY(make_store_map(&mChi, C.hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
-  if (C.lo) QAT_TRY(make_store_map(&mClo, C.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
+  if (C.hi && !epi.coef) QAT_TRY(make_store_map(&mChi, C.hi, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
+  if (C.lo && !epi.coef) QAT_TRY(make_store_map(&mClo, C.lo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, M, N, C.ld));
   if (C.h) QAT_TRY(make_store_map(&mCh, C.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
   if (C.ph) {
     QAT_TRY(make_store_map(&mChi, C.ph, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, M, N, C.ld));
@@ -765,7 +773,8 @@ inline int launch(Ctx& c, const void* A0, const void* A1, long long lda, long lo
   p.M = (int)M; p.N = N; p.K = K; p.epi = epi; p.C = C;
   p.tile_rows = G::BM;
   if (epi.coef) {
-    QAT_REQUIRE(BN == 256 && C.f && !C.hi && !C.h && !C.ph && !epi.res && !epi.res_h, "gemm_tc: the reduce epilogue writes one fp32 plane from 256-wide tiles");
+    QAT_REQUIRE(BN == 256 && C.f && (C.hi != nullptr) == (C.lo != nullptr) && !C.h && !C.ph && !epi.res && !epi.res_h,
+                "gemm_tc: the reduce epilogue writes one fp32 plane (+ optional bf16 hi / lo planes) from 256-wide tiles");
     QAT_REQUIRE(epi.coef_T >= 32 && epi.coef_T <= 128 && M % epi.coef_T == 0 && epi.coef_Ch % 32 == 0 && epi.coef_E >= 1 && epi.coef_mod >= 1,
                 "gemm_tc: reduce epilogue needs 32 <= T <= 128, M %% T == 0 and Ch %% 32 == 0 (T=%d Ch=%d)", epi.coef_T, epi.coef_Ch);
     p.tile_rows = (G::BM / epi.coef_T) * epi.coef_T;

@@ -9,6 +9,7 @@
 #include "gemm_simt.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_attn_ts.cuh"
+#include "gemm_splitk.cuh"
 #include "moe_front.cuh"
 #include "qat_common.cuh"
 #include "rowops.cuh"
@@ -21,7 +22,7 @@ thread_local long long g_launches = 0;
 
 static const char* const kOptNames[OPT_COUNT] = {"gemm_cg", "gemm_bn", "attn_fp32_in", "patch_chunk", "patch_fp32_planes",
                                                  "patch_no_fused_attn", "patch_no_fused_cross", "tome_match_rows",
-                                                 "moe_no_fused_reduce", "gemm_attn_no_ts", "gemm_attn_ts_flags"};
+                                                 "moe_no_fused_reduce", "gemm_attn_no_ts", "gemm_attn_ts_flags", "moe_w2_simt"};
 std::atomic<int> g_opt[OPT_COUNT];
 // defaults from the environment, read once at load time (QAT_GEMM_CG=1 etc.)
 static struct OptInit {
@@ -588,6 +589,7 @@ struct MoeMod {
   bool fused = false;              // M4 runs in the expert GEMM's epilogue
   float* coef = nullptr;           // [B*T, E]   (fused)
   Act Hb;                          // [nbranch*B, E*Ch + 64]  (fused: bias-column block already written)
+  bool w2_tc = false;              // second layer on the split-K tensor-core path (Hb carries bf16 hi / lo planes)
 };
 
 // temp_w -> router | gauss_pred for up to two modules per launch sequence (moe_front.cuh), then the per-row coefficients of
@@ -648,14 +650,17 @@ static int moe_front(Ctx& c, MoeMod* mods, int n, int B, int T) {
     const int nb = two ? 2 : 1;
     M.coef = reinterpret_cast<float*>(c.alloc((size_t)BT * E * 4));
     if (!c.dry && !M.coef) QAT_FAIL(QAT_EWORKSPACE, "workspace too small (need > %zu bytes, have %zu)", c.off, c.cap);
-    QAT_TRY(act_alloc(c, M.Hb, (long long)nb * B, KE, true, false));
+    // the second layer runs on the split-K tensor-core path when its weights carry planes: its operand then leaves the first
+    // layer's epilogue (and the bias block below) as bf16 (hi, lo) planes as well
+    M.w2_tc = gemm_splitk_ok((long long)nb * B, D, KE, wview(a->w2_ext).hi, wview(a->w2_ext).lo) && c.opt.v[OPT_MOE_W2_SIMT] != 1;
+    QAT_TRY(act_alloc(c, M.Hb, (long long)nb * B, KE, true, M.w2_tc));
     MoeCoefP& q = pk.m[nf++];
     q.g = GaussP();
     q.g.x = nullptr; q.g.st = 0; q.g.sb = 0;
     q.g.rl = M.RG.f; q.g.gr = M.RG.f + E; q.g.rl_ld = 3 * E; q.g.gr_ld = 3 * E; q.g.B = B; q.g.T = T; q.g.E = E; q.g.K = a->K; q.g.C = Ch;
     q.g.sigma = a->sigma; q.g.per_expert = 1; q.g.ring = 0;
     q.g.topk_inds = reinterpret_cast<long long*>(a->topk_inds); q.g.topk_probs = a->topk_probs; q.g.gauss_weight = a->gauss_weight;
-    q.coef = M.coef; q.hb = M.Hb.f; q.ldh = KE; q.col0 = E * Ch; q.nrep = nb;
+    q.coef = M.coef; q.hb = M.Hb.f; q.hbh = M.Hb.hi; q.hbl = M.Hb.lo; q.ldh = KE; q.col0 = E * Ch; q.nrep = nb;
   }
   if (nf) QAT_TRY(moe_coef(c, pk, nf));
   return QAT_OK;
@@ -705,10 +710,14 @@ static int moe_back(Ctx& c, MoeMod& M, int B, int T) {
     }
     QAT_TRY(act_alloc(c, Ob, (long long)nb * B, D, true, false));
     {
+      // second expert layer + biases as one [nb*B, E*Ch+64] x [D, E*Ch+64]^T contraction.  It comes after the router, so 16-bit
+      // operands are enough; at K = 1856 the CUDA-core kernel (shared-memory bound at its 4 x 4 register tile) took 23 + 35 us
+      // per step for the two modules
       Epi e2;
       WView w2 = W2;
       w2.bias = nullptr;
-      QAT_TRY(gemm(c, G_SIMT, Hb, (long long)nb * B, w2, e2, Ob));
+      if (M.w2_tc) QAT_TRY(gemm_splitk_bf16x3(c, Hb.hi, Hb.lo, Hb.ld, (long long)nb * B, w2.hi, w2.lo, w2.n, w2.k, e2, Ob));
+      else QAT_TRY(gemm(c, G_SIMT, Hb, (long long)nb * B, w2, e2, Ob));
     }
     QAT_TRY(ln(c, Ob.f, D, nullptr, 0, nullptr, 0, 1.f, a->norm_a, act_of(out_a, D), B, D));
     if (two) QAT_TRY(ln(c, Ob.f + (size_t)B * D, D, nullptr, 0, nullptr, 0, 1.f, a->norm_v, act_of(out_v, D), B, D));
@@ -790,8 +799,19 @@ static int ground_core(const QatGroundArgs* a, int B, Ctx& c, const float* qst, 
   QAT_TRY(act_alloc(c, KV, 2ll * B, 2 * D, true, false));
   AttnP p;
   if (d1 == d0 + (size_t)B * D) {
-    // the two length-1 inputs sit back to back: one contraction over [2B, D]; key i of sample b is row i*B + b
-    QAT_TRY(gemm(c, G_SIMT, act_of(d0, D), 2ll * B, wview(a->attn_kv), Epi(), KV));
+    // the two length-1 inputs sit back to back: one contraction over [2B, D]; key i of sample b is row i*B + b.  The block comes
+    // after the router, so in bf16 mode its largest contraction runs on the split-K tensor-core path (16-bit-mantissa operands;
+    // 24 -> 12 us per pass at B = 256), after a plane-conversion pass over the 2B input rows
+    const WView Wkv = wview(a->attn_kv);
+    if (c.prec == QAT_PREC_BF16 && gemm_splitk_ok(2ll * B, 2 * D, D, Wkv.hi, Wkv.lo) && 2ll * B >= 256 && c.opt.v[OPT_MOE_W2_SIMT] != 1) {
+      Act In = act_of(d0, D);
+      QAT_TRY(ensure_operand(c, In, 2ll * B, D, G_BF16X3));
+      Epi e;
+      e.bias = Wkv.bias;
+      QAT_TRY(gemm_splitk_bf16x3(c, In.hi, In.lo, D, 2ll * B, Wkv.hi, Wkv.lo, Wkv.n, Wkv.k, e, KV));
+    } else {
+      QAT_TRY(gemm(c, G_SIMT, act_of(d0, D), 2ll * B, Wkv, Epi(), KV));
+    }
     p.k_sn = 2 * D; p.k_si = (long long)B * 2 * D;
   } else {
     Act kv0 = KV, kv1 = KV;                                      // [B, 2, 2D]

@@ -38,6 +38,8 @@ enum {
   OPT_GEMM_ATTN_NO_TS,        // 1: the fused PatchSelecter kernels with both operands from shared memory (gemm_attn.cuh) instead of the
                               //    A-resident form (A operand in tensor memory, gemm_attn_ts.cuh)
   OPT_GEMM_ATTN_TS_FLAGS,     // per-stage cost-model bits of the A-resident kernels (GemmAttnP::flags); read by a -DQAT_PROFILE_BUILD library only
+  OPT_MOE_W2_SIMT,            // 1: the post-router contractions that default to the split-K bf16x3 tensor-core path (TempMoE's second expert layer,
+                              //    QstGrounding's K | V projection) on the fp32 CUDA-core GEMM
   OPT_COUNT
 };
 struct Options {

@@ -95,7 +95,7 @@ def test_moe_fused_reduce_matches_the_streaming_kernel(B, T, E, K, two):
     g = torch.Generator().manual_seed(B + T)
     q, d = torch.randn(B, 512, generator=g).to(dev()), torch.randn(B, T, 512, generator=g).to(dev())
     sub = [torch.randn(B, T, 512, generator=g).to(dev()), torch.randn(B, T, 512, generator=g).to(dev())] if two else None
-    with torch.no_grad():
+    with torch.no_grad(), _cabi.option("moe_w2_simt", 1):        # the same fp32 second layer behind both forms
         fused = m(q, d, sub)
         aux_f = [t.clone() for t in m.last_aux]
         with _cabi.option("moe_no_fused_reduce", 1):
@@ -105,6 +105,11 @@ def test_moe_fused_reduce_matches_the_streaming_kernel(B, T, E, K, two):
         assert torch.equal(x, y)
     for x, y in zip(fused if two else [fused], plain if two else [plain]):
         assert relerr(x, y) < 2e-6
+    # second expert layer on the split-K bf16x3 tensor-core path (default) against the fp32 CUDA-core GEMM: 16-bit operands, after the router
+    with torch.no_grad():
+        tcw2 = m(q, d, sub)
+    for x, y in zip(tcw2 if two else [tcw2], fused if two else [fused]):
+        assert relerr(x, y) < 3e-5
 
 
 def test_patch_selecter_a_resident_matches_shared_memory_operands(sd):
