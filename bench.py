@@ -629,6 +629,24 @@ def run_ours(args):
                                  "ms": t_ms, "shape": [M_, N_, K_],
                                  "note": f"nominal 2MNK FLOPs; peak = burst bf16 / {div:g} (kernel timed alone)"}
                 del xin, planes
+            # (2a) PatchSelecter's fused projection + attention kernels (A operand in tensor memory) on the rows of one pass:
+            #      nominal FLOPs = the projection (2*rows*N*K) + the attention products; peak = burst bf16 (one f16-kind MMA per product)
+            try:
+                nfr = chunk_rows // P
+                xh = (torch.randn(chunk_rows, 512, device=dev) * 0.5).half()
+                for nm, lin, nq in (("gemm_attn_patch_self", ps["slf_in"], None), ("gemm_attn_patch_cross", ps["crs_kv"], 2)):
+                    wh_, bb_ = lin.w.half().contiguous(), lin.b.contiguous()
+                    qh = torch.randn(nfr, 2, 512, device=dev).half() if nq else None
+                    t_ms = time_ms(lambda: _cabi.gemm_attn(xh, wh_, bb_, P, 8, q=qh), n=6)
+                    fl = 2.0 * chunk_rows * wh_.shape[0] * 512 + 4.0 * nfr * 8 * (nq or P) * P * 64
+                    ach = fl / (t_ms * 1e-3) / 1e12
+                    rooflines[nm] = {"bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
+                                     "frac_of_sustained": ach / tf_sust, "traffic": None, "ms": t_ms, "shape": [chunk_rows, wh_.shape[0], 512],
+                                     "note": "nominal FLOPs of projection + attention; tensor pipe 65 % (ncu): an N = 128 MMA costs ~100 clocks "
+                                             "for its 64-clock floor, the weight rows alone need 225 / 158 us at the 13 TB/s L2 -> SM rate (DESIGN section 5)"}
+                del xh
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write(f"[bench] gemm_attn roofline skipped: {e}\n")
             # (2b) AVQ self-attention core (HBM class: a (sequence, head) problem is far below a tensor tile): 2*B sequences x 60
             #     tokens, fp32 in / out, fp16 hi/lo mma.sync inside
             qa = [torch.randn(2 * B, T, 8, 64, device=dev) for _ in range(3)]
@@ -643,15 +661,15 @@ def run_ours(args):
             #     merge traffic of SURVEY 8d (56.49 MB per frame) over the WHOLE chain time (match kernels included)
             try:
                 from qa_tiger_b200.tome import merge as tm
-                nfr = 592                                  # 4 x 148: the match kernel runs one frame per CTA, one CTA per SM
-                xt = torch.randn(nfr, 577, 1024, device=dev)
+                nfr = 2 * 592                              # chunks of 4 x 148 frames (the match kernel runs one frame per CTA, one CTA
+                xt = torch.randn(nfr, 577, 1024, device=dev)     # per SM), two chunks on two streams as chain_frames runs them
                 for _ in range(2):
-                    tm.chain(xt)
+                    tm.chain_frames(xt, nfr, chunk=592)
                 torch.cuda.synchronize()
                 a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 a_.record()
                 for _ in range(3):
-                    tm.chain(xt)
+                    tm.chain_frames(xt, nfr, chunk=592)
                 b_.record()
                 torch.cuda.synchronize()
                 t_ms = a_.elapsed_time(b_) / 3

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define QAT_ABI_VERSION 3
+#define QAT_ABI_VERSION 4
 
 enum {
   QAT_OK = 0,
@@ -117,6 +117,26 @@ typedef struct {
   int64_t coef_mod;
 } QatGemmArgs;
 int qat_gemm(const QatGemmArgs* a);
+
+/* ---- PatchSelecter's fused projection + attention kernels (modules.py:688 and :692-698), exported for parity tests and roofline
+ *      timing.  fp16 planes in and out, fp32 bias, head dim 64, P <= 14 tokens per frame (whole frames per 128-row tile).
+ *      cross = 0:  O[nframes*P, ldo] = per-frame softmax((X Wq^T + bq)(X Wk^T + bk)^T * scale)(X Wv^T + bv),  W = in_proj [3D, K]
+ *      cross = 1:  O[nframes*2, ldo] = per-frame softmax(Q (X Wk^T + bk)^T * scale)(X Wv^T + bv) for the two projected query rows
+ *                  Q [nframes, 2, D] of every frame,  W = in_proj[D:] [2D, K]
+ *      K = 512 and an even head count run the A-resident kernels (A operand in tensor memory), other shapes the round-1 form ---- */
+typedef struct {
+  int32_t cross, nframes, P, H, K;
+  float scale;
+  void* stream;
+  const void* x_f16;       /* [nframes*P, ldx] */
+  int32_t ldx;
+  const void* w_f16;       /* [(3 - cross) * H*64, K] */
+  const float* bias;       /* [(3 - cross) * H*64] */
+  const void* q_f16;       /* cross only */
+  void* o_f16;
+  int32_t ldo;
+} QatGemmAttnArgs;
+int qat_gemm_attn_fwd(const QatGemmAttnArgs* a);
 
 /* ---- softmax(q k^T * scale) v on head-dim-64 heads: the attention cores every block above is built from (torch MHA
  *      slow path semantics, SURVEY 8a-A3: no masks except `causal`); exported for parity tests and roofline timing ---- */

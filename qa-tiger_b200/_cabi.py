@@ -13,7 +13,7 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("QAT_LIB") or os.path.join(HERE, "csrc", "libqat_b200.so")   # QAT_LIB: A/B builds while profiling
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 PREC_FP32, PREC_BF16 = 0, 1
 DT_F32, DT_BF16 = 0, 1
 OP_LINEAR, OP_AVQ, OP_PATCH, OP_MOE, OP_GROUND, OP_TOME_MATCH, OP_TOME_MERGE, OP_TOME_CHAIN, OP_CLIP_TEXT, OP_FORWARD, OP_TOME_BLOCK, OP_TOME_ATTENTION = range(12)
@@ -142,6 +142,12 @@ class AttnArgs(C.Structure):
                 ("o_rn", C.c_int64), ("o_ri", C.c_int64), ("ldo", C.c_int32), ("attw", C.c_void_p), ("kbias", C.c_void_p)]
 
 
+class GemmAttnArgs(C.Structure):
+    _fields_ = [("cross", C.c_int32), ("nframes", C.c_int32), ("P", C.c_int32), ("H", C.c_int32), ("K", C.c_int32),
+                ("scale", C.c_float), ("stream", C.c_void_p), ("x_f16", C.c_void_p), ("ldx", C.c_int32),
+                ("w_f16", C.c_void_p), ("bias", C.c_void_p), ("q_f16", C.c_void_p), ("o_f16", C.c_void_p), ("ldo", C.c_int32)]
+
+
 class ClipLayerW(C.Structure):
     _fields_ = [("ln_1", LayerNormW), ("ln_2", LayerNormW), ("in_proj", LinearW), ("out_proj", LinearW),
                 ("c_fc", LinearW), ("c_proj", LinearW)]
@@ -167,6 +173,7 @@ class GatherArgs(C.Structure):
 EXPORTS = {
     "qat_gemm": (C.c_int, [C.POINTER(GemmArgs)]),
     "qat_attention_fwd": (C.c_int, [C.POINTER(AttnArgs)]),
+    "qat_gemm_attn_fwd": (C.c_int, [C.POINTER(GemmAttnArgs)]),
     "qat_linear_fwd": (C.c_int, [C.POINTER(LinearArgs)]),
     "qat_avq_cross_attn_fwd": (C.c_int, [C.POINTER(AvqArgs)]),
     "qat_patch_select_fwd": (C.c_int, [C.POINTER(PatchArgs)]),
@@ -402,6 +409,22 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = 
     with torch.cuda.device(q.device):
         check(lib().qat_attention_fwd(C.byref(a)), "qat_attention_fwd")
     return (o, w) if need_weights else o
+
+
+def gemm_attn(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, P: int, H: int, q: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """PatchSelecter's fused projection + attention kernels (parity tests / roofline timing): x [nframes*P, K] fp16, w fp16
+    in_proj ([3D, K]; with `q` [nframes, 2, D] fp16: its k | v rows [2D, K]), bias fp32 -> o fp16 [nframes*P, D] ([nframes*2, D])."""
+    rows, K = x.shape
+    nf, D = rows // P, H * 64
+    assert rows == nf * P and x.dtype == torch.float16 and w.dtype == torch.float16 and bias.dtype == torch.float32
+    assert x.is_contiguous() and w.is_contiguous() and bias.is_contiguous() and (q is None or (q.is_contiguous() and q.dtype == torch.float16))
+    o = torch.empty(nf * (P if q is None else 2), D, device=x.device, dtype=torch.float16)
+    a = GemmAttnArgs()
+    a.cross, a.nframes, a.P, a.H, a.K, a.scale, a.stream = int(q is not None), nf, P, H, K, 0.125, stream_ptr(x.device)
+    a.x_f16, a.ldx, a.w_f16, a.bias, a.q_f16, a.o_f16, a.ldo = x.data_ptr(), K, w.data_ptr(), bias.data_ptr(), ptr(q), o.data_ptr(), D
+    with torch.cuda.device(x.device):
+        check(lib().qat_gemm_attn_fwd(C.byref(a)), "qat_gemm_attn_fwd")
+    return o
 
 
 # ---- workspace ----------------------------------------------------------------------------------

@@ -184,6 +184,17 @@ static int run_linear(const QatLinearArgs* a, Ctx& c) {
   return linear_core(c, a->w, act_of(a->x, a->w.k), a->rows, a->relu, act_of(a->y, a->w.n));
 }
 
+static int run_gemm_attn(const QatGemmAttnArgs* a, Ctx& c) {
+  QAT_REQUIRE(a->x_f16 && a->w_f16 && a->bias && a->o_f16 && (!a->cross || a->q_f16), "gemm_attn: NULL tensor");
+  QAT_REQUIRE(a->nframes >= 0 && a->P >= 1 && a->H >= 1, "gemm_attn: bad shape");
+  const __half* X = reinterpret_cast<const __half*>(a->x_f16);
+  const __half* W = reinterpret_cast<const __half*>(a->w_f16);
+  __half* O = reinterpret_cast<__half*>(a->o_f16);
+  if (a->cross)
+    return gemm_attn_cross_f16(c, X, a->ldx, a->nframes, a->P, a->H, a->K, W, a->bias, a->scale, reinterpret_cast<const __half*>(a->q_f16), O, a->ldo);
+  return gemm_attn_f16(c, X, a->ldx, a->nframes, a->P, a->H, a->K, W, a->bias, a->scale, O, a->ldo);
+}
+
 static int run_gemm(const QatGemmArgs* a, Ctx& c) {
   QAT_REQUIRE(a->kind >= G_SIMT && a->kind <= G_F16, "gemm: unknown kind %d", a->kind);
   QAT_REQUIRE(a->M >= 0 && a->w.n > 0 && a->w.k > 0 && a->lda >= a->w.k && a->ldc >= a->w.n, "gemm: bad shape");
@@ -1282,6 +1293,7 @@ using namespace qat;
 extern "C" {
 
 int qat_gemm(const QatGemmArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, run_gemm); }
+int qat_gemm_attn_fwd(const QatGemmAttnArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_BF16, nullptr, 0, run_gemm_attn); }
 int qat_attention_fwd(const QatAttnArgs* a) { return dispatch(a, a ? a->stream : nullptr, QAT_PREC_FP32, nullptr, 0, run_attention); }
 int qat_linear_fwd(const QatLinearArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_linear); }
 int qat_avq_cross_attn_fwd(const QatAvqArgs* a) { return dispatch(a, a ? a->stream : nullptr, a ? a->prec : 0, a ? a->workspace : nullptr, a ? a->workspace_bytes : 0, run_avq); }

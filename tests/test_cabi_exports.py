@@ -26,7 +26,7 @@ def test_header_symbols_are_exported():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _cabi.EXPORTS, f"{n} declared in qat.h but not bound in _cabi.py"
-    assert lib.qat_abi_version() == 3
+    assert lib.qat_abi_version() == _cabi.ABI_VERSION == 4
     assert lib.qat_tome_clamp_r(577, 25, 1) == 25 and lib.qat_tome_clamp_r(27, 25, 1) == 13 and lib.qat_tome_clamp_r(1, 25, 1) == 0
 
 
@@ -37,7 +37,7 @@ def test_struct_layout_matches_c(tmp_path):
              "QatPatchArgs": _cabi.PatchArgs, "QatGaussArgs": _cabi.GaussArgs, "QatMoeArgs": _cabi.MoeArgs,
              "QatGroundArgs": _cabi.GroundArgs, "QatTomeMatchArgs": _cabi.TomeMatchArgs,
              "QatTomeMergeArgs": _cabi.TomeMergeArgs, "QatTomeChainArgs": _cabi.TomeChainArgs,
-             "QatClipLayerW": _cabi.ClipLayerW, "QatClipTextArgs": _cabi.ClipTextArgs, "QatAttnArgs": _cabi.AttnArgs,
+             "QatClipLayerW": _cabi.ClipLayerW, "QatClipTextArgs": _cabi.ClipTextArgs, "QatAttnArgs": _cabi.AttnArgs, "QatGemmAttnArgs": _cabi.GemmAttnArgs,
              "QatForwardArgs": _cabi.ForwardArgs, "QatGatherArgs": _cabi.GatherArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "qat.h"', 'int main(void){']
     for cname, ct in pairs.items():
@@ -71,7 +71,7 @@ def test_options_are_set_through_the_abi_not_the_environment(monkeypatch):
         _cabi.set_option("gemm_dbg", 1)
     blob = open(_cabi.LIB_PATH, "rb").read()
     assert b"QAT_GEMM_DBG" not in blob
-    assert lib.qat_abi_version() == 3
+    assert lib.qat_abi_version() == _cabi.ABI_VERSION == 4
 
 
 def test_workspace_sizing_runs_without_gpu():

@@ -160,3 +160,26 @@ def test_gemm_reduce_epilogue(cg, S, T, E, rep, opt):
     assert relerr(got, ref) < 2e-5
     # bit-reproducible: no atomics anywhere in the reduction
     assert torch.equal(got, _cabi.gemm_reduce(a, lin, coef, T, Ch))
+
+
+@pytest.mark.parametrize("nf,cross", [(1, False), (9, False), (40, False), (1000, False), (9, True), (1000, True)])
+def test_fused_projection_attention_matches_fp64(nf, cross):
+    """qat_gemm_attn_fwd (PatchSelecter's fused in-projection + 14-token attention / K|V projection + two-query attention, A operand
+    in tensor memory) against the same fp16 operands contracted in fp64: the projection is exact up to fp32 accumulation, then rounded
+    to fp16 (as the kernel stores it in its shared-memory tile), softmax in fp32, P and O rounded to fp16."""
+    from qa_tiger_b200 import _cabi
+    P, H, D, K = 14, 8, 512, 512
+    g = torch.Generator().manual_seed(nf + int(cross))
+    x = (torch.randn(nf * P, K, generator=g) * 0.5).half()
+    w = (torch.randn((2 if cross else 3) * D, K, generator=g) * 0.05).half()
+    b = torch.randn((2 if cross else 3) * D, generator=g) * 0.1
+    q = torch.randn(nf, 2, D, generator=g).half() if cross else None
+    o = _cabi.gemm_attn(x.cuda(), w.cuda(), b.cuda(), P, H, q=None if q is None else q.cuda()).float().cpu()
+    proj = (x.double() @ w.double().t() + b.double()).half().double()                       # the tile is stored as fp16
+    if cross:
+        qq, kk, vv = q.double().view(nf, 2, H, 64), proj[:, :D].view(nf, P, H, 64), proj[:, D:].view(nf, P, H, 64)
+    else:
+        qq, kk, vv = (proj[:, i * D:(i + 1) * D].view(nf, P, H, 64) for i in range(3))
+    s_ = torch.einsum("nihd,njhd->nhij", qq, kk) * 0.125
+    ref = torch.einsum("nhij,njhd->nihd", torch.softmax(s_, -1), vv).reshape(o.shape)
+    assert relerr(o, ref) < 2e-3, relerr(o, ref)                                            # P and O are fp16 (11 bits)
