@@ -290,7 +290,8 @@ int qat_qst_grounding_head_fwd(const QatGroundArgs* a);
 typedef struct {
   int32_t N, t, C;          /* metric [N,t,C] */
   int32_t r;                /* requested; clamped as merge.py:43-44 */
-  int32_t class_token;
+  int32_t class_token;      /* protected-token flags: bit 0 = token 0 is a class token (merge.py:54-55, 66-68), bit 1 = token 1 is a
+                               distillation token (merge.py:56-57); the same flag word wherever `class_token` appears below */
   void* stream;
   const float* metric;
   int32_t* unm_idx;         /* [N, ceil(t/2)-r'] */
@@ -308,6 +309,7 @@ enum { QAT_TOME_MODE_WAVG = 0, /* merge_wavg: x*size summed / summed size */
 typedef struct {
   int32_t N, t, C, r;       /* r = clamped */
   int32_t mode;             /* QAT_TOME_MODE_* */
+  int32_t distill_token;    /* 1: output rows ordered [unm_0, dst_0, unm_1.., dst_1..] (merge.py:77-78) instead of [unm | dst] */
   void* stream;
   const float* x;           /* [N,t,C] */
   const float* size;        /* [N,t] or NULL (= ones); WAVG only */

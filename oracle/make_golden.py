@@ -207,6 +207,25 @@ def gen_tome():
         d[f"{nm}.xo"], d[f"{nm}.so"] = xo.numpy(), so.numpy()
     np.savez_compressed(os.path.join(OUT, "tome.npz"), **d)
     print("tome ok", k, "steps")
+    # (3) distillation token (merge.py:56-57, 77-78; never set by the extractor): single steps, with and without the class token
+    dd = {}
+    cases = {"d_a": (3, 27, 64, 25, True), "d_b": (2, 52, 64, 10, False), "d_c": (2, 577, 64, 25, True), "d_d": (1, 4, 64, 25, True),
+             "d_e": (2, 197, 64, 25, True)}
+    for nm, (n, t, c, r, cls) in cases.items():
+        metric = torch.randn(n, t, c, generator=g)
+        xx = torch.randn(n, t, 32, generator=g)
+        merge, _ = rm.bipartite_soft_matching(metric, r, class_token=cls, distill_token=True)
+        cells = {k2: c2.cell_contents for k2, c2 in zip(merge.__code__.co_freevars, merge.__closure__)}
+        xo, so = rm.merge_wavg(merge, xx, None)
+        dd[f"{nm}.cfg"] = np.array([n, t, c, r, int(cls)])
+        dd[f"{nm}.metric"], dd[f"{nm}.x"] = metric.numpy(), xx.numpy()
+        for kk in ("unm", "src", "dst"):
+            dd[f"{nm}.{kk}"] = cells[kk + "_idx"][..., 0].numpy().astype(np.int16)
+        dd[f"{nm}.xo"], dd[f"{nm}.so"] = xo.numpy(), so.numpy()
+        dd[f"{nm}.mean"] = merge(xx, mode="mean").numpy()
+        dd[f"{nm}.group"] = rm.merge_source(merge, xx, None).argmax(dim=1).numpy().astype(np.int16)
+    np.savez_compressed(os.path.join(OUT, "tome_distill.npz"), **dd)
+    print("tome distill ok")
 
 
 def load_reference_tome_patch():

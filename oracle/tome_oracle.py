@@ -51,7 +51,14 @@ def match(metric: Tensor, r: int, class_token: bool = True, distill_token: bool 
     return unm_idx, src_idx, dst_idx, node_max, node_idx
 
 
-def merge_apply(x: Tensor, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, mode: str = "sum") -> Tensor:
+def _cat(unm: Tensor, dst: Tensor, distill_token: bool) -> Tensor:
+    """merge.py:77-80: with a distillation token the class and distillation tokens lead the merged sequence"""
+    if distill_token:
+        return torch.cat([unm[:, :1], dst[:, :1], unm[:, 1:], dst[:, 1:]], dim=1)
+    return torch.cat([unm, dst], dim=1)
+
+
+def merge_apply(x: Tensor, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, mode: str = "sum", distill_token: bool = False) -> Tensor:
     """merge closure (:70-80): out = [A[unm_idx], B scatter-reduced with A[src_idx] at dst_idx]."""
     N, t, C = x.shape
     A, Bs = x[:, 0::2, :], x[:, 1::2, :].clone()
@@ -66,10 +73,10 @@ def merge_apply(x: Tensor, unm_idx: Tensor, src_idx: Tensor, dst_idx: Tensor, mo
                 Bs[n, d] = torch.maximum(Bs[n, d], src[n, k])
             else:
                 raise ValueError(mode)
-    return torch.cat([unm, Bs], dim=1)
+    return _cat(unm, Bs, distill_token)
 
 
-def merge_apply_fast(x, unm_idx, src_idx, dst_idx, mode="sum"):
+def merge_apply_fast(x, unm_idx, src_idx, dst_idx, mode="sum", distill_token=False):
     """Same result as merge_apply via index_add (used for the bigger cases; sum order may differ
     in the last bit when several sources hit one destination)."""
     N, t, C = x.shape
@@ -77,20 +84,20 @@ def merge_apply_fast(x, unm_idx, src_idx, dst_idx, mode="sum"):
     unm = torch.gather(A, 1, unm_idx[..., None].expand(-1, -1, C))
     src = torch.gather(A, 1, src_idx[..., None].expand(-1, -1, C))
     Bs = Bs.scatter_reduce(1, dst_idx[..., None].expand(-1, -1, C), src, reduce=mode)
-    return torch.cat([unm, Bs], dim=1)
+    return _cat(unm, Bs, distill_token)
 
 
-def merge_wavg(x: Tensor, size: Optional[Tensor], idx, fast: bool = True):
+def merge_wavg(x: Tensor, size: Optional[Tensor], idx, fast: bool = True, distill_token: bool = False):
     """merge.py:210-225: size-weighted mean.  size [N,t,1]."""
     if size is None:
         size = torch.ones_like(x[..., 0, None])
     f = merge_apply_fast if fast else merge_apply
-    xs = f(x * size, *idx, mode="sum")
-    size = f(size, *idx, mode="sum")
+    xs = f(x * size, *idx, mode="sum", distill_token=distill_token)
+    size = f(size, *idx, mode="sum", distill_token=distill_token)
     return xs / size, size
 
 
-def group_ids_update(group: Tensor, t: int, idx) -> Tensor:
+def group_ids_update(group: Tensor, t: int, idx, distill_token: bool = False) -> Tensor:
     """Integer form of merge_source (:228-241).  group [N,T0] holds, per ORIGINAL token, its current
     token position; after a merge step it holds the position in the merged sequence."""
     unm_idx, src_idx, dst_idx = idx
@@ -99,9 +106,13 @@ def group_ids_update(group: Tensor, t: int, idx) -> Tensor:
     n_unm = unm_idx.shape[1]
     newpos = torch.empty(N, t, dtype=torch.int64)
     for n in range(N):
-        newpos[n, 1::2] = n_unm + torch.arange(t // 2)
-        newpos[n, 2 * unm_idx[n]] = torch.arange(n_unm)
-        newpos[n, 2 * src_idx[n]] = n_unm + dst_idx[n]
+        pu, pd = torch.arange(n_unm), n_unm + torch.arange(t // 2)
+        if distill_token:                                           # [unm_0, dst_0, unm_1.., dst_1..]
+            pu = torch.where(pu > 0, pu + 1, pu)
+            pd[0] = 1
+        newpos[n, 1::2] = pd
+        newpos[n, 2 * unm_idx[n]] = pu
+        newpos[n, 2 * src_idx[n]] = pd[dst_idx[n]]
     return torch.gather(newpos, 1, group)
 
 

@@ -110,7 +110,7 @@ class TomeMatchArgs(C.Structure):
 
 
 class TomeMergeArgs(C.Structure):
-    _fields_ = [("N", C.c_int32), ("t", C.c_int32), ("C", C.c_int32), ("r", C.c_int32), ("mode", C.c_int32), ("stream", C.c_void_p),
+    _fields_ = [("N", C.c_int32), ("t", C.c_int32), ("C", C.c_int32), ("r", C.c_int32), ("mode", C.c_int32), ("distill_token", C.c_int32), ("stream", C.c_void_p),
                 ("x", C.c_void_p), ("size", C.c_void_p), ("unm_idx", C.c_void_p), ("src_idx", C.c_void_p),
                 ("dst_idx", C.c_void_p), ("x_out", C.c_void_p), ("size_out", C.c_void_p), ("group", C.c_void_p),
                 ("T0", C.c_int32), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]

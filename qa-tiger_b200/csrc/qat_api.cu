@@ -1069,7 +1069,7 @@ static int run_tome_merge(const QatTomeMergeArgs* a, Ctx& c) {
   StageRange nvtx_(c, "qat.tome.merge");
   QAT_REQUIRE(a->x && a->unm_idx && a->src_idx && a->dst_idx && a->x_out, "tome_merge: NULL tensor");
   return tome_merge(c, a->x, a->size, a->N, a->t, a->C, a->r, a->mode, a->unm_idx, a->src_idx, a->dst_idx, a->x_out,
-                    a->size_out, a->group, a->T0);
+                    a->size_out, a->group, a->T0, a->distill_token != 0);
 }
 
 static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
@@ -1118,11 +1118,11 @@ static int run_tome_chain(const QatTomeChainArgs* a, Ctx& c) {
     if (!fused || !have_metric) QAT_TRY(tome_metric(c, xcur, metric[mp], (long long)N * t, C));
     QAT_TRY(tome_match(c, metric[mp], N, t, 64, r, a->class_token, unm, src, dst));
     if (fused) {
-      QAT_TRY(tome_merge_wavg(c, xcur, scur, N, t, C, r, unm, src, dst, xb[pp], sb[pp], metric[mp ^ 1], a->group, a->t0));
+      QAT_TRY(tome_merge_wavg(c, xcur, scur, N, t, C, r, unm, src, dst, xb[pp], sb[pp], metric[mp ^ 1], a->group, a->t0, (a->class_token >> 1) & 1));
       mp ^= 1;
       have_metric = true;
     } else {
-      QAT_TRY(tome_merge(c, xcur, scur, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, xb[pp], sb[pp], a->group, a->t0));
+      QAT_TRY(tome_merge(c, xcur, scur, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, xb[pp], sb[pp], a->group, a->t0, (a->class_token >> 1) & 1));
     }
     xcur = xb[pp];
     scur = sb[pp];
@@ -1232,9 +1232,9 @@ static int tome_block_core(const QatTomeBlockArgs* a, Ctx& c, bool attn_only) {
     QAT_TRY(tome_match(c, metric, N, t, 64, r, a->class_token, unm, src, dst));
     QAT_TRY(act_alloc(c, X2, rows2, C, true, false));
     if (tome_merge_wavg_supported(C)) {
-      QAT_TRY(tome_merge_wavg(c, X1.f, a->size, N, t, C, r, unm, src, dst, X2.f, a->size_out, nullptr, a->group, a->T0));
+      QAT_TRY(tome_merge_wavg(c, X1.f, a->size, N, t, C, r, unm, src, dst, X2.f, a->size_out, nullptr, a->group, a->T0, (a->class_token >> 1) & 1));
     } else {
-      QAT_TRY(tome_merge(c, X1.f, a->size, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, X2.f, a->size_out, a->group, a->T0));
+      QAT_TRY(tome_merge(c, X1.f, a->size, N, t, C, r, QAT_TOME_WAVG, unm, src, dst, X2.f, a->size_out, a->group, a->T0, (a->class_token >> 1) & 1));
     }
   } else {
     X2 = X1;

@@ -16,14 +16,32 @@
 
 namespace qat {
 
+// `class_token` throughout this file is the protected-token flag word of the C ABI: bit 0 = token 0 is a class token
+// (merge.py:54-55, 66-68), bit 1 = token 1 is a distillation token (merge.py:56-57, 77-78)
 __host__ __device__ inline int tome_clamp_r(int t, int r, int class_token) {
-  int prot = class_token ? 1 : 0;
+  int prot = (class_token & 1) + ((class_token >> 1) & 1);
   int m = (t - prot) / 2;
   r = r < m ? r : m;
   return r > 0 ? r : 0;
 }
 
 constexpr int TOME_MAX_C = 64;   // metric channels held in registers per thread
+
+// Output row layout of merge(): [unm | dst], or with a distillation token [unm_0, dst_0, unm_1.., dst_1..] (merge.py:77-80).
+__device__ __forceinline__ int tome_pos_unm(int k, int distill) { return distill && k > 0 ? k + 1 : k; }
+__device__ __forceinline__ int tome_pos_dst(int j, int n_unm, int distill) { return distill ? (j == 0 ? 1 : n_unm + j) : n_unm + j; }
+// row -> (is it an unmerged A token?, index into unm_idx / B)
+__device__ __forceinline__ bool tome_row_is_unm(int row, int n_unm, int distill, int& idx) {
+  if (!distill) {
+    idx = row < n_unm ? row : row - n_unm;
+    return row < n_unm;
+  }
+  if (row == 0) { idx = 0; return true; }
+  if (row == 1) { idx = 0; return false; }
+  if (row <= n_unm) { idx = row - 1; return true; }
+  idx = row - n_unm;
+  return false;
+}
 
 // ---- T1 -------------------------------------------------------------------------------------------
 // One CTA per frame.  Thread (i, half) owns row i of set A (even tokens) and scans half of set B.
@@ -75,13 +93,14 @@ __global__ void __launch_bounds__(640) tome_match_kernel(const float* __restrict
 
   const int halfT = NT / 2;
   const int half = tid / halfT;
+  const bool cls = (class_token & 1) != 0, dis = (class_token & 2) != 0;
   const int jlo = half == 0 ? 0 : (tb + 1) / 2, jhi = half == 0 ? (tb + 1) / 2 : tb;
   for (int i = tid % halfT; i < ta; i += halfT) {
     float a[C];
     normalise(mf + (size_t)(2 * i) * C, a);
     float best = -INFINITY;
     int bidx = jlo;
-    int j = jlo;
+    int j = (dis && jlo == 0) ? 1 : jlo;                       // merge.py:57: column 0 (the distillation token) is -inf
     for (; j + 4 <= jhi; j += 4) {
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
       const float4* b0 = reinterpret_cast<const float4*>(Bs + (size_t)j * C);
@@ -115,7 +134,7 @@ __global__ void __launch_bounds__(640) tome_match_kernel(const float* __restrict
     int i0 = nidx[i];
     // the upper half of B only wins with a strictly larger score (first index on ties, merge.py:59)
     if (hmax[i] > m0) { m0 = hmax[i]; i0 = hidx[i]; }
-    if (class_token && i == 0) { m0 = -INFINITY; i0 = 0; }     // merge.py:55: whole row -inf -> argmax 0
+    if (cls && i == 0) { m0 = -INFINITY; i0 = 0; }             // merge.py:55: whole row -inf -> argmax 0
     nmax[i] = m0;
     nidx[i] = i0;
   }
@@ -140,7 +159,7 @@ __global__ void __launch_bounds__(640) tome_match_kernel(const float* __restrict
     if (rk < r) {
       src[rk] = i;
       dst[rk] = nidx[i];
-    } else if (!class_token) {
+    } else if (!(class_token & 1)) {
       unm[rk - r] = i;                                         // stays in sorted-score order
     } else {
       int pos = 0;                                             // merge.py:66-68: ascending token order
@@ -214,7 +233,8 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
   // ---- phase 2: scores = a . b (merge.py:52) and the running (max, first argmax) of every A row within a B segment ----
   {
     const int warp = tid >> 5, lane = tid & 31;
-    const int row0 = class_token ? 1 : 0;
+    const int row0 = (class_token & 1) ? 1 : 0;
+    const bool dis = (class_token & 2) != 0;
     const int aw_n = (ta - row0 + 32 * R - 1) / (32 * R);
     const int seg = warp / aw_n, aw = warp % aw_n;
     if (seg < nseg) {
@@ -256,7 +276,7 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
         }
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
-          if (j0 + jj < tb) {
+          if (j0 + jj < tb && !(dis && j0 + jj == 0)) {        // merge.py:57: column 0 (the distillation token) is -inf
 #pragma unroll
             for (int i = 0; i < R; ++i)
               if (sc[i][jj] > best[i]) { best[i] = sc[i][jj]; bidx[i] = j0 + jj; }
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
   for (int i = tid; i < ta; i += NT) {
     float m0 = -INFINITY;
     int i0 = 0;
-    if (!(class_token && i == 0)) {                            // merge.py:55: the class token's row is -inf -> argmax 0
+    if (!((class_token & 1) && i == 0)) {                      // merge.py:55: the class token's row is -inf -> argmax 0
       m0 = segmax[i];
       i0 = segidx[i];
       // a later segment only wins with a strictly larger score (first index on ties, merge.py:59)
@@ -305,7 +325,7 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
     if (rk < r) {
       src[rk] = i;
       dst[rk] = nidx[i];
-    } else if (!class_token) {
+    } else if (!(class_token & 1)) {
       unm[rk - r] = i;                                         // stays in sorted-score order
     } else {
       int pos = 0;                                             // merge.py:66-68: ascending token order
@@ -342,7 +362,7 @@ template <int V>
 __global__ void __launch_bounds__(256) tome_merge_kernel(const float* __restrict__ x, const float* __restrict__ size, int t, int C, int r, int mode,
                                                          const int* __restrict__ unm_idx, const int* __restrict__ src_idx,
                                                          const int* __restrict__ dst_idx, float* __restrict__ x_out,
-                                                         float* __restrict__ size_out, int* __restrict__ group, int T0) {
+                                                         float* __restrict__ size_out, int* __restrict__ group, int T0, int distill) {
   extern __shared__ __align__(16) int smi[];
   const int ta = (t + 1) / 2, tb = t / 2, n_unm = ta - r, t_out = t - r;
   int* s_src = smi;               // [r]
@@ -362,8 +382,9 @@ __global__ void __launch_bounds__(256) tome_merge_kernel(const float* __restrict
   typedef typename TVec<V>::T VT;
   for (int row = blockIdx.y * nwarp + warp; row < t_out; row += gridDim.y * nwarp) {
     float* xo = x_out + ((size_t)n * t_out + row) * C;
-    if (row < n_unm) {
-      const int tok = 2 * unm_idx[(size_t)n * n_unm + row];
+    int ri;
+    if (tome_row_is_unm(row, n_unm, distill, ri)) {
+      const int tok = 2 * unm_idx[(size_t)n * n_unm + ri];
       const float s = sf ? sf[tok] : 1.f;
       for (int c = lane; c < CV; c += 32) {
         VT v = TVec<V>::ld(xf + (size_t)tok * C + c * V);
@@ -372,7 +393,7 @@ __global__ void __launch_bounds__(256) tome_merge_kernel(const float* __restrict
       }
       if (wavg && lane == 0) size_out[(size_t)n * t_out + row] = s;
     } else {
-      const int j = row - n_unm;
+      const int j = ri;
       const int tok = 2 * j + 1;
       const float s0 = sf ? sf[tok] : 1.f;
       float stot = s0;
@@ -401,9 +422,9 @@ __global__ void __launch_bounds__(256) tome_merge_kernel(const float* __restrict
     }
   }
   if (group && blockIdx.y == 0) {
-    for (int j = tid; j < tb; j += blockDim.x) s_newpos[2 * j + 1] = n_unm + j;
-    for (int k = tid; k < n_unm; k += blockDim.x) s_newpos[2 * unm_idx[(size_t)n * n_unm + k]] = k;
-    for (int k = tid; k < r; k += blockDim.x) s_newpos[2 * s_src[k]] = n_unm + s_dst[k];
+    for (int j = tid; j < tb; j += blockDim.x) s_newpos[2 * j + 1] = tome_pos_dst(j, n_unm, distill);
+    for (int k = tid; k < n_unm; k += blockDim.x) s_newpos[2 * unm_idx[(size_t)n * n_unm + k]] = tome_pos_unm(k, distill);
+    for (int k = tid; k < r; k += blockDim.x) s_newpos[2 * s_src[k]] = tome_pos_dst(s_dst[k], n_unm, distill);
     __syncthreads();
     int* g = group + (size_t)n * T0;
     for (int o = tid; o < T0; o += blockDim.x) g[o] = s_newpos[g[o]];
@@ -420,7 +441,7 @@ __global__ void __launch_bounds__(256) tome_merge_wavg_kernel(const float* __res
                                                               const int* __restrict__ unm_idx, const int* __restrict__ src_idx,
                                                               const int* __restrict__ dst_idx, float* __restrict__ x_out,
                                                               float* __restrict__ size_out, float* __restrict__ metric_out,
-                                                              int* __restrict__ group, int T0) {
+                                                              int* __restrict__ group, int T0, int distill) {
   extern __shared__ __align__(16) int smi[];
   constexpr int C = 64 * G;
   const int ta = (t + 1) / 2, tb = t / 2, n_unm = ta - r, t_out = t - r;
@@ -445,8 +466,9 @@ __global__ void __launch_bounds__(256) tome_merge_wavg_kernel(const float* __res
   for (int row = blockIdx.y * nhw + hw; row < t_out; row += gridDim.y * nhw) {
     float4 v[G];
     float stot;
-    if (row < n_unm) {
-      const int tok = 2 * unm_idx[(size_t)n * n_unm + row];
+    int ri;
+    if (tome_row_is_unm(row, n_unm, distill, ri)) {
+      const int tok = 2 * unm_idx[(size_t)n * n_unm + ri];
       load_row(tok, v);
       stot = sf ? sf[tok] : 1.f;
 #pragma unroll
@@ -454,7 +476,7 @@ __global__ void __launch_bounds__(256) tome_merge_wavg_kernel(const float* __res
         v[g].x = __fmul_rn(v[g].x, stot); v[g].y = __fmul_rn(v[g].y, stot); v[g].z = __fmul_rn(v[g].z, stot); v[g].w = __fmul_rn(v[g].w, stot);
       }
     } else {
-      const int j = row - n_unm;
+      const int j = ri;
       const int tok = 2 * j + 1;
       load_row(tok, v);
       const float s0 = sf ? sf[tok] : 1.f;
@@ -500,9 +522,9 @@ __global__ void __launch_bounds__(256) tome_merge_wavg_kernel(const float* __res
     if (l16 == 0) size_out[(size_t)n * t_out + row] = stot;
   }
   if (group && blockIdx.y == 0) {
-    for (int j = tid; j < tb; j += blockDim.x) s_newpos[2 * j + 1] = n_unm + j;
-    for (int k = tid; k < n_unm; k += blockDim.x) s_newpos[2 * unm_idx[(size_t)n * n_unm + k]] = k;
-    for (int k = tid; k < r; k += blockDim.x) s_newpos[2 * s_src[k]] = n_unm + s_dst[k];
+    for (int j = tid; j < tb; j += blockDim.x) s_newpos[2 * j + 1] = tome_pos_dst(j, n_unm, distill);
+    for (int k = tid; k < n_unm; k += blockDim.x) s_newpos[2 * unm_idx[(size_t)n * n_unm + k]] = tome_pos_unm(k, distill);
+    for (int k = tid; k < r; k += blockDim.x) s_newpos[2 * s_src[k]] = tome_pos_dst(s_dst[k], n_unm, distill);
     __syncthreads();
     int* g = group + (size_t)n * T0;
     for (int o = tid; o < T0; o += blockDim.x) g[o] = s_newpos[g[o]];
@@ -545,7 +567,7 @@ inline int tome_match(Ctx& c, const float* metric, int N, int t, int C, int r, i
   // register-tiled kernel whenever the frame's normalised rows fit one CTA's shared memory (t <= ~700)
   {
     const int ta = (t + 1) / 2, tb = t / 2;
-    const int rows = ta - (class_token ? 1 : 0);
+    const int rows = ta - ((class_token & 1) ? 1 : 0);
     int R = 4;                                                // the tile height that pads the A rows least (ties: the taller)
     for (int cand = 3; cand >= 2; --cand)
       if ((rows + 32 * cand - 1) / (32 * cand) * cand < (rows + 32 * R - 1) / (32 * R) * R) R = cand;
@@ -575,7 +597,7 @@ inline int tome_match(Ctx& c, const float* metric, int N, int t, int C, int r, i
 }
 
 inline int tome_merge(Ctx& c, const float* x, const float* size, int N, int t, int C, int r, int mode, const int* unm, const int* src,
-                      const int* dst, float* x_out, float* size_out, int* group, int T0) {
+                      const int* dst, float* x_out, float* size_out, int* group, int T0, int distill = 0) {
   QAT_REQUIRE(mode >= QAT_TOME_WAVG && mode <= QAT_TOME_AMAX, "tome_merge: unknown mode %d", mode);
   QAT_REQUIRE(r > 0 && r <= t / 2, "tome_merge: bad r=%d for t=%d", r, t);
   QAT_REQUIRE(mode != QAT_TOME_WAVG || size_out, "tome_merge: size_out missing");
@@ -586,16 +608,16 @@ inline int tome_merge(Ctx& c, const float* x, const float* size, int N, int t, i
   dim3 grid(N, rs);
   const bool vec = (C % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out)) % 16 == 0);
   if (vec)
-    tome_merge_kernel<4><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0);
+    tome_merge_kernel<4><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0, distill);
   else
-    tome_merge_kernel<1><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0);
+    tome_merge_kernel<1><<<grid, 256, smem, c.stream>>>(x, size, t, C, r, mode, unm, src, dst, x_out, size_out, group, T0, distill);
   return check_launch("tome_merge_kernel");
 }
 
 // chain step: merge_wavg + the next step's metric (metric_out may be NULL).  C must be 64*G with G in {4, 8, 16}.
 inline bool tome_merge_wavg_supported(int C) { return C == 256 || C == 512 || C == 1024; }
 inline int tome_merge_wavg(Ctx& c, const float* x, const float* size, int N, int t, int C, int r, const int* unm, const int* src,
-                           const int* dst, float* x_out, float* size_out, float* metric_out, int* group, int T0) {
+                           const int* dst, float* x_out, float* size_out, float* metric_out, int* group, int T0, int distill = 0) {
   QAT_REQUIRE(tome_merge_wavg_supported(C), "tome_merge_wavg: C=%d unsupported", C);
   QAT_REQUIRE(r > 0 && r <= t / 2 && size_out, "tome_merge_wavg: bad r=%d for t=%d or size_out missing", r, t);
   QAT_REQUIRE((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(x_out) | reinterpret_cast<uintptr_t>(metric_out)) % 16 == 0,
@@ -605,9 +627,9 @@ inline int tome_merge_wavg(Ctx& c, const float* x, const float* size, int N, int
   while ((long long)N * rs < 148 * 4 && rs < 64) rs *= 2;
   const size_t smem = ((size_t)2 * r + t) * 4 + 16;
   dim3 grid(N, rs);
-  if (C == 1024) tome_merge_wavg_kernel<16><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0);
-  else if (C == 512) tome_merge_wavg_kernel<8><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0);
-  else tome_merge_wavg_kernel<4><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0);
+  if (C == 1024) tome_merge_wavg_kernel<16><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0, distill);
+  else if (C == 512) tome_merge_wavg_kernel<8><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0, distill);
+  else tome_merge_wavg_kernel<4><<<grid, 256, smem, c.stream>>>(x, size, t, r, unm, src, dst, x_out, size_out, metric_out, group, T0, distill);
   return check_launch("tome_merge_wavg_kernel");
 }
 

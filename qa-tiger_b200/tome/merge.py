@@ -7,7 +7,8 @@ plus the index-form API the kernels really speak (`match`, `merge_with`, `chain`
 
 Indices are bit-identical to the reference's (tests/test_gpu_tome.py); they are int64 `[N,k,1]` tensors
 on the closures (`merge.unm_idx`, `.src_idx`, `.dst_idx`) exactly like the reference's closure cells.
-`distill_token=True` is not built (the extractor never sets it: timm.py:48-53) and raises.
+`distill_token=True` (merge.py:56-57, 77-78; the extractor never sets it, timm.py:48-53) is carried as bit 1 of the C ABI's
+protected-token flag word; `unmerge` keeps the reference's own (distill-unaware) row split.
 """
 from __future__ import annotations
 
@@ -25,15 +26,19 @@ def do_nothing(x, mode=None):
     return x
 
 
-def clamp_r(t: int, r: int, class_token: bool = False) -> int:
-    return cabi.lib().qat_tome_clamp_r(int(t), int(r), int(bool(class_token)))
+def _flags(class_token, distill_token=False) -> int:
+    return int(bool(class_token)) | (2 if distill_token else 0)
 
 
-def match(metric: torch.Tensor, r: int, class_token: bool = False):
+def clamp_r(t: int, r: int, class_token: bool = False, distill_token: bool = False) -> int:
+    return cabi.lib().qat_tome_clamp_r(int(t), int(r), _flags(class_token, distill_token))
+
+
+def match(metric: torch.Tensor, r: int, class_token: bool = False, distill_token: bool = False):
     """metric [N,t,64] fp32 -> (unm_idx [N,ta-r], src_idx [N,r], dst_idx [N,r]) int32, or None when r clamps to 0."""
     cabi.require_cuda_f32(metric, "metric")
     N, t, Cc = metric.shape
-    rr = clamp_r(t, r, class_token)
+    rr = clamp_r(t, r, class_token, distill_token)
     if rr <= 0:
         return None
     ta = (t + 1) // 2
@@ -42,7 +47,7 @@ def match(metric: torch.Tensor, r: int, class_token: bool = False):
     src = torch.empty(N, rr, dtype=torch.int32, device=dev)
     dst = torch.empty(N, rr, dtype=torch.int32, device=dev)
     a = cabi.TomeMatchArgs()
-    a.N, a.t, a.C, a.r, a.class_token = N, t, Cc, r, int(bool(class_token))
+    a.N, a.t, a.C, a.r, a.class_token = N, t, Cc, r, _flags(class_token, distill_token)
     a.stream, a.metric = cabi.stream_ptr(dev), metric.data_ptr()
     a.unm_idx, a.src_idx, a.dst_idx = unm.data_ptr(), src.data_ptr(), dst.data_ptr()
     with torch.cuda.device(dev):
@@ -51,7 +56,7 @@ def match(metric: torch.Tensor, r: int, class_token: bool = False):
 
 
 def merge_with(x: torch.Tensor, idx, mode: str = "wavg", size: Optional[torch.Tensor] = None,
-               group: Optional[torch.Tensor] = None):
+               group: Optional[torch.Tensor] = None, distill_token: bool = False):
     """Apply one merge step.  mode 'wavg' returns (x_out, size_out [N,t-r,1]); other modes return x_out."""
     unm, src, dst = idx
     cabi.require_cuda_f32(x, "x")
@@ -61,6 +66,7 @@ def merge_with(x: torch.Tensor, idx, mode: str = "wavg", size: Optional[torch.Te
     out = torch.empty(N, t - r, Cc, dtype=torch.float32, device=dev)
     a = cabi.TomeMergeArgs()
     a.N, a.t, a.C, a.r, a.mode, a.stream = N, t, Cc, r, MODES[mode], cabi.stream_ptr(dev)
+    a.distill_token = int(bool(distill_token))
     a.x, a.unm_idx, a.src_idx, a.dst_idx, a.x_out = x.data_ptr(), unm.data_ptr(), src.data_ptr(), dst.data_ptr(), out.data_ptr()
     size_out = None
     if mode == "wavg":
@@ -81,9 +87,7 @@ def merge_with(x: torch.Tensor, idx, mode: str = "wavg", size: Optional[torch.Te
 
 def bipartite_soft_matching(metric: torch.Tensor, r: int, class_token: bool = False,
                             distill_token: bool = False) -> Tuple[Callable, Callable]:
-    if distill_token:
-        raise RuntimeError("bipartite_soft_matching: distill_token=True is not built on the B200 path")
-    idx = match(metric, r, class_token)
+    idx = match(metric, r, class_token, distill_token)
     if idx is None:
         return do_nothing, do_nothing
     unm, src, dst = idx
@@ -91,7 +95,7 @@ def bipartite_soft_matching(metric: torch.Tensor, r: int, class_token: bool = Fa
     rr = src.shape[1]
 
     def merge(x: torch.Tensor, mode="mean") -> torch.Tensor:
-        return merge_with(x.contiguous().float(), idx, mode)
+        return merge_with(x.contiguous().float(), idx, mode, distill_token=distill_token)
 
     def unmerge(x: torch.Tensor) -> torch.Tensor:                     # merge.py:82-95 (not on the hot path)
         unm_len = unm.shape[1]
@@ -105,6 +109,7 @@ def bipartite_soft_matching(metric: torch.Tensor, r: int, class_token: bool = Fa
         return out
 
     merge.idx = idx
+    merge.distill_token = bool(distill_token)
     merge.unm_idx, merge.src_idx, merge.dst_idx = (i.long()[..., None] for i in idx)
     return merge, unmerge
 
@@ -114,7 +119,7 @@ def merge_wavg(merge: Callable, x: torch.Tensor, size: Optional[torch.Tensor] = 
         if size is None:
             size = torch.ones_like(x[..., 0, None])
         return x, size
-    return merge_with(x.contiguous().float(), merge.idx, "wavg", size)
+    return merge_with(x.contiguous().float(), merge.idx, "wavg", size, distill_token=getattr(merge, "distill_token", False))
 
 
 def merge_source(merge: Callable, x: torch.Tensor, source: Optional[torch.Tensor] = None) -> torch.Tensor:

@@ -103,16 +103,15 @@ class ToMeBlock(_QatModule):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         self._guard()
         info = self._tome_info
-        if info.get("distill_token"):
-            raise RuntimeError("ToMeBlock: distill_token=True is not built on the B200 path")
+        flags = int(bool(info["class_token"])) | (2 if info.get("distill_token") else 0)     # the C ABI's protected-token flag word
         prec = self._prec()
         w = self._prepared(prec)
         N, t, Cc = x.shape
         cabi.require_cuda_f32(x, "x", (N, t, Cc))
         r = info["r"].pop(0)
-        rr = cabi.lib().qat_tome_clamp_r(t, r, int(info["class_token"])) if r > 0 else 0
+        rr = cabi.lib().qat_tome_clamp_r(t, r, flags) if r > 0 else 0
         a = cabi.TomeBlockArgs()
-        a.N, a.t, a.C, a.H, a.r, a.class_token, a.prop_attn, a.prec, a.eps = (N, t, Cc, self.attn.num_heads, r, int(info["class_token"]),
+        a.N, a.t, a.C, a.H, a.r, a.class_token, a.prop_attn, a.prec, a.eps = (N, t, Cc, self.attn.num_heads, r, flags,
                                                                            int(bool(info["prop_attn"])), prec, self.eps)
         a.x = x.data_ptr()
         size = info["size"]
@@ -156,12 +155,12 @@ class ToMeStack(nn.Module):
     """A list of ToMeBlocks run with one r schedule: the bookkeeping of ToMeVisionTransformer.forward (timm.py:118-125)."""
 
     def __init__(self, blocks: List[ToMeBlock], r: Union[List[int], Tuple[int, float], int] = 0, trace_source: bool = False,
-                 prop_attn: bool = True, class_token: bool = True):
+                 prop_attn: bool = True, class_token: bool = True, distill_token: bool = False):
         super().__init__()
         self.blocks = nn.ModuleList(blocks)
         self.r = r
         self._tome_info = dict(r=[0], size=None, source=None, trace_source=trace_source, prop_attn=prop_attn, class_token=class_token,
-                               distill_token=False)
+                               distill_token=distill_token)
         for b in self.blocks:
             b._tome_info = self._tome_info
 

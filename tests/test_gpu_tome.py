@@ -90,8 +90,8 @@ def test_r_zero_and_errors():
     m = torch.randn(1, 1, 64, device=dev())
     merge, unmerge = tm.bipartite_soft_matching(m, 25, class_token=True)
     assert merge is tm.do_nothing
-    with pytest.raises(RuntimeError, match="distill"):
-        tm.bipartite_soft_matching(torch.randn(1, 8, 64, device=dev()), 2, distill_token=True)
+    merge, _ = tm.bipartite_soft_matching(torch.randn(1, 3, 64, device=dev()), 2, class_token=True, distill_token=True)
+    assert merge is tm.do_nothing                                  # (3 - 2 protected) // 2 = 0
     with pytest.raises(RuntimeError, match="C="):
         tm.bipartite_soft_matching(torch.randn(1, 8, 48, device=dev()), 2)
 
@@ -108,3 +108,23 @@ def test_chain_frames_side_streams_match_serial_chunks():
     torch.cuda.synchronize()
     for u, v, w in zip(a, b, c):
         assert torch.equal(u, v) and torch.equal(u, w)
+
+
+@pytest.mark.parametrize("nm", ["d_a", "d_b", "d_c", "d_d", "d_e"])
+def test_single_steps_with_distill_token_bit_exact(nm):
+    """bipartite_soft_matching(distill_token=True) (merge.py:56-57, 77-78) against goldens of the real reference: indices, merge_wavg
+    values and sizes, the bare mean-mode closure and the merge_source groups, all bit-exact."""
+    tm = _tm()
+    g = golden("tome_distill")
+    n, t, c, r, cls = g[nm + ".cfg"].tolist()
+    metric, x = torch.as_tensor(g[nm + ".metric"]).to(dev()), torch.as_tensor(g[nm + ".x"]).to(dev())
+    merge, _ = tm.bipartite_soft_matching(metric, r, class_token=bool(cls), distill_token=True)
+    for key in ("unm", "src", "dst"):
+        assert getattr(merge, key + "_idx")[..., 0].cpu().tolist() == g[f"{nm}.{key}"].astype(np.int64).tolist(), key
+    xo, so = tm.merge_wavg(merge, x, None)
+    assert torch.equal(xo.cpu(), torch.as_tensor(g[nm + ".xo"]))
+    assert torch.equal(so.cpu(), torch.as_tensor(g[nm + ".so"]))
+    assert torch.equal(merge(x, mode="mean").cpu(), torch.as_tensor(g[nm + ".mean"]))
+    group = torch.arange(t, dtype=torch.int32, device=dev())[None, :].expand(n, t).contiguous()
+    tm.merge_with(x, merge.idx, "wavg", None, group=group, distill_token=True)
+    assert group.cpu().tolist() == g[nm + ".group"].astype(np.int64).tolist()

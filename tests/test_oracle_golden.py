@@ -106,6 +106,26 @@ def test_tome_single_steps(nm):
         assert torch.equal(so, torch.as_tensor(g[nm + ".so"]))
 
 
+@pytest.mark.parametrize("nm", ["d_a", "d_b", "d_c", "d_d", "d_e"])
+def test_tome_single_steps_with_distill_token(nm):
+    """merge.py:56-57, 77-78: the distillation token (b-token 0) is never a merge destination and the merged sequence starts
+    [unm_0, dst_0, ...]; goldens from the real bipartite_soft_matching(distill_token=True)."""
+    g = np.load(os.path.join(GOLDEN, "tome_distill.npz"))
+    n, t, c, r, cls = g[nm + ".cfg"].tolist()
+    metric, x = torch.as_tensor(g[nm + ".metric"]), torch.as_tensor(g[nm + ".x"])
+    res = TO.match(metric, r, class_token=bool(cls), distill_token=True)
+    assert res is not None
+    for got, key in zip(res[:3], ("unm", "src", "dst")):
+        assert got.tolist() == g[f"{nm}.{key}"].astype(np.int64).tolist(), key
+    assert not (res[2] == 0).any()                                   # nothing merges into the distillation token
+    for fast in (True, False):
+        xo, so = TO.merge_wavg(x, None, res[:3], fast=fast, distill_token=True)
+        assert relerr(xo, g[nm + ".xo"]) < 1e-6
+        assert torch.equal(so, torch.as_tensor(g[nm + ".so"]))
+    group = TO.group_ids_update(torch.arange(t)[None, :].expand(n, t).contiguous(), t, res[:3], distill_token=True)
+    assert group.tolist() == g[nm + ".group"].astype(np.int64).tolist()
+
+
 @pytest.mark.parametrize("nm", ["b197", "b577"])
 def test_tome_vit_block_matches_reference(nm):
     """the oracle's ToMeAttention / ToMeBlock restatement against the real tome/patch/timm.py (goldens minted with
