@@ -266,8 +266,9 @@ typedef struct {
 } QatMoeArgs;
 int qat_temp_moe_fwd(const QatMoeArgs* a);
 
-/* ---- G1 (x1) : QstGrounding.forward, modules.py:304-347, on a length-2 sequence; optionally
- *      followed by H1: head(relu(.)) net.py:141-142 ------------------------------------------ */
+/* ---- G1 (x1) : QstGrounding.forward, modules.py:304-347; optionally followed by H1: head(relu(.)) net.py:141-142.
+ *      Two forms: the length-2 data list of both call sites (net.py:136, 138) as d0 / d1, or any concatenated sequence as
+ *      `data` [B,S,D] with S >= 1 (modules.py:318-326 accept any list of [B,S_i,D] tensors) ---------------------------------- */
 typedef struct {
   int32_t B, D, H;
   int32_t prec;
@@ -275,6 +276,8 @@ typedef struct {
   const float* qst;        /* [B,D] */
   const float* d0;         /* [B,D] first element of the data list */
   const float* d1;         /* [B,D] second */
+  const float* data;       /* general form: [B,S,D] contiguous (d0 / d1 ignored); NULL selects the d0 / d1 form */
+  int32_t S;
   QatLinearW attn_q, attn_kv, attn_out, mlp0, mlp2;
   QatLayerNormW norm;
   float* out;              /* [B,D] */

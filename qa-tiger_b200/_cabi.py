@@ -89,7 +89,7 @@ class MoeArgs(C.Structure):
 
 class GroundArgs(C.Structure):
     _fields_ = [("B", C.c_int32), ("D", C.c_int32), ("H", C.c_int32), ("prec", C.c_int32), ("stream", C.c_void_p),
-                ("qst", C.c_void_p), ("d0", C.c_void_p), ("d1", C.c_void_p),
+                ("qst", C.c_void_p), ("d0", C.c_void_p), ("d1", C.c_void_p), ("data", C.c_void_p), ("S", C.c_int32),
                 ("attn_q", LinearW), ("attn_kv", LinearW), ("attn_out", LinearW), ("mlp0", LinearW), ("mlp2", LinearW),
                 ("norm", LayerNormW), ("out", C.c_void_p), ("has_head", C.c_int32), ("head", LinearW),
                 ("logits", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]

@@ -870,7 +870,59 @@ static int ground_core(const QatGroundArgs* a, int B, Ctx& c, const float* qst, 
   return QAT_OK;
 }
 
+// QstGrounding over any sequence: data [B, S, D] (the concatenated list of modules.py:318-326).  Off the eval path (both call
+// sites have S = 2, ground_core above): plain composition of the exported pieces.
+static int ground_general(const QatGroundArgs* a, Ctx& c) {
+  StageRange nvtx_(c, "qat.qst_grounding");
+  const int B = a->B, S = a->S, D = a->D, H = a->H;
+  QAT_REQUIRE(B >= 1 && S >= 1 && D == H * 64, "qst_grounding: need B, S >= 1 and D==H*64");
+  QAT_TRY(check_w(a->attn_q, D, D, "ground.attn_q", c.prec));
+  QAT_TRY(check_w(a->attn_kv, 2 * D, D, "ground.attn_kv", c.prec));
+  QAT_TRY(check_w(a->attn_out, D, D, "ground.attn_out", c.prec));
+  QAT_TRY(check_w(a->mlp0, D / 2, D, "ground.mlp0", c.prec));
+  QAT_TRY(check_w(a->mlp2, D, D / 2, "ground.mlp2", c.prec));
+  const long long BS = (long long)B * S;
+  Act KV, Q, O, A1, Hm, Mo, Mean;
+  QAT_TRY(act_alloc(c, KV, BS, 2 * D, true, false));
+  QAT_TRY(linear_core(c, a->attn_kv, act_of(a->data, D), BS, 0, KV));
+  QAT_TRY(act_alloc(c, Q, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, act_of(a->qst, D), B, wview(a->attn_q), Epi(), Q));
+  QAT_TRY(act_alloc(c, O, B, D, true, false));
+  AttnP p;
+  p.nseq = B; p.H = H; p.Lq = 1; p.Lk = S; p.scale = 0.125f;
+  p.q = Q.f; p.q_sn = Q.ld; p.q_si = Q.ld;
+  p.k = KV.f; p.v = KV.f + D; p.k_sn = (long long)S * 2 * D; p.k_si = 2 * D; p.k_shift = 0; p.k_mod = B;
+  p.o = O; p.o_rn = 1; p.o_ri = 1; p.attw = nullptr;
+  QAT_TRY(attention(c, p));
+  QAT_TRY(act_alloc(c, A1, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, O, B, wview(a->attn_out), Epi(), A1));
+  QAT_TRY(act_alloc(c, Hm, B, D / 2, true, false));
+  {
+    Epi e;
+    e.relu = 1;
+    QAT_TRY(gemm(c, G_SIMT, A1, B, wview(a->mlp0), e, Hm));
+  }
+  QAT_TRY(act_alloc(c, Mo, B, D, true, false));
+  QAT_TRY(gemm(c, G_SIMT, Hm, B, wview(a->mlp2), Epi(), Mo));
+  // feat = mean_seq(data) + mlp(attn) -> LN   (:344-346)
+  QAT_TRY(act_alloc(c, Mean, B, D, true, false));
+  QAT_TRY(mean_seq(c, a->data, Mean.f, B, S, D));
+  QAT_TRY(ln(c, Mean.f, D, nullptr, 0, Mo.f, D, 1.f, a->norm, act_of(a->out, D), B, D));
+  if (a->has_head) {
+    QAT_REQUIRE((c.dry || a->logits) && a->head.w && a->head.k == D, "qst_grounding: head weights/logits missing");
+    Act R;
+    QAT_TRY(act_alloc(c, R, B, D, true, false));
+    if (!c.dry) QAT_TRY(relu_rows(c, a->out, R.f, (long long)B * D));
+    QAT_TRY(gemm(c, G_SIMT, R, B, wview(a->head), Epi(), act_of(a->logits, a->head.n)));
+  }
+  return QAT_OK;
+}
+
 static int run_ground(const QatGroundArgs* a, Ctx& c) {
+  if (a->data) {
+    QAT_REQUIRE(c.dry || (a->qst && a->out), "qst_grounding: NULL tensor");
+    return ground_general(a, c);
+  }
   QAT_REQUIRE(c.dry || (a->qst && a->d0 && a->d1 && a->out), "qst_grounding: NULL tensor");
   return ground_core(a, a->B, c, a->qst, a->d0, a->d1, a->out, a->has_head != 0, a->logits);
 }

@@ -136,6 +136,29 @@ inline int widen_f16(Ctx& c, const __half* x, float* y, long long n) {
   return check_launch("widen_f16_kernel");
 }
 
+// out[b, :] = mean_s x[b, s, :]  (x [B, S, D] contiguous; the sum runs over s in order, then one division)
+__global__ void __launch_bounds__(256) mean_seq_kernel(const float* __restrict__ x, float* __restrict__ out, long long B, int S, int D4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * D4) return;
+  const long long b = i / D4;
+  const int c4 = (int)(i % D4);
+  const float4* p = reinterpret_cast<const float4*>(x + b * S * D4 * 4) + c4;
+  float4 a = __ldg(p);
+  for (int s = 1; s < S; ++s) {
+    const float4 v = __ldg(p + (long long)s * D4);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+  }
+  const float inv = (float)S;
+  reinterpret_cast<float4*>(out)[i] = make_float4(a.x / inv, a.y / inv, a.z / inv, a.w / inv);
+}
+inline int mean_seq(Ctx& c, const float* x, float* out, long long B, int S, int D) {
+  QAT_REQUIRE(D % 4 == 0 && S >= 1, "mean_seq: D=%d must be a multiple of 4", D);
+  if (c.dry || B == 0) return QAT_OK;
+  const long long n = B * (D / 4);
+  mean_seq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, c.stream>>>(x, out, B, S, D / 4);
+  return check_launch("mean_seq_kernel");
+}
+
 __global__ void __launch_bounds__(256) relu_kernel(const float* __restrict__ x, float* __restrict__ y, long long n) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = fmaxf(x[i], 0.f);

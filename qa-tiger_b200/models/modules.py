@@ -221,17 +221,20 @@ class QstGrounding(_QatModule):
             parts = [d.reshape(d.shape[0], -1, d.shape[-1]) for d in data]
             data = parts[0] if len(parts) == 1 else torch.cat(parts, dim=1)
         B, S, D = data.shape
-        if S != 2:
-            raise RuntimeError(f"QstGrounding: the B200 path is built for the length-2 sequences of net.py:136-138, got {S}")
-        d0, d1 = data[:, 0].contiguous(), data[:, 1].contiguous()
         qst = qst.reshape(B, D)
         cabi.require_cuda_f32(qst, "qst", (B, D))
-        cabi.require_cuda_f32(d0, "data[0]", (B, D))
         out = torch.empty(B, D, device=qst.device, dtype=torch.float32)
         a = cabi.GroundArgs()
         a.B, a.prec = B, prec
         hold = self.fill_weights(a, prec, head)
-        a.qst, a.d0, a.d1 = qst.data_ptr(), d0.data_ptr(), d1.data_ptr()
+        if S == 2:                                  # both call sites of the forward (net.py:136, 138): the fused length-2 form
+            d0, d1 = data[:, 0].contiguous(), data[:, 1].contiguous()
+            cabi.require_cuda_f32(d0, "data[0]", (B, D))
+            a.qst, a.d0, a.d1 = qst.data_ptr(), d0.data_ptr(), d1.data_ptr()
+        else:                                       # any other concatenated sequence (modules.py:318-326)
+            data = data.contiguous()
+            cabi.require_cuda_f32(data, "data", (B, S, D))
+            a.qst, a.data, a.S = qst.data_ptr(), data.data_ptr(), S
         a.out = out.data_ptr()
         logits = None
         if head is not None:

@@ -142,6 +142,29 @@ def test_qst_grounding_and_head(sd, prec, B):
     assert relerr(feat, ref) < TOL[prec] and relerr(logits, rl) < TOL[prec]
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_qst_grounding_any_sequence_length(sd, prec):
+    """modules.py:318-326: `data` may be any list of [B, S_i, D] tensors (or one tensor); the forward's two call sites use two
+    length-1 entries, every other length runs the general form."""
+    M = _mods()
+    m = M.QstGrounding(512, 8)
+    m.load_state_dict(sub_sd(sd, "quest_grounding"))
+    m = m.to(dev()).eval()
+    m.precision = prec
+    head = torch.nn.Linear(512, 42)
+    head.load_state_dict(sub_sd(sd, "head"))
+    head = head.to(dev())
+    g = torch.Generator().manual_seed(21)
+    for B, lens in ((5, (1,)), (3, (3,)), (4, (2, 5)), (2, (60, 1, 14)), (300, (7,))):
+        q = torch.randn(B, 512, generator=g)
+        data = [torch.randn(B, L, 512, generator=g) for L in lens]
+        ref = O.qst_grounding(sd, "quest_grounding", q, data)
+        arg = [d.to(dev()) for d in data] if len(data) > 1 else data[0].to(dev())
+        feat, logits = m(q.to(dev()), arg, head=head)
+        rl = O.linear(torch.relu(ref), sd["head.weight"], sd["head.bias"])
+        assert relerr(feat, ref) < TOL[prec] and relerr(logits, rl) < TOL[prec], (B, lens, relerr(feat, ref))
+
+
 def test_errors_are_loud(sd):
     M = _mods()
     m = M.AVQCrossAttn(512, 8).to(dev())
