@@ -229,7 +229,7 @@ typedef struct {
   int64_t* topk_inds;      /* optional [B,K] */
   float* topk_probs;       /* optional [B,K] renormalised */
   float* gauss_weight;     /* optional [B,K,T] peak-normalised */
-  int32_t t_split;         /* CTAs per sample (cluster size) 0 = auto */
+  int32_t t_split;         /* CTAs per sample (column slices of one cluster) 0 = auto */
 } QatGaussArgs;
 int qat_gauss_reduce_fwd(const QatGaussArgs* a);
 
