@@ -255,7 +255,11 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
   StageRange nvtx_(c, "qat.avq_cross_attn");
   const int D = a->D, H = a->H;
   QAT_REQUIRE(B >= 1 && T >= 1 && L >= 1 && H >= 1 && D == H * 64, "avq: need D == H*64 (D=%d H=%d)", D, H);
-  QAT_REQUIRE(T <= 128 && L <= 128, "avq: sequence lengths T=%d L=%d must be <= 128", T, L);
+  // sequences up to 128 tokens run on the register-resident mma.sync cores (fp16 plane pairs in bf16 mode); longer ones on the
+  // flash-style long-sequence core (attn_long.cuh), which reads fp32 q / k / v and has no weights output
+  QAT_REQUIRE(T <= 4096 && L <= 4096, "avq: sequence lengths T=%d L=%d must be <= 4096", T, L);
+  const bool longseq = T > 128 || L > 128;
+  QAT_REQUIRE(!(L > 128 && (attw_audio || attw_video)), "avq: attention weights (visualize) need L=%d <= 128 words", L);
   QAT_TRY(check_w(a->in_src, 7 * D, D, "avq.in_src", c.prec));
   QAT_TRY(check_w(a->in_words, 2 * D, D, "avq.in_words", c.prec));
   QAT_TRY(check_w(a->out_cat, D, 3 * D, "avq.out_cat", c.prec));
@@ -271,7 +275,8 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
   QAT_TRY(ensure_operand(c, Xw, BL, D, k_words));
   // S = in-projections of both modalities, rows [0,BT) audio, [BT,2BT) video; cols as in_src
   // bf16 mode: the in-projections leave as fp16 (hi, lo) plane pairs (same bytes as fp32), the form the attention cores eat
-  const bool pp = k_src == G_BF16X3 && k_words == G_BF16X3 && D % 8 == 0 && c.opt.v[OPT_ATTN_FP32_IN] != 1;
+  const bool pp = k_src == G_BF16X3 && k_words == G_BF16X3 && D % 8 == 0 && c.opt.v[OPT_ATTN_FP32_IN] != 1 && !longseq;
+  auto attn = [&](const AttnP& q) { return q.Lk > 128 ? attention_long(c, q) : attention(c, q); };
   Act S, KVw, O, X1, Hh, Y;
   if (pp) {
     QAT_TRY(act_alloc_pp(c, S, 2 * BT, 7 * D));
@@ -316,22 +321,22 @@ static int avq_core(const QatAvqArgs* a, int B, int T, int L, Ctx& c, Act Xa, Ac
     // the two outputs are separate tensors: run the two directions as separate launches
     AttnP pa = p;
     pa.nseq = B; pa.attw = attw_audio;
-    QAT_TRY(attention(c, pa));
+    QAT_TRY(attn(pa));
     AttnP pv = p;
     pv.nseq = B; pv.attw = attw_video; set_q(pv, BT * 7 * D); pv.o = O.rows(BT).cols(0);
-    QAT_TRY(attention(c, pv));
+    QAT_TRY(attn(pv));
   } else {
-    QAT_TRY(attention(c, p));
+    QAT_TRY(attn(p));
   }
   // slf: own keys/values
   p.attw = nullptr;
   set_q(p, D); set_kv(p, S, 2 * D, 3 * D); p.k_sn = p.q_sn; p.k_si = 7 * D; p.k_shift = 0; p.k_mod = 2 * B; p.Lk = T;
   p.o = O.cols(D);
-  QAT_TRY(attention(c, p));
+  QAT_TRY(attn(p));
   // crs: keys/values of the OTHER modality (direction 2 sees the original audio, modules.py:257-259)
   set_q(p, 4 * D); set_kv(p, S, 5 * D, 6 * D); p.k_shift = B; p.k_mod = 2 * B;
   p.o = O.cols(2 * D);
-  QAT_TRY(attention(c, p));
+  QAT_TRY(attn(p));
   // x1 = LN1(src + [o_qst|o_slf|o_crs] Wout^T + (b_qst+b_slf+b_crs))
   QAT_TRY(act_alloc(c, Y, 2 * BT, D, true, false));
   {
@@ -615,7 +620,7 @@ static int moe_front(Ctx& c, MoeMod* mods, int n, int B, int T) {
     MoeMod& M = mods[m];
     const QatMoeArgs* a = M.a;
     const int D = a->D, H = a->H, E = a->E, K = a->K;
-    QAT_REQUIRE(B >= 1 && T >= 1 && T <= 128 && D == H * 64, "temp_moe: need T<=128 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
+    QAT_REQUIRE(B >= 1 && T >= 1 && T <= 1024 && D == H * 64, "temp_moe: need T<=1024 and D==H*64 (T=%d D=%d H=%d)", T, D, H);
     QAT_REQUIRE(E >= 1 && E <= GAUSS_MAX_E && K >= 1 && K <= E, "temp_moe: need 1<=K<=E<=%d", GAUSS_MAX_E);
     QAT_REQUIRE((M.sub_a == nullptr) == (M.sub_v == nullptr), "temp_moe: sub_data needs both tensors or none");
     QAT_REQUIRE(m == 0 || (a->D == mods[0].a->D && a->H == mods[0].a->H && a->E == mods[0].a->E && a->K == mods[0].a->K),

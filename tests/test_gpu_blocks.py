@@ -57,6 +57,28 @@ def test_avq_cross_attn(sd, prec, B, T, L):
 
 
 @pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("B,T,L", [(2, 200, 77), (3, 129, 77), (1, 300, 150), (2, 60, 200)])
+def test_avq_cross_attn_long_sequences(sd, prec, B, T, L):
+    """modules.py:217-221 takes any sequence length: more than 128 frames / words run on the long-sequence attention core."""
+    M = _mods()
+    m = M.AVQCrossAttn(512, 8)
+    m.load_state_dict(sub_sd(sd, "crs_attn"))
+    m = m.to(dev()).eval()
+    m.precision = prec
+    g = torch.Generator().manual_seed(B * 1000 + T + L)
+    a, v, w = torch.randn(B, T, 512, generator=g), torch.randn(B, T, 512, generator=g), torch.randn(B, L, 512, generator=g)
+    ra, rv, (raw, rvw) = O.avq_cross_attn(sd, "crs_attn", a, v, w, visualize=True)
+    ga, gv = m(a.to(dev()), v.to(dev()), w.to(dev()))
+    assert relerr(ga, ra) < TOL[prec] and relerr(gv, rv) < TOL[prec]
+    if L <= 128:
+        ga2, gv2, (gaw, gvw) = m(a.to(dev()), v.to(dev()), w.to(dev()), visualize=True)
+        assert relerr(ga2, ra) < TOL[prec] and relerr(gaw, raw) < TOL[prec] and relerr(gvw, rvw) < TOL[prec]
+    else:
+        with pytest.raises(RuntimeError, match="visualize"):
+            m(a.to(dev()), v.to(dev()), w.to(dev()), visualize=True)
+
+
+@pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,T,P,chunk,fuse_proj", [(2, 60, 14, 0, True), (2, 60, 14, 50, True), (1, 9, 14, 4, False),
                                                   (3, 60, 14, 0, False), (2, 30, 5, 7, True), (40, 60, 14, 0, True)])
 def test_patch_selecter(sd, prec, B, T, P, chunk, fuse_proj):
@@ -88,7 +110,8 @@ def test_patch_selecter(sd, prec, B, T, P, chunk, fuse_proj):
 
 @pytest.mark.parametrize("prec", PRECS)
 @pytest.mark.parametrize("B,T,E,K,two", [(6, 60, 7, 7, False), (6, 60, 7, 7, True), (1, 60, 7, 7, True), (5, 60, 10, 5, True),
-                                         (4, 120, 14, 14, True), (37, 60, 7, 7, True), (70, 60, 7, 3, False)])
+                                         (4, 120, 14, 14, True), (37, 60, 7, 7, True), (70, 60, 7, 3, False), (3, 200, 7, 7, True),
+                                         (2, 20, 7, 4, False)])
 def test_temp_moe(prec, B, T, E, K, two):
     M = _mods()
     sdm = synth.make_state_dict(720 + E, num_experts=E, text_tower=False)
@@ -176,6 +199,6 @@ def test_errors_are_loud(sd):
         m(x.transpose(0, 1).contiguous().transpose(0, 1), x, x)
     with pytest.raises(RuntimeError, match="float32"):
         m(x.half(), x, x)
-    long = torch.randn(1, 200, 512, device=dev())
-    with pytest.raises(RuntimeError, match="<= 128"):
+    long = torch.randn(1, 5000, 512, device=dev())
+    with pytest.raises(RuntimeError, match="<= 4096"):
         m(long, long, x[:1])

@@ -167,6 +167,21 @@ def test_stress_config_at_its_own_batch(prec):
     assert out.argmax(1).cpu().tolist() == g["argmax"].tolist()
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+@pytest.mark.parametrize("B,T", [(3, 150), (2, 40)])
+def test_forward_any_frame_count_matches_oracle(prec, B, T):
+    """net.py:106-144 is length-agnostic in T (modules.py:217-221, 562-578): frame counts past the 128-token attention cores
+    (and short ones off the fused expert epilogue's tile) are compared with the oracle on the same batch."""
+    sd = synth.make_state_dict(713, num_experts=7)
+    model = build_model(sd, 7, 7, prec)
+    batch = synth.make_batch(17 + T, B, T)
+    with torch.no_grad():
+        ref = O.qa_tiger_forward(sd, batch, K=7, E=7)
+        out = model({k: v.to(dev()) for k, v in batch.items()})["out"]
+    assert relerr(out, ref) < TOL[prec]
+    assert out.argmax(1).cpu().tolist() == ref.argmax(1).tolist()
+
+
 def test_two_threads_two_streams_are_reentrant():
     """nn.DataParallel (trainutils.py:107-108) drives one Python thread per replica through the same library: two threads,
     each with its own stream, model replica and batch, run concurrently and must reproduce their single-threaded logits."""
