@@ -178,15 +178,28 @@ __global__ void __launch_bounds__(640) tome_match_kernel(const float* __restrict
 // discarded (merge.py:55), is not computed (the row-per-thread kernel above re-read B once per A row: 1 wavefront per 4
 // FMAs, and spent as long again normalising its A rows twice).  Every score is still ONE sequential FMA chain over the
 // channel index and the winners are compared in ascending j, so the indices are bit-identical to the reference's.
+//
+// Round 2 (ncu stall samples of the first form at t = 577: 20 % of the samples in the normalisation -- thread-per-row 128-bit
+// global loads touch 32 lines per instruction --, 67 % in the score tiles with the FMA pipe 41 % active over the launch -- 18
+// warps sit 5 / 5 / 4 / 4 on the four schedulers --, 12 % in the rank / index lists with half the warps idle):
+//   * the raw rows arrive by 16-byte cp.async copies (consecutive threads = consecutive 16 bytes of the frame) and are
+//     normalised in place, thread per row, two passes over shared memory -- no 64-register row copy;
+//   * each warp walks a contiguous range of 8-column blocks; the segment count is the one whose busiest scheduler (warp w
+//     issues on scheduler w % 4) walks the fewest blocks, up to 24 warps;
+//   * ranks are counted by all threads (NT / ta threads per row, integer atomics: order-free), the ascending list of the
+//     unmerged tokens (class-token form, merge.py:66-68) by a ballot prefix sum instead of a loop per token.
+// Measured: the 22 match launches of the 577 -> 14 chain 2.41 -> 2.30 ms per 592 frames (step 0: 247 -> 220-239 us); the samples
+// overstated what the side phases cost on the critical path.
 constexpr int TM_LD = 68;
+constexpr int TM_NT_MAX = 768;
 
 template <int C, int R>
-__global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __restrict__ metric, int t, int r, int class_token, int nseg,
-                                                               int seg_len, int* __restrict__ unm_idx, int* __restrict__ src_idx,
-                                                               int* __restrict__ dst_idx) {
+__global__ void __launch_bounds__(TM_NT_MAX) tome_match_tiled_kernel(const float* __restrict__ metric, int t, int r, int class_token, int nseg,
+                                                                     int ncb, int* __restrict__ unm_idx, int* __restrict__ src_idx,
+                                                                     int* __restrict__ dst_idx) {
   static_assert(C == 64, "metric channels");
   extern __shared__ __align__(16) float smem[];
-  const int ta = (t + 1) / 2, tb = t / 2, tb_pad = nseg * seg_len;
+  const int ta = (t + 1) / 2, tb = t / 2, tb_pad = ncb * 8;
   float* An = smem;                                          // [ta][TM_LD] normalised even tokens
   float* Bn = An + (size_t)ta * TM_LD;                       // [tb_pad][TM_LD] normalised odd tokens (+ zero rows)
   float* segmax = Bn + (size_t)tb_pad * TM_LD;               // [nseg][ta]
@@ -194,40 +207,52 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
   float* nmax = reinterpret_cast<float*>(segidx + (size_t)nseg * ta);   // [ta]
   int* nidx = reinterpret_cast<int*>(nmax + ta);             // [ta]
   int* rank = nidx + ta;                                     // [ta]
+  int* wcnt = rank + ta;                                     // [32] per-warp counts of the unmerged-token prefix sum
   const int n = blockIdx.x, tid = threadIdx.x, NT = blockDim.x;
   const float* mf = metric + (size_t)n * t * C;
 
-  // ---- phase 1: row / ||row|| (merge.py:50) in the reference's summation order ----
-  for (int row = tid; row < t + (tb_pad - tb); row += NT) {
-    if (row >= t) {                                          // zero rows behind B: read by the last tile, never compared
-      float4* z = reinterpret_cast<float4*>(Bn + (size_t)(tb + row - t) * TM_LD);
-#pragma unroll
-      for (int d = 0; d < C / 4; ++d) z[d] = make_float4(0.f, 0.f, 0.f, 0.f);
-      continue;
-    }
-    float o[C];
-    const float* src = mf + (size_t)row * C;
-#pragma unroll
-    for (int d = 0; d < C; d += 4) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(src + d));
-      o[d] = v.x; o[d + 1] = v.y; o[d + 2] = v.z; o[d + 3] = v.w;
-    }
+  // ---- phase 0: the frame's raw rows -> shared memory, 16 bytes per copy, consecutive threads = consecutive addresses ----
+  for (int q = tid; q < t * (C / 4); q += NT) {
+    const int row = q / (C / 4), d4 = q - row * (C / 4);
+    float* dst = ((row & 1) ? Bn : An) + (size_t)(row >> 1) * TM_LD + d4 * 4;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(mf + (size_t)q * 4) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  for (int q = tid; q < (tb_pad - tb) * (C / 4); q += NT)    // zero rows behind B: read by the last tile, never compared
+    reinterpret_cast<float4*>(Bn + (size_t)(tb + q / (C / 4)) * TM_LD)[q % (C / 4)] = make_float4(0.f, 0.f, 0.f, 0.f);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- phase 1: row / ||row|| (merge.py:50) in the reference's summation order, in place; threads [0, ta) own the A rows,
+  //      [ta, t) the B rows (a warp's rows are consecutive in one matrix: conflict-free 128-bit accesses) ----
+  for (int i = tid; i < t; i += NT) {
+    float4* row = reinterpret_cast<float4*>(i < ta ? An + (size_t)i * TM_LD : Bn + (size_t)(i - ta) * TM_LD);
     float acc[8];
 #pragma unroll
     for (int l = 0; l < 8; ++l) acc[l] = 0.f;
-#pragma unroll
-    for (int d = 0; d < C; d += 8)
-#pragma unroll
-      for (int l = 0; l < 8; ++l) acc[l] = __fadd_rn(acc[l], __fmul_rn(o[d + l], o[d + l]));
+#pragma unroll 4
+    for (int d = 0; d < C / 4; d += 2) {
+      const float4 v0 = row[d], v1 = row[d + 1];
+      acc[0] = __fadd_rn(acc[0], __fmul_rn(v0.x, v0.x));
+      acc[1] = __fadd_rn(acc[1], __fmul_rn(v0.y, v0.y));
+      acc[2] = __fadd_rn(acc[2], __fmul_rn(v0.z, v0.z));
+      acc[3] = __fadd_rn(acc[3], __fmul_rn(v0.w, v0.w));
+      acc[4] = __fadd_rn(acc[4], __fmul_rn(v1.x, v1.x));
+      acc[5] = __fadd_rn(acc[5], __fmul_rn(v1.y, v1.y));
+      acc[6] = __fadd_rn(acc[6], __fmul_rn(v1.z, v1.z));
+      acc[7] = __fadd_rn(acc[7], __fmul_rn(v1.w, v1.w));
+    }
     float sq = acc[0];
 #pragma unroll
     for (int l = 1; l < 8; ++l) sq = __fadd_rn(sq, acc[l]);
     const float nrm = __fsqrt_rn(sq);
-    float4* dst = reinterpret_cast<float4*>(((row & 1) ? Bn : An) + (size_t)(row >> 1) * TM_LD);
-#pragma unroll
-    for (int d = 0; d < C; d += 4)
-      dst[d / 4] = make_float4(__fdiv_rn(o[d], nrm), __fdiv_rn(o[d + 1], nrm), __fdiv_rn(o[d + 2], nrm), __fdiv_rn(o[d + 3], nrm));
+#pragma unroll 4
+    for (int d = 0; d < C / 4; ++d) {
+      const float4 v = row[d];
+      row[d] = make_float4(__fdiv_rn(v.x, nrm), __fdiv_rn(v.y, nrm), __fdiv_rn(v.z, nrm), __fdiv_rn(v.w, nrm));
+    }
   }
+  for (int i = tid; i < ta; i += NT) rank[i] = 0;
   __syncthreads();
 
   // ---- phase 2: scores = a . b (merge.py:52) and the running (max, first argmax) of every A row within a B segment ----
@@ -247,9 +272,10 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
       }
       float best[R];
       int bidx[R];
+      const int j_beg = (int)((long long)seg * ncb / nseg) * 8, j_end = (int)((long long)(seg + 1) * ncb / nseg) * 8;
 #pragma unroll
-      for (int i = 0; i < R; ++i) { best[i] = -INFINITY; bidx[i] = seg * seg_len; }
-      for (int j0 = seg * seg_len; j0 < (seg + 1) * seg_len; j0 += 8) {
+      for (int i = 0; i < R; ++i) { best[i] = -INFINITY; bidx[i] = j_beg; }
+      for (int j0 = j_beg; j0 < j_end; j0 += 8) {
         float sc[R][8];
 #pragma unroll
         for (int i = 0; i < R; ++i)
@@ -305,32 +331,59 @@ __global__ void __launch_bounds__(640) tome_match_tiled_kernel(const float* __re
     nidx[i] = i0;
   }
   __syncthreads();
-  // descending, index-stable rank by counting
-  for (int i = tid; i < ta; i += NT) {
-    const float v = nmax[i];
-    int rk = 0;
-    for (int k = 0; k < ta; ++k) {
-      float u = nmax[k];
-      rk += (u > v) || (u == v && k < i);
+  // descending, index-stable rank by counting; `parts` threads share a row's comparisons (integer atomics: order-free)
+  {
+    const int parts = NT / ta > 0 ? NT / ta : 1;
+    for (int w = tid; w < ta * parts; w += NT) {
+      const int part = w / ta, i = w - part * ta;
+      const int k0 = (int)((long long)part * ta / parts), k1 = (int)((long long)(part + 1) * ta / parts);
+      const float v = nmax[i];
+      int rk = 0;
+      for (int k = k0; k < k1; ++k) {
+        const float u = nmax[k];
+        rk += (u > v) || (u == v && k < i);
+      }
+      if (parts > 1) atomicAdd(&rank[i], rk);
+      else rank[i] = rk;
     }
-    rank[i] = rk;
   }
   __syncthreads();
   const int n_unm = ta - r;
   int* unm = unm_idx + (size_t)n * n_unm;
   int* src = src_idx + (size_t)n * r;
   int* dst = dst_idx + (size_t)n * r;
-  for (int i = tid; i < ta; i += NT) {
-    const int rk = rank[i];
-    if (rk < r) {
-      src[rk] = i;
-      dst[rk] = nidx[i];
-    } else if (!(class_token & 1)) {
-      unm[rk - r] = i;                                         // stays in sorted-score order
-    } else {
-      int pos = 0;                                             // merge.py:66-68: ascending token order
-      for (int k = 0; k < i; ++k) pos += rank[k] >= r;
-      unm[pos] = i;
+  if (!(class_token & 1)) {
+    for (int i = tid; i < ta; i += NT) {
+      const int rk = rank[i];
+      if (rk < r) {
+        src[rk] = i;
+        dst[rk] = nidx[i];
+      } else {
+        unm[rk - r] = i;                                       // stays in sorted-score order
+      }
+    }
+  } else {
+    // merge.py:66-68: the unmerged tokens in ascending token order = an exclusive prefix count of (rank >= r)
+    const int warp = tid >> 5, lane = tid & 31, nw = NT >> 5;
+    int carry = 0;
+    for (int base = 0; base < ta; base += NT) {                // one round for ta <= NT
+      const int i = base + tid;
+      const int rk = i < ta ? rank[i] : 0;
+      const bool keep = i < ta && rk >= r;
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      if (lane == 0) wcnt[warp] = __popc(bal);
+      __syncthreads();
+      int pos = carry;
+      for (int w = 0; w < warp; ++w) pos += wcnt[w];
+      pos += __popc(bal & ((1u << lane) - 1u));
+      if (i < ta) {
+        if (keep) unm[pos] = i;
+        else { src[rk] = i; dst[rk] = nidx[i]; }
+      }
+      int tot = 0;
+      for (int w = 0; w < nw; ++w) tot += wcnt[w];
+      carry += tot;
+      __syncthreads();
     }
   }
 }
@@ -572,17 +625,31 @@ inline int tome_match(Ctx& c, const float* metric, int N, int t, int C, int r, i
     for (int cand = 3; cand >= 2; --cand)
       if ((rows + 32 * cand - 1) / (32 * cand) * cand < (rows + 32 * R - 1) / (32 * R) * R) R = cand;
     const int aw_n = rows > 0 ? (rows + 32 * R - 1) / (32 * R) : 1;
-    int nseg = 20 / aw_n;
-    if (nseg > (tb + 7) / 8) nseg = (tb + 7) / 8;
+    const int ncb = (tb + 7) / 8;                             // 8-column blocks of B
+    // segments: warps = aw_n * nseg <= 24; warp w issues on scheduler w % 4, so pick the count whose busiest scheduler walks
+    // the fewest 8-column blocks (ties: more warps, i.e. more latency hiding)
+    int nseg = 1;
+    {
+      int best_load = 1 << 30;
+      for (int cand = 1; cand * aw_n * 32 <= TM_NT_MAX && cand <= ncb; ++cand) {
+        int load[4] = {0, 0, 0, 0};
+        for (int sg = 0; sg < cand; ++sg) {
+          const int nb = (int)((long long)(sg + 1) * ncb / cand) - (int)((long long)sg * ncb / cand);
+          for (int aw = 0; aw < aw_n; ++aw) load[(sg * aw_n + aw) & 3] += nb;
+        }
+        int mx = load[0];
+        for (int q = 1; q < 4; ++q) mx = load[q] > mx ? load[q] : mx;
+        if (mx <= best_load) { best_load = mx; nseg = cand; }
+      }
+    }
+    if (nseg > ncb) nseg = ncb;
     if (nseg < 1) nseg = 1;
-    const int seg_len = (((tb + nseg - 1) / nseg) + 7) / 8 * 8;
-    nseg = (tb + seg_len - 1) / seg_len;
-    const size_t smem_t = ((size_t)(ta + nseg * seg_len) * TM_LD + (size_t)2 * nseg * ta + (size_t)3 * ta) * 4 + 16;
-    if (rows > 0 && aw_n * nseg <= 20 && smem_t <= 220 * 1024 && c.opt.v[OPT_TOME_MATCH_ROWS] != 1) {
+    const size_t smem_t = ((size_t)(ta + ncb * 8) * TM_LD + (size_t)2 * nseg * ta + (size_t)3 * ta + 32) * 4 + 16;
+    if (rows > 0 && aw_n * nseg * 32 <= TM_NT_MAX && smem_t <= 220 * 1024 && c.opt.v[OPT_TOME_MATCH_ROWS] != 1) {
       if (c.dry || N == 0) return QAT_OK;
       auto kern = R == 4 ? tome_match_tiled_kernel<64, 4> : (R == 3 ? tome_match_tiled_kernel<64, 3> : tome_match_tiled_kernel<64, 2>);
       if (smem_t > 48 * 1024) QAT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_t));
-      kern<<<N, 32 * aw_n * nseg, smem_t, c.stream>>>(metric, t, r, class_token, nseg, seg_len, unm, src, dst);
+      kern<<<N, 32 * aw_n * nseg, smem_t, c.stream>>>(metric, t, r, class_token, nseg, ncb, unm, src, dst);
       return check_launch("tome_match_tiled_kernel");
     }
   }
