@@ -36,8 +36,8 @@ T, P, E, K_TOP = 60, 14, 7, 7
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=256)
@@ -343,6 +343,23 @@ def run_tome(args):
                "note": "bound by the host link: 2.36 MB of fp32 tokens per frame in, 57 KB out"}
     except Exception as e_:   # noqa: BLE001
         sys.stderr.write(f"[bench] ToMe e2e leg skipped: {e_}\n")
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference ToMe chain (oracle port, tests' checker) on the box's host cores, N = 60 frames
+        try:
+            import os
+            import time as _time
+            from oracle import tome_oracle as TO
+            torch.set_num_threads(os.cpu_count() or 1)
+            xc = x[:60].cpu()
+            TO.chain(xc[:4])
+            t0 = _time.perf_counter()
+            TO.chain(xc)
+            dt = _time.perf_counter() - t0
+            cpu_base = {"value": 60 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+                        "sample": "oracle/tome_oracle.chain over 60 frames (one video of configs[2]), 23 steps, after a 4-frame warm-up"}
+        except Exception as e_:   # noqa: BLE001
+            sys.stderr.write(f"[bench] ToMe cpu baseline skipped: {e_}\n")
     if rank == 0:
         tmax = float(t[0]) * 1e-3
         fps = n_frames * args.steps / tmax
@@ -359,7 +376,7 @@ def run_tome(args):
                 "roofline": {"bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s", "frac": ach / hbm_peak, "traffic": None,
                              "kernel": "tome chain (tome_match_tiled_kernel + tome_merge_wavg_kernel x 23 steps)",
                              "note": "per GPU: stepwise algorithmic traffic 56.49 MB per frame (SURVEY 8d) over the whole chain time"},
-                "e2e": e2e, "peaks_source": peak_src}
+                "e2e": e2e, "cpu_baseline": cpu_base, "peaks_source": peak_src}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
