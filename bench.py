@@ -533,7 +533,7 @@ def run_ours(args):
             if copies:
                 cur.wait_stream(copy_stream)
 
-        e2e_steps = max(4, min(args.steps, 32))     # the pipeline drains once: the last step's compute is not hidden by a copy
+        e2e_steps = max(4, min(args.steps, 64))     # the pipeline drains once: the last step's compute is not hidden by a copy
         e2e_run(2)
         torch.cuda.synchronize()
         if world > 1:
