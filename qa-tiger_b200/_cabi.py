@@ -270,14 +270,22 @@ def stream_ptr(device) -> int:
 
 
 # ---- weights ------------------------------------------------------------------------------------
+def aligned(t: torch.Tensor) -> torch.Tensor:
+    """A detached contiguous fp32 tensor on a 16-byte boundary (the kernels read weights with 128-bit loads / TMA).  Module
+    parameters normally are; nn.DataParallel's replicas are views into coalesced broadcast buffers and need not be -- those are
+    copied (the copy lives in the prepared-weight cache, keyed on the replica's data_ptr / version)."""
+    t = t.detach().contiguous().float()
+    return t if t.data_ptr() % 16 == 0 else t.clone()
+
+
 class Lin:
     """A prepared nn.Linear operand: fp32 weight (+ bf16 hi/lo split when prec == bf16) and bias.
     Holds the tensors alive; `.c` is the C struct."""
 
     def __init__(self, w: torch.Tensor, b: Optional[torch.Tensor], prec: int, f16: bool = False):
-        w = w.detach().contiguous().float()
+        w = aligned(w)
         self.w = w
-        self.b = None if b is None else b.detach().contiguous().float()
+        self.b = None if b is None else aligned(b)
         self.hi = self.lo = self.h = None
         if prec == PREC_BF16:
             self.hi = w.to(torch.bfloat16)
@@ -289,8 +297,8 @@ class Lin:
 
 class LN:
     def __init__(self, m: torch.nn.LayerNorm):
-        self.g = m.weight.detach().contiguous().float()
-        self.b = m.bias.detach().contiguous().float()
+        self.g = aligned(m.weight)
+        self.b = aligned(m.bias)
         self.c = LayerNormW(ptr(self.g), ptr(self.b))
 
 
@@ -428,15 +436,17 @@ def gemm_attn(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, P: int, H: i
 
 
 # ---- workspace ----------------------------------------------------------------------------------
-_ws: Dict[Tuple[int, int], torch.Tensor] = {}
+_ws: Dict[Tuple[int, int, int], torch.Tensor] = {}
 _ws_retired: list = []          # superseded buffers that a captured CUDA graph may still point into: never released
 _ws_lock = threading.Lock()     # nn.DataParallel drives one Python thread per GPU through this module
 
 
 def workspace(device: torch.device, nbytes: int) -> torch.Tensor:
-    """Per (device, stream) grow-only scratch buffer owned by torch's caching allocator.  A buffer that is outgrown while a
-    stream capture is (or may have been) using it is retired, not freed: a captured graph has its address baked in."""
-    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device))
+    """Per (device, stream, host thread) grow-only scratch buffer owned by torch's caching allocator.  A buffer that is outgrown
+    while a stream capture is (or may have been) using it is retired, not freed: a captured graph has its address baked in.
+    The thread is part of the key because two host threads may legally issue on ONE stream (nn.DataParallel with replicas on
+    the same device, the legacy default stream): their calls interleave in stream order and must not share scratch memory."""
+    key = (device.index if device.index is not None else torch.cuda.current_device(), stream_ptr(device), threading.get_ident())
     with _ws_lock:
         buf = _ws.get(key)
         if buf is None or buf.numel() < nbytes:

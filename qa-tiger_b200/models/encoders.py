@@ -172,8 +172,8 @@ class CLIP_TEncoder(nn.Module):
                 setattr(arr[i], k, v.c)
         w = dict(layers=arr, hold=hold, ln_final=cabi.LN(self.ln_final),
                  text_projection=cabi.Lin(self.text_projection.t(), None, cabi.PREC_FP32),
-                 tok=self.token_embedding.weight.detach().contiguous().float(),
-                 pos=self.positional_embedding.detach().contiguous().float())
+                 tok=cabi.aligned(self.token_embedding.weight),
+                 pos=cabi.aligned(self.positional_embedding))
         self.__dict__["_native"] = (key, w)
         return w
 

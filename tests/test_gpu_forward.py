@@ -215,6 +215,29 @@ def test_two_threads_two_streams_are_reentrant():
         assert torch.equal(got[i], want[i])
 
 
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_nn_dataparallel_wrapper(prec):
+    """trainutils.py:107-108 wraps the model in nn.DataParallel when it is not distributed: replicate() + one host thread per
+    replica.  The logits depend on the LOCAL batch, so the wrapped forward equals the plain model run on each
+    scattered chunk.  On a one-GPU box both replicas sit on device 0 (two host threads on one stream); with two or more
+    GPUs the same check also runs across devices 0 and 1."""
+    sd = synth.make_state_dict(713, num_experts=7)
+    model = build_model(sd, 7, 7, prec)
+    batch = synth.make_batch(23, 8, 60)
+    data = {k: v.to(dev()) for k, v in batch.items()}
+    with torch.no_grad():
+        halves = [model({k: v[i * 4:(i + 1) * 4].contiguous() for k, v in data.items()})["out"] for i in range(2)]
+    want = torch.cat(halves)
+    id_sets = [[0, 0]] + ([[0, 1]] if torch.cuda.device_count() >= 2 else [])
+    for ids in id_sets:
+        dp = torch.nn.DataParallel(model, device_ids=ids, output_device=0)
+        with torch.no_grad():
+            got = dp(data)["out"]
+        torch.cuda.synchronize()
+        assert got.shape == (8, 42)
+        assert torch.equal(got, want), f"DataParallel over devices {ids} differs from the per-chunk forwards"
+
+
 def test_data_writes_need_invalidate_prepared():
     """ADVICE: derived weights are cached on (data_ptr, _version); load_state_dict / .to() invalidate them automatically,
     writes through `.data` need qa_tiger_b200._cabi.invalidate_prepared()."""
