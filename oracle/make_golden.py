@@ -66,6 +66,7 @@ FWD_CASES = {
     "fwd_stress": (4, 120, 14, 14, 715, 5),   # BASELINE config 5 shape (T=120, E=K=14)
     "fwd_b256": (256, 60, 7, 7, 713, 1234),   # BASELINE config 2 batch (logits + ranks only)
     "fwd_stress_b128": (128, 120, 14, 14, 715, 6),   # BASELINE config 5 at its own per-GPU batch (logits + ranks only)
+    "fwd_t150": (9, 150, 7, 7, 713, 7),       # more frames than one 128-token attention tile (logits + ranks only)
 }
 
 

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["fwd_b8", "fwd_b3", "fwd_b1", "fwd_k5", "fwd_stress", "fwd_b256"])
+@pytest.mark.parametrize("name", ["fwd_b8", "fwd_b3", "fwd_b1", "fwd_k5", "fwd_stress", "fwd_b256", "fwd_t150"])
 def test_forward_matches_reference_golden(name, prec):
     g = golden(name)
     B, T, E, K, wseed, bseed = FWD_CASES[name]

@@ -37,6 +37,21 @@ def test_forward_matches_reference(name):
         assert relerr(aux[k], g[k]) < 2e-5, k
 
 
+@pytest.mark.parametrize("name", ["fwd_t150"])
+def test_forward_matches_reference_logits_only(name):
+    """Goldens that hold logits + router ranks only (B > 8): here the frame count past one 128-token attention tile."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    B, T, E, K, wseed, bseed = FWD_CASES[name]
+    sd = synth.make_state_dict(wseed, num_experts=E)
+    batch = synth.make_batch(bseed, B, T)
+    with torch.no_grad():
+        out, aux = O.qa_tiger_forward(sd, batch, K=K, E=E, with_aux=True)
+    assert relerr(out, g["out"]) < 2e-5
+    assert out.argmax(1).tolist() == g["argmax"].tolist()
+    for agg, key in (("at_aggregator", "at"), ("vt_aggregator", "vt")):
+        assert aux[key]["topk_inds"].tolist() == g[agg + ".topk_inds"].astype(np.int64).tolist()
+
+
 def test_batch_coupling_quirk_is_reproduced():
     """sample 0 alone differs from sample 0 inside a batch."""
     g = np.load(os.path.join(GOLDEN, "fwd_b3.npz"))
