@@ -392,7 +392,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
 
 template <typename VecT, int VEC, int SLOTS>
 __global__ void __launch_bounds__(GAUSS_NT) gauss_reduce_kernel(const __grid_constant__ CUtensorMap mX, GaussP p) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  extern __shared__ __align__(128) unsigned char gauss_smem[];
   const int T = p.T, E = p.E, C = p.C;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = p.split, TG = p.tg, ring = p.ring;
@@ -405,8 +405,8 @@ __global__ void __launch_bounds__(GAUSS_NT) gauss_reduce_kernel(const __grid_con
   // ---- shared layout: ring | barriers | prologue arrays ----------------------------------------------
   const uint32_t stage_bytes = (uint32_t)TG * nloc * sizeof(VecT);                              // bytes one box load delivers
   const uint32_t svec = (stage_bytes + 127u) / 128u * 128u / (uint32_t)sizeof(VecT);            // stage pitch (TMA: 128-byte aligned)
-  VecT* s_ring = reinterpret_cast<VecT*>(smem_raw);                                             // [ring][TG][E][cw]
-  uint64_t* s_full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ring * svec * sizeof(VecT)); // [ring]
+  VecT* s_ring = reinterpret_cast<VecT*>(gauss_smem);                                             // [ring][TG][E][cw]
+  uint64_t* s_full = reinterpret_cast<uint64_t*>(gauss_smem + (size_t)ring * svec * sizeof(VecT)); // [ring]
   uint64_t* s_empty = s_full + ring;                                                            // [ring]
   const int csz = p.csz, cr = csz > 1 ? s : 0;   // CTAs that share one prologue (the sample's cluster), rank among them
   const GaussCl sm = gauss_cl_carve(reinterpret_cast<unsigned char*>(s_empty + ring), T, E, p.K, csz);
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(GAUSS_NT) gauss_reduce_kernel(const __grid_con
   } else {
     // out[b, c] = sum over the experts in index order: the per-expert sums meet in shared memory (the ring is free: every
     // stage has been consumed, the producer has no load outstanding)
-    float* s_part = reinterpret_cast<float*>(smem_raw);   // [E][cw*VEC]
+    float* s_part = reinterpret_cast<float*>(gauss_smem);   // [E][cw*VEC]
     asm volatile("bar.sync 1, %0;" ::"n"(GAUSS_NC) : "memory");
 #pragma unroll
     for (int k = 0; k < SLOTS; ++k) {

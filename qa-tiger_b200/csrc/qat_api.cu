@@ -86,19 +86,6 @@ static int act_alloc_for(Ctx& c, Act& a, long long rows, int ld, GemmKind consum
   if (consumer == G_F16) return act_alloc_h(c, a, rows, ld);
   return act_alloc(c, a, rows, ld, !reads_planes(consumer), reads_planes(consumer));
 }
-// module input -> the operand view an engine reads (conversion pass only when the engine does not read fp32)
-static int operand_of(Ctx& c, const float* x, long long rows, int cols, GemmKind k, Act& out) {
-  out = Act();
-  out.f = const_cast<float*>(x);
-  out.ld = cols;
-  if (k == G_BF16X3 || k == G_F16) {
-    Act pl;
-    QAT_TRY(act_alloc_for(c, pl, rows, cols, k));
-    QAT_TRY(add_rows(c, x, cols, nullptr, 0, pl, rows, cols));
-    out.hi = pl.hi; out.lo = pl.lo; out.h = pl.h;
-  }
-  return QAT_OK;
-}
 
 // make sure `x` (which always carries its fp32 view) also has the storage planes engine `k` reads; a conversion pass runs
 // only when the producer did not already emit them (inside qat_forward_fwd the producers do)
@@ -143,17 +130,6 @@ static Act act_of(float* p, int ld) {
 }
 static Act act_of(const float* p, int ld) { return act_of(const_cast<float*>(p), ld); }
 
-// an input tensor that a bf16x3 GEMM wants to read: make the planes (and keep the fp32 view)
-static int planes_of(Ctx& c, const float* x, long long rows, int cols, bool want, Act& out) {
-  out = act_of(x, cols);
-  if (!want) return QAT_OK;
-  Act pl;
-  QAT_TRY(act_alloc(c, pl, rows, cols, false, true));
-  QAT_TRY(add_rows(c, x, cols, nullptr, 0, pl, rows, cols));
-  out.hi = pl.hi;
-  out.lo = pl.lo;
-  return QAT_OK;
-}
 
 static int ln(Ctx& c, const float* x0, long long ld0, const float* x1, long long ld1, const float* x2, long long ld2, float c01,
               const QatLayerNormW& w, Act out, long long rows, int D, const float* post = nullptr, long long ldp = 0, float eps = 1e-5f) {
