@@ -117,6 +117,19 @@ def peaks():
 
 
 # ---------------------------------------------------------------------------------------------------
+def cpu_model() -> str:
+    """Model name of the host CPU (printed next to the core count of every CPU baseline)."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    import platform
+    return platform.processor() or platform.machine()
+
+
 def cpu_reference_forward(B: int, reps: int, warm: int, with_text: bool):
     """The reference algorithm's CPU port (oracle/qat_oracle.py, pinned against the real reference by
     tests/golden/) on the host cores.  Returns (q/s, threads, seconds per forward)."""
@@ -161,7 +174,7 @@ def run_reference(args):
                    "sample": f"B={B} questions per step (the faster of configs[0]'s B=8 and B=32: "
                              + ", ".join(f"B={b_}: {q_:.1f} q/s" for q_, b_, _ in cand) + ")",
                    "text_tower": "excluded (precomputed), as in the GPU arm's `value`"},
-        "cpu_baseline": {"value": qps, "unit": "questions/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": qps, "unit": "questions/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
                          "sample": f"forwards of B={B}, T=60 ({args.steps} timed at B=8, up to 8 at B=32, median) after "
                                    f"{min(args.warmup, 3)} warm-up; oracle/qat_oracle.py "
                                    "(CPU restatement pinned to reference-generated goldens; the reference itself is "
@@ -355,7 +368,7 @@ def run_tome(args):
             t0 = _time.perf_counter()
             TO.chain(xc)
             dt = _time.perf_counter() - t0
-            cpu_base = {"value": 60 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "kind": "port",
+            cpu_base = {"value": 60 / dt, "unit": "frames/s", "cores": torch.get_num_threads(), "cpu": cpu_model(), "kind": "port",
                         "sample": "oracle/tome_oracle.chain over 60 frames (one video of configs[2]), 23 steps, after a 4-frame warm-up"}
         except Exception as e_:   # noqa: BLE001
             sys.stderr.write(f"[bench] ToMe cpu baseline skipped: {e_}\n")
@@ -822,7 +835,7 @@ def run_ours(args):
                 os.sched_setaffinity(0, prev_affinity)
             qps_cpu, cores, sec = cpu_reference_forward(8, 5, 2, with_text=False)
             qps_cpu_t, _, sec_t = cpu_reference_forward(8, 3, 1, with_text=True)
-            line["cpu_baseline"] = {"value": qps_cpu, "unit": "questions/s", "cores": cores, "kind": "port",
+            line["cpu_baseline"] = {"value": qps_cpu, "unit": "questions/s", "cores": cores, "cpu": cpu_model(), "kind": "port",
                                     "sample": "5 forwards of B=8,T=60 (configs[0]) after 2 warm-up, hot path only; "
                                               f"with the text tower: {qps_cpu_t:.1f} questions/s",
                                     "with_text_tower": qps_cpu_t}
