@@ -40,3 +40,18 @@ def test_reference_arm_prints_one_json_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["gpu_launches"] == 0
+
+
+def test_tome_frame_shards_are_contiguous_and_cover_every_frame():
+    """configs[2] shards by frame, no exchange -- rank r owns [r*ceil(N/W), (r+1)*ceil(N/W)), in order, no overlap, no
+    padding; ranks beyond the frames own nothing."""
+    from qa_tiger_b200.tome.merge import frame_shard
+    for n in (0, 1, 7, 592, 15360, 15361):
+        for world in (1, 2, 3, 8, 16):
+            shards = [frame_shard(n, r, world) for r in range(world)]
+            covered = [f for lo, hi in shards for f in range(lo, hi)]
+            assert covered == list(range(n)), (n, world)
+            sizes = [hi - lo for lo, hi in shards]
+            assert max(sizes) - min(s for s in sizes if s or n < world) <= -(-n // world)
+            assert all(lo <= hi for lo, hi in shards)
+    assert frame_shard(15360, 3, 8) == (5760, 7680)
